@@ -1,0 +1,350 @@
+// glue.cu -- decoder-step glue: LayerNorm, token+position embedding, fp16 logits + argmax (SIMT path).
+//
+// These are TensorRT-native layers in the reference graph (T/tensorrt_llm/models/whisper/model.py:74-118,257-292)
+// and torch ops in the oracle (T/examples/whisper/torch_model.py:25-27,205-218).  They are the "next" row 1 of
+// SURVEY.md section 8f and are needed to measure whole decoder steps.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace b200
+{
+
+// y = (x - mean) * rsqrt(var + eps) * gamma + beta, statistics in fp32 (torch_model.py:25-27 casts to float).
+// one CTA (128 threads) per row; cols % 8 == 0; row cached in registers (cols <= 8192).
+template <int VEC_PER_THREAD>
+__global__ void __launch_bounds__(128) layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+    const __half* __restrict__ beta, __half* __restrict__ y, int cols, float eps)
+{
+    grid_dep_wait();
+    const int row = blockIdx.x;
+    const __half* xr = x + (size_t) row * cols;
+    __half* yr = y + (size_t) row * cols;
+    const int nvec = cols / 8;
+    float v[VEC_PER_THREAD][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_PER_THREAD; ++i)
+    {
+        const int idx = threadIdx.x + i * 128;
+        if (idx < nvec)
+        {
+            const uint4 u = *reinterpret_cast<const uint4*>(xr + idx * 8);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const float2 f = __half22float2(h[j]);
+                v[i][2 * j] = f.x;
+                v[i][2 * j + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+    }
+    __shared__ float red[4];
+    __shared__ float bc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0)
+        red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        bc = (red[0] + red[1] + red[2] + red[3]) / (float) cols;
+    __syncthreads();
+    const float mean = bc;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_PER_THREAD; ++i)
+    {
+        const int idx = threadIdx.x + i * 128;
+        if (idx < nvec)
+        {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                const float d = v[i][j] - mean;
+                sq += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    __syncthreads();
+    if (lane == 0)
+        red[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        bc = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float) cols + eps);
+    __syncthreads();
+    const float rstd = bc;
+#pragma unroll
+    for (int i = 0; i < VEC_PER_THREAD; ++i)
+    {
+        const int idx = threadIdx.x + i * 128;
+        if (idx < nvec)
+        {
+            const uint4 g = *reinterpret_cast<const uint4*>(gamma + idx * 8);
+            const uint4 bt = *reinterpret_cast<const uint4*>(beta + idx * 8);
+            const __half2* gh = reinterpret_cast<const __half2*>(&g);
+            const __half2* bh = reinterpret_cast<const __half2*>(&bt);
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const float2 gf = __half22float2(gh[j]);
+                const float2 bf = __half22float2(bh[j]);
+                oh[j] = __floats2half2_rn((v[i][2 * j] - mean) * rstd * gf.x + bf.x, (v[i][2 * j + 1] - mean) * rstd * gf.y + bf.y);
+            }
+            *reinterpret_cast<uint4*>(yr + idx * 8) = o;
+        }
+    }
+}
+
+// out[r] = tok_emb[tokens[r]] + pos_emb[positions[r]]  (fp16 add, like torch_model.py:205-209 in fp16)
+__global__ void embed_kernel(const int* __restrict__ tokens, const int* __restrict__ positions,
+    const __half* __restrict__ tok_emb, const __half* __restrict__ pos_emb, __half* __restrict__ out, int cols, int vocab,
+    int n_ctx)
+{
+    grid_dep_wait();
+    const int r = blockIdx.x;
+    int tok = tokens[r];
+    int pos = positions[r];
+    tok = min(max(tok, 0), vocab - 1);
+    pos = min(max(pos, 0), n_ctx - 1);
+    const __half2* te = reinterpret_cast<const __half2*>(tok_emb + (size_t) tok * cols);
+    const __half2* pe = reinterpret_cast<const __half2*>(pos_emb + (size_t) pos * cols);
+    __half2* o = reinterpret_cast<__half2*>(out + (size_t) r * cols);
+    for (int i = threadIdx.x; i < cols / 2; i += blockDim.x)
+        o[i] = __hadd2(te[i], pe[i]);
+}
+
+// SIMT logits: one warp per vocabulary row, all `rows` activations (<= 16 per pass) staged in shared memory.
+// logits[r][v] = sum_k x[r][k] * emb[v][k], fp32 accumulation.
+constexpr int kLogitsRowsPerPass = 16;
+
+__global__ void __launch_bounds__(256) logits_simt_kernel(const __half* __restrict__ x, const __half* __restrict__ emb,
+    float* __restrict__ logits, int rows, int cols, int vocab, int row0)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __half* sx = reinterpret_cast<__half*>(s_raw); // [nr][cols]
+    grid_dep_wait();
+    const int nr = min(kLogitsRowsPerPass, rows - row0);
+    for (int i = threadIdx.x; i < nr * cols / 8; i += blockDim.x)
+        reinterpret_cast<uint4*>(sx)[i] = reinterpret_cast<const uint4*>(x + (size_t) row0 * cols)[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v = blockIdx.x * 8 + warp;
+    if (v >= vocab)
+        return;
+    float acc[kLogitsRowsPerPass];
+#pragma unroll
+    for (int r = 0; r < kLogitsRowsPerPass; ++r)
+        acc[r] = 0.f;
+    const __half* er = emb + (size_t) v * cols;
+    for (int k = lane * 8; k < cols; k += 256)
+    {
+        const uint4 e4 = __ldg(reinterpret_cast<const uint4*>(er + k));
+        const __half2* eh = reinterpret_cast<const __half2*>(&e4);
+        float ef[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const float2 f = __half22float2(eh[j]);
+            ef[2 * j] = f.x;
+            ef[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int r = 0; r < kLogitsRowsPerPass; ++r)
+        {
+            if (r < nr)
+            {
+                const uint4 x4 = *reinterpret_cast<const uint4*>(sx + (size_t) r * cols + k);
+                const __half2* xh = reinterpret_cast<const __half2*>(&x4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const float2 f = __half22float2(xh[j]);
+                    acc[r] = fmaf(f.x, ef[2 * j], acc[r]);
+                    acc[r] = fmaf(f.y, ef[2 * j + 1], acc[r]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kLogitsRowsPerPass; ++r)
+    {
+        if (r < nr)
+        {
+            float a = acc[r];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1)
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0)
+                logits[(size_t) (row0 + r) * vocab + v] = a;
+        }
+    }
+}
+
+// argmax over fp32 logits, first index on ties (torch.argmax).  grid = rows, 1024 threads.
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int* __restrict__ next_token, int vocab)
+{
+    grid_dep_wait();
+    const int r = blockIdx.x;
+    const float* lr = logits + (size_t) r * vocab;
+    float best = -FLT_MAX;
+    int bi = 0x7fffffff;
+    for (int v = threadIdx.x; v < vocab; v += blockDim.x)
+    {
+        const float x = lr[v];
+        if (x > best || (x == best && v < bi))
+        {
+            best = x;
+            bi = v;
+        }
+    }
+    __shared__ float sb[32];
+    __shared__ int si[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+    {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi))
+        {
+            best = ob;
+            bi = oi;
+        }
+    }
+    if (lane == 0)
+    {
+        sb[warp] = best;
+        si[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+        best = sb[lane];
+        bi = si[lane];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1)
+        {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi))
+            {
+                best = ob;
+                bi = oi;
+            }
+        }
+        if (lane == 0)
+            next_token[r] = bi;
+    }
+}
+
+int logits_tc(const __half* x, const __half* emb, float* logits, int rows, int cols, int vocab, cudaStream_t stream);
+extern int g_logits_policy;
+int g_logits_policy = 0; // 0 auto (tcgen05), 1 simt
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_layernorm_fp16(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols,
+    float eps, b200_stream_t stream)
+{
+    B200_REQUIRE(x && gamma && beta && y, B200_ERR_INVALID_ARG, "null pointer");
+    B200_REQUIRE(cols > 0 && cols % 8 == 0 && cols <= 8192, B200_ERR_UNSUPPORTED, "cols=%d must be a multiple of 8 and <= 8192", cols);
+    if (rows <= 0)
+        return B200_OK;
+    B200_REQUIRE_DEVICE();
+    const int vpt = (cols / 8 + 127) / 128;
+    cudaStream_t st = as_stream(stream);
+    const __half *xh = static_cast<const __half*>(x), *g = static_cast<const __half*>(gamma), *b = static_cast<const __half*>(beta);
+    __half* yh = static_cast<__half*>(y);
+    if (vpt <= 1)
+        layernorm_kernel<1><<<rows, 128, 0, st>>>(xh, g, b, yh, cols, eps);
+    else if (vpt <= 2)
+        layernorm_kernel<2><<<rows, 128, 0, st>>>(xh, g, b, yh, cols, eps);
+    else if (vpt <= 4)
+        layernorm_kernel<4><<<rows, 128, 0, st>>>(xh, g, b, yh, cols, eps);
+    else
+        layernorm_kernel<8><<<rows, 128, 0, st>>>(xh, g, b, yh, cols, eps);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_embed_tokens_fp16(const int32_t* tokens, const int32_t* positions, const void* tok_emb,
+    const void* pos_emb, void* out, int rows, int cols, int vocab, int n_ctx, b200_stream_t stream)
+{
+    B200_REQUIRE(tokens && positions && tok_emb && pos_emb && out, B200_ERR_INVALID_ARG, "null pointer");
+    B200_REQUIRE(cols > 0 && cols % 2 == 0, B200_ERR_INVALID_ARG, "cols=%d must be even", cols);
+    if (rows <= 0)
+        return B200_OK;
+    B200_REQUIRE_DEVICE();
+    embed_kernel<<<rows, 128, 0, as_stream(stream)>>>(tokens, positions, static_cast<const __half*>(tok_emb),
+        static_cast<const __half*>(pos_emb), static_cast<__half*>(out), cols, vocab, n_ctx);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" size_t b200_logits_workspace_bytes(int rows, int vocab)
+{
+    if (rows <= 0 || vocab <= 0)
+        return 0;
+    return (size_t) rows * vocab * sizeof(float);
+}
+
+extern "C" int b200_logits_set_kernel_policy(int policy)
+{
+    B200_REQUIRE(policy == 0 || policy == 1, B200_ERR_INVALID_ARG, "policy must be 0 (auto) or 1 (simt)");
+    g_logits_policy = policy;
+    return B200_OK;
+}
+
+extern "C" int b200_logits_argmax_fp16(const void* x, const void* emb, void* logits_fp32, int32_t* next_token, int rows,
+    int cols, int vocab, void* workspace, size_t workspace_bytes, b200_stream_t stream)
+{
+    B200_REQUIRE(x && emb, B200_ERR_INVALID_ARG, "null pointer (x/emb)");
+    B200_REQUIRE(logits_fp32 || next_token, B200_ERR_INVALID_ARG, "nothing to compute: logits and next_token are both NULL");
+    B200_REQUIRE(cols > 0 && cols % 64 == 0, B200_ERR_UNSUPPORTED, "cols=%d must be a multiple of 64", cols);
+    if (rows <= 0)
+        return B200_OK;
+    B200_REQUIRE_DEVICE();
+    float* lg = static_cast<float*>(logits_fp32);
+    if (lg == nullptr)
+    {
+        B200_REQUIRE(workspace && workspace_bytes >= (size_t) rows * vocab * sizeof(float), B200_ERR_WORKSPACE,
+            "logits: workspace of %zu bytes needed", (size_t) rows * vocab * sizeof(float));
+        lg = static_cast<float*>(workspace);
+    }
+    cudaStream_t st = as_stream(stream);
+    if (g_logits_policy == 0)
+    {
+        if (int rc = logits_tc(static_cast<const __half*>(x), static_cast<const __half*>(emb), lg, rows, cols, vocab, st))
+            return rc;
+    }
+    else
+    {
+        const size_t smem = (size_t) kLogitsRowsPerPass * cols * sizeof(__half);
+        B200_REQUIRE(smem <= 200 * 1024, B200_ERR_UNSUPPORTED, "cols=%d too large for the SIMT logits path", cols);
+        if (smem > 48 * 1024)
+            B200_CUDA(cudaFuncSetAttribute(logits_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        for (int r0 = 0; r0 < rows; r0 += kLogitsRowsPerPass)
+        {
+            logits_simt_kernel<<<(vocab + 7) / 8, 256, smem, st>>>(
+                static_cast<const __half*>(x), static_cast<const __half*>(emb), lg, rows, cols, vocab, r0);
+            B200_LAUNCH_CHECK();
+        }
+    }
+    if (next_token != nullptr)
+    {
+        argmax_kernel<<<rows, 1024, 0, st>>>(lg, next_token, vocab);
+        B200_LAUNCH_CHECK();
+    }
+    return B200_OK;
+}

@@ -1,0 +1,70 @@
+// woq_api.cu -- C ABI entry points of the weight-only matmul and their dispatch.
+// Mirrors WeightOnlyQuantMatmulPlugin::enqueue's m == 1 -> GEMV / else -> tensor-core GEMM split
+// (T/cpp/tensorrt_llm/plugins/weightOnlyQuantMatmulPlugin/weightOnlyQuantMatmulPlugin.cpp:162-222), with the
+// B200 crossover: SIMT GEMV for M <= 4, tcgen05 for M > 4 (CUDA cores cannot sustain 16 MACs per weight byte at
+// HBM rate).
+#include "common.cuh"
+
+namespace b200
+{
+int woq_gemv_simt(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
+    int activation, const __half* residual, __half* C, cudaStream_t stream);
+int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
+    int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t woq_tc_workspace_bytes(int max_m, int N, int K);
+int tc_init();
+
+static int g_policy = 0; // 0 auto, 1 simt, 2 tcgen05
+} // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_woq_set_kernel_policy(int policy)
+{
+    B200_REQUIRE(policy >= 0 && policy <= 2, B200_ERR_INVALID_ARG, "policy must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+    g_policy = policy;
+    return B200_OK;
+}
+
+extern "C" size_t b200_woq_workspace_bytes(int max_m, int n, int k)
+{
+    if (max_m < 1 || n < 1 || k < 1)
+        return 0;
+    return woq_tc_workspace_bytes(max_m, n, k);
+}
+
+extern "C" int b200_woq_int8_gemm_fused(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N,
+    const void* bias, int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes,
+    b200_stream_t stream)
+{
+    B200_REQUIRE(A && Wproc && scales && C, B200_ERR_INVALID_ARG, "null pointer (A/W/scales/C)");
+    B200_REQUIRE(M >= 0, B200_ERR_INVALID_ARG, "M=%d must be >= 0", M);
+    B200_REQUIRE(K > 0 && K % 64 == 0, B200_ERR_INVALID_ARG, "K=%d must be a positive multiple of 64", K);
+    B200_REQUIRE(N > 0 && N % 64 == 0, B200_ERR_INVALID_ARG, "N=%d must be a positive multiple of 64", N);
+    B200_REQUIRE(activation >= B200_ACT_NONE && activation <= B200_ACT_GELU_TANH, B200_ERR_INVALID_ARG,
+        "unknown activation %d", activation);
+    if (M == 0)
+        return B200_OK; // empty batch: nothing to do (the reference would launch an empty grid)
+    B200_REQUIRE_DEVICE();
+    const bool simt = (g_policy == 1) || (g_policy == 0 && M <= 4);
+    if (simt)
+        return woq_gemv_simt(static_cast<const __half*>(A), M, K, reinterpret_cast<const uint8_t*>(Wproc),
+            static_cast<const __half*>(scales), N, static_cast<const __half*>(bias), activation,
+            static_cast<const __half*>(residual), static_cast<__half*>(C), as_stream(stream));
+    return woq_gemm_tc(static_cast<const __half*>(A), M, K, reinterpret_cast<const uint8_t*>(Wproc),
+        static_cast<const __half*>(scales), N, static_cast<const __half*>(bias), activation,
+        static_cast<const __half*>(residual), static_cast<__half*>(C), workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int b200_woq_int8_gemm(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N, void* C,
+    void* workspace, size_t workspace_bytes, b200_stream_t stream)
+{
+    return b200_woq_int8_gemm_fused(
+        A, M, K, Wproc, scales, N, nullptr, B200_ACT_NONE, nullptr, C, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200_init(void)
+{
+    B200_REQUIRE_DEVICE();
+    return tc_init();
+}

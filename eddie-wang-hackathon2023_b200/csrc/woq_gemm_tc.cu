@@ -1,0 +1,702 @@
+// woq_gemm_tc.cu -- fp16 activations x per-channel int8 weights on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Replaces CutlassFpAIntBGemmRunner<half,uint8_t>::gemm
+//   T/cpp/tensorrt_llm/kernels/cutlass_kernels/fpA_intB_gemm/fpA_intB_gemm_template.h:358-435
+//   (kernel T/cpp/tensorrt_llm/cutlass_extensions/include/cutlass_extensions/gemm/kernel/fpA_intB_gemm.h:57-490),
+// which does not build for sm_100 (static_assert at fpA_intB_gemm.h:483-485), on the reference's exact
+// preprocessed weight layout ([N/2][2K] bytes, see quantize.cu).
+//
+// B200 design ("swap-AB", weights are the UMMA A operand and live in TMEM):
+//   D[n, m] = sum_k W16[n, k] * X[m, k]      UMMA M = 128 weight columns n, UMMA N = MT activation rows m.
+//  * warp 4 (one lane): TMA producer.  Per 64-wide k-block it loads the int8 weight tile (64 row pairs x 128 B,
+//    one 2-D box of the [N/2][2K] byte matrix, 128B-swizzled so the dequant warps' 128-bit reads are
+//    conflict-free) and the fp16 activation tile (MT rows x 64 k, K-major, 128B swizzle = the canonical UMMA
+//    B layout) into a shared-memory ring.  Weight loads are issued before griddepcontrol.wait (PDL).
+//  * warps 0-3: dequant.  Thread T owns weight column n0+T: it reads its 64 bytes of the k-block, converts
+//    them with PRMT/HSUB2 (the 0x6400|b trick), multiplies by the fp16 column scale (effective weight
+//    fp16(q*s), identical to the reference's mma_tensorop_dequantizer.h:253-270) and writes 32 packed-half2
+//    registers straight into TMEM lane T with one tcgen05.st.32x32b.x32.  The reference layout's row
+//    permutation + byte swizzle make every converted register a k-adjacent pair, i.e. exactly one 32-bit
+//    TMEM column of the K-major A operand -- no shuffles, no second shared-memory round trip.
+//  * warp 5 (one lane): issues tcgen05.mma.kind::f16 with A from TMEM and B from shared memory, fp32
+//    accumulator in TMEM, and tcgen05.commit to release the stages.
+//  * warps 0-3 again: epilogue.  tcgen05.ld the accumulator (lane = n, column = m), fused bias / GELU /
+//    residual, fp16 store (lanes of a warp write 32 consecutive n: coalesced).  With split-K, partial tiles
+//    go to fp32 slabs in the workspace and the last CTA of a tile reduces them in split order (deterministic).
+// HBM traffic: every weight byte is read once per m-tile; activations are re-read per n-tile from L2.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace b200
+{
+
+struct TcParams
+{
+    const __half* scales;
+    const __half* bias;
+    const __half* residual;
+    __half* C;
+    float* slabs;  // split-K partial tiles (workspace)
+    int* counters; // per-tile arrival counters (library owned, self-resetting)
+    int M, N, K;
+    int ldc;
+    int activation;
+    int kb_total; // K / 64
+    int splits;
+};
+
+__device__ __forceinline__ void tc_fence_before()
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_fence_after()
+{
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]   (kind::f16, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_st_x32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_ld_x16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+constexpr int kWTileBytes = 64 * 128; // 64 row pairs x 128 B = 128 columns x 64 k
+
+__host__ __device__ constexpr uint32_t tmem_cols_pow2(uint32_t c)
+{
+    return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
+}
+
+// K-major, 128B-swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_128B(=2)<<61
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
+{
+    return (uint64_t) ((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int MT, int SS, int AS>
+__global__ void __launch_bounds__(192, 1)
+    woq_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const TcParams p)
+{
+    constexpr int XTileBytes = MT * 128;
+    constexpr uint32_t kTmemCols = tmem_cols_pow2(32 * AS + MT);
+    constexpr uint32_t kDCol = 32 * AS;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=f16 (0), K-major both,
+    // N>>3 at bit 17, M>>4 at bit 24
+    constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t) (MT >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms (TMA and UMMA agree on address bits 7..9)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smW = smem;
+    uint8_t* smX = smem + SS * kWTileBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smX + SS * XTileBytes);
+    uint64_t* smem_free = full + SS;
+    uint64_t* a_ready = smem_free + SS;
+    uint64_t* mma_done = a_ready + AS;
+    uint64_t* acc_done = mma_done + AS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+    int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+    const int kb_begin = (int) (((long long) split * p.kb_total) / p.splits);
+    const int kb_end = (int) (((long long) (split + 1) * p.kb_total) / p.splits);
+    const int nkb = kb_end - kb_begin;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < SS; ++s)
+        {
+            mbar_init(&full[s], 1);
+            mbar_init(&smem_free[s], 1);
+        }
+        for (int a = 0; a < AS; ++a)
+        {
+            mbar_init(&a_ready[a], 4);
+            mbar_init(&mma_done[a], 1);
+        }
+        mbar_init(acc_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4 && lane == 0)
+    {
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmX);
+    }
+    if (warp == 5)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4)
+    {
+        // ===== TMA producer =====
+        if (lane == 0)
+        {
+            const int pre = nkb < SS ? nkb : SS;
+            // weights first: they do not depend on the previous kernel
+            for (int i = 0; i < pre; ++i)
+            {
+                mbar_arrive_expect_tx(&full[i], kWTileBytes + XTileBytes);
+                tma_load_2d(smW + i * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[i]);
+            }
+            grid_dep_wait();
+            for (int i = 0; i < pre; ++i)
+                tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &full[i]);
+            for (int i = pre; i < nkb; ++i)
+            {
+                const int ss = i % SS;
+                mbar_wait(&smem_free[ss], ((i / SS) - 1) & 1);
+                mbar_arrive_expect_tx(&full[ss], kWTileBytes + XTileBytes);
+                tma_load_2d(smW + ss * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[ss]);
+                tma_load_2d(smX + ss * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &full[ss]);
+            }
+        }
+    }
+    else if (warp == 5)
+    {
+        // ===== MMA issuer =====
+        if (lane == 0)
+        {
+            const uint32_t d_tmem = tmem_base + kDCol;
+            for (int i = 0; i < nkb; ++i)
+            {
+                const int ss = i % SS, as = i % AS;
+                mbar_wait(&full[ss], (i / SS) & 1);
+                mbar_wait(&a_ready[as], (i / AS) & 1);
+                tc_fence_after();
+                const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smX + ss * XTileBytes));
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                {
+                    // K advance inside the 128-byte swizzle atom: 16 halves = 32 bytes = 2 descriptor units
+                    tc_mma_ts(d_tmem, tmem_base + as * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
+                }
+                tc_commit(&mma_done[as]);
+                tc_commit(&smem_free[ss]);
+            }
+            tc_commit(acc_done);
+        }
+    }
+    else
+    {
+        // ===== dequant warps 0..3, then epilogue =====
+        const int T = threadIdx.x; // weight column inside the tile == TMEM lane
+        const int n = n_tile * 128 + T;
+        const int jl = T >> 1, hf = T & 1, sw = jl & 7;
+        const __half sc = (n < p.N) ? p.scales[n] : __float2half(0.f);
+        const __half2 sc2 = __half2half2(sc);
+        const uint32_t lane_field = (uint32_t) (warp * 32) << 16;
+
+        for (int i = 0; i < nkb; ++i)
+        {
+            const int ss = i % SS, as = i % AS;
+            mbar_wait(&full[ss], (i / SS) & 1);
+            const uint8_t* rowp = smW + ss * kWTileBytes + jl * 128;
+            uint4 v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                v[c] = *reinterpret_cast<const uint4*>(rowp + (((4 * hf + c) ^ sw) << 4));
+            uint32_t r[32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+                const uint32_t words[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                {
+                    __half2 lo, hi;
+                    dequant_word(words[w], lo, hi);
+                    lo = __hmul2(lo, sc2);
+                    hi = __hmul2(hi, sc2);
+                    // chunk c = k-slice [16c, 16c+16): column 8c+w holds k = 2w, 2w+1; column 8c+4+w holds 8+2w, 8+2w+1
+                    r[8 * c + w] = *reinterpret_cast<uint32_t*>(&lo);
+                    r[8 * c + 4 + w] = *reinterpret_cast<uint32_t*>(&hi);
+                }
+            }
+            if (i >= AS)
+            {
+                mbar_wait(&mma_done[as], ((i / AS) - 1) & 1);
+                tc_fence_after();
+            }
+            tc_st_x32(tmem_base + lane_field + as * 32, r);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&a_ready[as]);
+        }
+
+        // ---- epilogue ----
+        mbar_wait(acc_done, 0);
+        tc_fence_after();
+        const int n_tiles = gridDim.x, m_tiles = gridDim.y;
+        const int tile_id = m_tile * n_tiles + n_tile;
+        const bool direct = (p.splits == 1);
+        float* slab = direct ? nullptr
+                             : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * (size_t) (128 * MT);
+#pragma unroll 1
+        for (int c16 = 0; c16 < MT / 16; ++c16)
+        {
+            uint32_t acc[16];
+            tc_ld_x16(tmem_base + lane_field + kDCol + c16 * 16, acc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+            {
+                const int ml = c16 * 16 + i;
+                const int m = m_tile * MT + ml;
+                const float val = __uint_as_float(acc[i]);
+                if (direct)
+                {
+                    if (m < p.M && n < p.N)
+                    {
+                        const size_t idx = (size_t) m * p.ldc + n;
+                        p.C[idx] = epilogue_apply(val, 1.0f, p.bias, p.activation, p.residual, n, idx);
+                    }
+                }
+                else if (m < p.M)
+                {
+                    slab[ml * 128 + T] = val;
+                }
+            }
+        }
+        if (!direct)
+        {
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (T == 0)
+            {
+                const int old = atomicAdd(&p.counters[tile_id], 1);
+                *last_flag = (old == p.splits - 1) ? 1 : 0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*last_flag)
+            {
+                __threadfence();
+                const int m_valid = min(MT, p.M - m_tile * MT);
+                if (n < p.N)
+                {
+                    for (int ml = 0; ml < m_valid; ++ml)
+                    {
+                        float sum = 0.f;
+                        for (int s = 0; s < p.splits; ++s)
+                            sum += __ldcg(p.slabs + ((size_t) s * m_tiles * n_tiles + tile_id) * (size_t) (128 * MT)
+                                + ml * 128 + T);
+                        const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
+                        p.C[idx] = epilogue_apply(sum, 1.0f, p.bias, p.activation, p.residual, n, idx);
+                    }
+                }
+                if (T == 0)
+                    p.counters[tile_id] = 0; // self-reset for the next launch using this slot
+            }
+        }
+    }
+
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5)
+    {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+// =====================================================================================================
+// fp16 x fp16 -> fp32 "swap-AB" GEMM for the logits projection: out[m, v] = sum_k X[m, k] * E[v, k].
+// E (token embedding, [vocab, K] fp16, not quantized in the reference: model.py:231,290) is the UMMA A operand
+// straight from TMA-staged shared memory (128 vocabulary rows per CTA), X the B operand (MT <= 256 rows).
+// =====================================================================================================
+struct LogitsParams
+{
+    float* out; // [M, vocab] fp32
+    int M, vocab, kb_total;
+};
+
+template <int MT, int SS>
+__global__ void __launch_bounds__(192, 1)
+    fp16_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmX, const LogitsParams p)
+{
+    constexpr int ETileBytes = 128 * 128;
+    constexpr int XTileBytes = MT * 128;
+    constexpr uint32_t kTmemCols = tmem_cols_pow2(MT);
+    constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t) (MT >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smE = smem;
+    uint8_t* smX = smem + SS * ETileBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smX + SS * XTileBytes);
+    uint64_t* smem_free = full + SS;
+    uint64_t* acc_done = smem_free + SS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int nkb = p.kb_total;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < SS; ++s)
+        {
+            mbar_init(&full[s], 1);
+            mbar_init(&smem_free[s], 1);
+        }
+        mbar_init(acc_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4 && lane == 0)
+    {
+        tma_prefetch_desc(&tmE);
+        tma_prefetch_desc(&tmX);
+    }
+    if (warp == 5)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4)
+    {
+        if (lane == 0)
+        {
+            const int pre = nkb < SS ? nkb : SS;
+            for (int i = 0; i < pre; ++i)
+            {
+                mbar_arrive_expect_tx(&full[i], ETileBytes + XTileBytes);
+                tma_load_2d(smE + i * ETileBytes, &tmE, i * 64, n_tile * 128, &full[i]);
+            }
+            grid_dep_wait();
+            for (int i = 0; i < pre; ++i)
+                tma_load_2d(smX + i * XTileBytes, &tmX, i * 64, m_tile * MT, &full[i]);
+            for (int i = pre; i < nkb; ++i)
+            {
+                const int ss = i % SS;
+                mbar_wait(&smem_free[ss], ((i / SS) - 1) & 1);
+                mbar_arrive_expect_tx(&full[ss], ETileBytes + XTileBytes);
+                tma_load_2d(smE + ss * ETileBytes, &tmE, i * 64, n_tile * 128, &full[ss]);
+                tma_load_2d(smX + ss * XTileBytes, &tmX, i * 64, m_tile * MT, &full[ss]);
+            }
+        }
+    }
+    else if (warp == 5)
+    {
+        if (lane == 0)
+        {
+            for (int i = 0; i < nkb; ++i)
+            {
+                const int ss = i % SS;
+                mbar_wait(&full[ss], (i / SS) & 1);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_k_sw128(smem_u32(smE + ss * ETileBytes));
+                const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smX + ss * XTileBytes));
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    tc_mma_ss(tmem_base, adesc + 2 * k4, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
+                tc_commit(&smem_free[ss]);
+            }
+            tc_commit(acc_done);
+        }
+    }
+    else
+    {
+        mbar_wait(acc_done, 0);
+        tc_fence_after();
+        const int v = n_tile * 128 + threadIdx.x;
+        const uint32_t lane_field = (uint32_t) (warp * 32) << 16;
+#pragma unroll 1
+        for (int c16 = 0; c16 < MT / 16; ++c16)
+        {
+            uint32_t acc[16];
+            tc_ld_x16(tmem_base + lane_field + c16 * 16, acc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+            {
+                const int m = m_tile * MT + c16 * 16 + i;
+                if (m < p.M && v < p.vocab)
+                    p.out[(size_t) m * p.vocab + v] = __uint_as_float(acc[i]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5)
+    {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once,
+        []()
+        {
+            void* sym = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess
+                && qres == cudaDriverEntryPointSuccess)
+                fn = reinterpret_cast<PFN_encodeTiled>(sym);
+        });
+    return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uint64_t dim0, uint64_t dim1,
+    uint64_t stride1_bytes, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz)
+{
+    PFN_encodeTiled enc = get_encode();
+    B200_REQUIRE(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {stride1_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
+    return B200_OK;
+}
+
+struct TcPlan
+{
+    int MT, m_tiles, n_tiles, splits;
+    size_t slab_bytes;
+};
+
+TcPlan plan_tc(int M, int N, int K)
+{
+    TcPlan pl{};
+    pl.MT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+    pl.m_tiles = (M + pl.MT - 1) / pl.MT;
+    pl.n_tiles = (N + 127) / 128;
+    const int kb_total = K / 64;
+    const int tiles = pl.m_tiles * pl.n_tiles;
+    const int sms = num_sms();
+    int splits = 1;
+    if (tiles < sms && tiles <= 4096)
+    {
+        splits = sms / tiles;
+        // keep at least 2 k-blocks per split so the per-CTA fixed cost is amortised
+        if (splits > kb_total / 2)
+            splits = kb_total / 2;
+        if (splits < 1)
+            splits = 1;
+    }
+    pl.splits = splits;
+    pl.slab_bytes = splits > 1 ? (size_t) splits * tiles * 128 * pl.MT * sizeof(float) : 0;
+    return pl;
+}
+
+static int* g_counters = nullptr;
+static std::mutex g_counter_mu;
+static unsigned g_counter_slot = 0;
+constexpr int kCounterSlots = 64, kCounterSlotInts = 4096;
+
+int tc_init()
+{
+    std::lock_guard<std::mutex> lk(g_counter_mu);
+    if (g_counters == nullptr)
+    {
+        B200_CUDA(cudaMalloc(&g_counters, sizeof(int) * kCounterSlots * kCounterSlotInts));
+        B200_CUDA(cudaMemset(g_counters, 0, sizeof(int) * kCounterSlots * kCounterSlotInts));
+    }
+    return B200_OK;
+}
+
+template <int MT, int SS, int AS>
+static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcParams& p, dim3 grid, cudaStream_t stream)
+{
+    auto kern = woq_gemm_tc_kernel<MT, SS, AS>;
+    const size_t smem = 1024 + (size_t) SS * (kWTileBytes + MT * 128) + sizeof(uint64_t) * (2 * SS + 2 * AS + 1) + 16;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_set = true;
+    }
+    kern<<<grid, 192, smem, stream>>>(tmW, tmX, p);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// tcgen05 path entry: any M >= 1.
+int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
+    int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream)
+{
+    const TcPlan pl = plan_tc(M, N, K);
+    B200_REQUIRE(pl.slab_bytes == 0 || (workspace != nullptr && workspace_bytes >= pl.slab_bytes), B200_ERR_WORKSPACE,
+        "woq gemm: workspace of %zu bytes needed for split-K, got %zu", pl.slab_bytes, workspace_bytes);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+        B200_ERR_INVALID_ARG, "woq gemm: A and W must be 16-byte aligned for TMA");
+    if (g_counters == nullptr)
+    {
+        if (int rc = tc_init())
+            return rc;
+    }
+    CUtensorMap tmW, tmX;
+    if (int rc = make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, W, (uint64_t) 2 * K, (uint64_t) N / 2,
+            (uint64_t) 2 * K, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B))
+        return rc;
+    if (int rc = make_tmap_2d(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A, (uint64_t) K, (uint64_t) M, (uint64_t) K * 2, 64,
+            (uint32_t) pl.MT, CU_TENSOR_MAP_SWIZZLE_128B))
+        return rc;
+    TcParams p{};
+    p.scales = scales;
+    p.bias = bias;
+    p.residual = residual;
+    p.C = C;
+    p.slabs = static_cast<float*>(workspace);
+    {
+        std::lock_guard<std::mutex> lk(g_counter_mu);
+        p.counters = g_counters + (size_t) (g_counter_slot++ % kCounterSlots) * kCounterSlotInts;
+    }
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.ldc = N;
+    p.activation = activation;
+    p.kb_total = K / 64;
+    p.splits = pl.splits;
+    dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
+    switch (pl.MT)
+    {
+    case 16: return launch_tc<16, 8, 6>(tmW, tmX, p, grid, stream);
+    case 32: return launch_tc<32, 8, 6>(tmW, tmX, p, grid, stream);
+    case 64: return launch_tc<64, 8, 6>(tmW, tmX, p, grid, stream);
+    case 128: return launch_tc<128, 6, 4>(tmW, tmX, p, grid, stream);
+    default: return launch_tc<256, 4, 8>(tmW, tmX, p, grid, stream);
+    }
+}
+
+size_t woq_tc_workspace_bytes(int max_m, int N, int K)
+{
+    // plan_tc never uses more than num_sms() slabs of one 128 x MT fp32 tile (splits * tiles <= num_sms), and MT
+    // grows with M, so the class of max_m bounds every smaller M.
+    (void) N;
+    (void) K;
+    const int MT = max_m <= 16 ? 16 : max_m <= 32 ? 32 : max_m <= 64 ? 64 : max_m <= 128 ? 128 : 256;
+    return (size_t) num_sms() * 128 * MT * sizeof(float);
+}
+
+template <int MT, int SS>
+static int launch_logits(const CUtensorMap& tmE, const CUtensorMap& tmX, const LogitsParams& p, dim3 grid, cudaStream_t stream)
+{
+    auto kern = fp16_gemm_tc_kernel<MT, SS>;
+    const size_t smem = 1024 + (size_t) SS * (128 * 128 + MT * 128) + sizeof(uint64_t) * (2 * SS + 1) + 16;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_set = true;
+    }
+    kern<<<grid, 192, smem, stream>>>(tmE, tmX, p);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+int logits_tc(const __half* x, const __half* emb, float* logits, int rows, int cols, int vocab, cudaStream_t stream)
+{
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0,
+        B200_ERR_INVALID_ARG, "logits: x and emb must be 16-byte aligned for TMA");
+    const int MT = rows <= 16 ? 16 : rows <= 32 ? 32 : rows <= 64 ? 64 : rows <= 128 ? 128 : 256;
+    CUtensorMap tmE, tmX;
+    if (int rc = make_tmap_2d(&tmE, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, emb, (uint64_t) cols, (uint64_t) vocab,
+            (uint64_t) cols * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))
+        return rc;
+    if (int rc = make_tmap_2d(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x, (uint64_t) cols, (uint64_t) rows,
+            (uint64_t) cols * 2, 64, (uint32_t) MT, CU_TENSOR_MAP_SWIZZLE_128B))
+        return rc;
+    LogitsParams p{};
+    p.out = logits;
+    p.M = rows;
+    p.vocab = vocab;
+    p.kb_total = cols / 64;
+    dim3 grid((vocab + 127) / 128, (rows + MT - 1) / MT);
+    switch (MT)
+    {
+    case 16: return launch_logits<16, 6>(tmE, tmX, p, grid, stream);
+    case 32: return launch_logits<32, 6>(tmE, tmX, p, grid, stream);
+    case 64: return launch_logits<64, 6>(tmE, tmX, p, grid, stream);
+    case 128: return launch_logits<128, 5>(tmE, tmX, p, grid, stream);
+    default: return launch_logits<256, 4>(tmE, tmX, p, grid, stream);
+    }
+}
+
+} // namespace b200

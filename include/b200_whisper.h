@@ -1,0 +1,202 @@
+/*
+ * b200_whisper.h -- C ABI of the B200-native (sm_100a) quantized Whisper decoder hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `extern "C"`, CUDA stream last, int status.
+ * The C++ TensorRT plugin classes under eddie-wang-hackathon2023_b200/plugins/ (same names, fields and
+ * serialization as the reference's) only marshal into these entry points, and so does the Python mirror of
+ * the reference's operator API (ctypes).  Every entry point cites the reference interface it replaces;
+ * paths are relative to /root/reference/tensorrt_llm_july-release-v1/ (T/).
+ *
+ * All `const void*` tensors are DEVICE pointers unless the function name ends in `_host`.
+ * fp16 tensors are IEEE binary16 (`half`), row-major, innermost dimension contiguous.
+ * Functions are asynchronous on `stream` and return B200_OK (0) or an error code; b200_last_error()
+ * returns a thread-local message for the last failure.  There is NO CPU fallback anywhere: on a machine
+ * without an sm_100 device every compute entry point returns B200_ERR_CUDA.
+ */
+#ifndef B200_WHISPER_H
+#define B200_WHISPER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+typedef struct CUstream_st* b200_stream_t; /* == cudaStream_t */
+
+enum
+{
+    B200_OK = 0,
+    B200_ERR_INVALID_ARG = 1,
+    B200_ERR_UNSUPPORTED = 2,
+    B200_ERR_CUDA = 3,
+    B200_ERR_WORKSPACE = 4
+};
+
+/* dtype codes (same numbering as nvinfer1::DataType: kFLOAT=0, kHALF=1, kINT8=2, kINT32=3) */
+enum
+{
+    B200_DTYPE_F32 = 0,
+    B200_DTYPE_F16 = 1,
+    B200_DTYPE_I8 = 2,
+    B200_DTYPE_I32 = 3
+};
+
+/* epilogue activation codes for the fused matmul / conv entry points */
+enum
+{
+    B200_ACT_NONE = 0,
+    B200_ACT_GELU_ERF = 1, /* torch nn.GELU(), T/examples/whisper/torch_model.py:120,143-144 */
+    B200_ACT_GELU_TANH = 2 /* TRT-LLM gelu(), T/tensorrt_llm/functional.py:2044-2056 */
+};
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+unsigned long long b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight preparation.
+ * Replaces  symmetric_quantize<half,half|float>  T/cpp/tensorrt_llm/kernels/cutlass_kernels/cutlass_preprocessors.cpp:615-721
+ *           preprocess_weights_for_mixed_gemm    same file :537-578 (Sm80..Sm90 layout: row permute, column major,
+ *                                                2-column interleave in 64-row tiles, +128 bias and byte swizzle)
+ * as reached from torch.ops.fastertransformer.symmetric_quantize_last_axis_of_batched_matrix
+ *           T/cpp/tensorrt_llm/thop/weightOnlyQuantOp.cpp:143-236.
+ * The reference runs these single-threaded on the host; here they are CUDA kernels, bit-exact with it.
+ *
+ * w: [K, N] row-major (the transpose of torch's [out, in] Linear weight, as T/examples/whisper/weight.py:76-77
+ * passes it), dtype B200_DTYPE_F16 or B200_DTYPE_F32.  K % 64 == 0 and N % 64 == 0 (reference checks :187-192,
+ * :498-500).  proc: K*N bytes in the processed layout; raw (nullable): [K, N] int8; scales: [N] of scale_dtype
+ * (F16 or F32).  Stored scale = amax/128 rounded to scale_dtype; quantization divides by the fp32 scale.
+ * ---------------------------------------------------------------------------------------------- */
+int b200_symmetric_quantize_int8(const void* w, int w_dtype, int K, int N, int8_t* proc, int8_t* raw, void* scales,
+    int scale_dtype, b200_stream_t stream);
+int b200_preprocess_weights_int8(const int8_t* raw, int K, int N, int8_t* proc, b200_stream_t stream);
+/* Host-pointer conveniences (H2D copy, kernels, D2H copy, stream synchronised on return) -- these mirror the
+ * reference torch op, which takes and returns CPU tensors. */
+int b200_symmetric_quantize_int8_host(const void* w, int w_dtype, int K, int N, int8_t* proc, int8_t* raw,
+    void* scales, int scale_dtype);
+int b200_preprocess_weights_int8_host(const int8_t* raw, int K, int N, int8_t* proc);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp16 activations x per-channel int8 weights (weightOnlyQuantMatmul / fpA_intB).
+ * Replaces  weight_only_gemv_launcher                 T/cpp/tensorrt_llm/kernels/weightOnlyMatrixVectorMultiplication.cu:371-378 (m == 1)
+ *           CutlassFpAIntBGemmRunner<half,uint8_t>::gemm  T/cpp/tensorrt_llm/kernels/cutlass_kernels/fpA_intB_gemm/fpA_intB_gemm_template.h:358-435 (m > 1)
+ *           ...::getWorkspaceSize                     same file :426-435
+ * as dispatched by WeightOnlyQuantMatmulPlugin::enqueue  T/cpp/tensorrt_llm/plugins/weightOnlyQuantMatmulPlugin/weightOnlyQuantMatmulPlugin.cpp:162-222.
+ *
+ * A [M, K] fp16; Wproc: K*N bytes in the processed layout above; scales [N] fp16; C [M, N] fp16.
+ * C = fp16( (sum_k A[m,k] * q[k,n]) * scales[n] ), fp32 accumulation.  K % 64 == 0, N % 64 == 0, M >= 1.
+ * The _fused variant additionally applies, in this order and each rounded to fp16 like the reference's separate
+ * elementwise layers (T/tensorrt_llm/quantization/layer.py:311-312): + bias[n], activation, + residual[m, n].
+ * bias / residual may be NULL.  residual may alias C.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200_woq_workspace_bytes(int max_m, int n, int k);
+int b200_woq_int8_gemm(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N, void* C,
+    void* workspace, size_t workspace_bytes, b200_stream_t stream);
+int b200_woq_int8_gemm_fused(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N,
+    const void* bias, int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes,
+    b200_stream_t stream);
+/* Forces a kernel family for tests/benchmarks: 0 = auto, 1 = SIMT GEMV, 2 = tcgen05 GEMM. */
+int b200_woq_set_kernel_policy(int policy);
+/* One-time allocation of library-owned device state (split-K tile counters).  Call before CUDA-graph capture. */
+int b200_init(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked multi-head attention, generation phase, contiguous KV cache [B, 2, H, Smax, Dh], fp16 I/O,
+ * int8 or fp16 cache.
+ * Replaces  masked_multihead_attention (Dh=64 half)   T/cpp/tensorrt_llm/kernels/decoderMaskedMultiheadAttention/decoderMaskedMultiheadAttentionTemplate.h:1195-2017
+ *           Masked_multihead_attention_params         T/cpp/tensorrt_llm/kernels/decoderMaskedMultiheadAttention.h:70-188
+ *           KVLinearBuffer                            T/cpp/tensorrt_llm/kernels/kvCacheUtils.h:114-170
+ * as filled by GPTAttentionPluginCommon::enqueueGeneration  T/cpp/tensorrt_llm/plugins/gptAttentionCommon/gptAttentionCommon.cpp:649-780.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200_mmha_params
+{
+    const void* qkv;              /* [B, 3*H*Dh] fp16: q | k | v of the current token (params.q/k/v + stride) */
+    const void* qkv_bias;         /* [3*H*Dh] fp16 or NULL (plugin passes NULL, gptAttentionCommon.cpp:723) */
+    void* out;                    /* [B, H*Dh] fp16 */
+    void* kv_cache;               /* [B, 2, H, Smax, Dh] int8 or fp16; read for t < length, written at t = length */
+    const int32_t* sequence_lengths; /* [B] device: tokens already in the cache per sequence (length_per_sample);
+                                        NULL => past_kv_length for every sequence */
+    const int32_t* masked_tokens; /* [B, Smax] device, nonzero = key excluded (padding); may be NULL */
+    const float* kv_scale_orig_quant; /* [1] device fp32, used when cache is int8 */
+    const float* kv_scale_quant_orig; /* [1] device fp32 */
+    int32_t batch_size;           /* B (beam width 1) */
+    int32_t num_heads;            /* H */
+    int32_t head_size;            /* Dh: 64 */
+    int32_t max_seq_len;          /* Smax (memory_max_len) */
+    int32_t past_kv_length;       /* host scalar, timestep */
+    int32_t int8_kv_cache;        /* 1: int8 cache, 0: fp16 cache */
+    float q_scaling;              /* inv_sqrt_dh = 1 / (sqrt(Dh) * q_scaling) */
+} b200_mmha_params;
+
+int b200_mmha_generation(const b200_mmha_params* params, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Context (prompt) phase: causal attention over S tokens per sequence + KV cache fill (optionally int8).
+ * Replaces  GPTAttentionPluginCommon::enqueueContext  T/cpp/tensorrt_llm/plugins/gptAttentionCommon/gptAttentionCommon.cpp:361-620
+ *           (add_fusedQKV_bias_transpose, transpose4dBatchMajorKVCache T/cpp/tensorrt_llm/kernels/unfusedAttentionKernels.cu:1106-1490,1552-1646,
+ *            cuBLAS QK^T, softmax_kernel :179-257, cuBLAS PV, transpose) -- nine launches there, one here.
+ * qkv [B, S, 3*H*Dh] fp16; input_lengths [B] device (tokens >= length are padding: their outputs are
+ * unspecified and they are not attended to); out [B, S, H*Dh]; kv_cache as above, rows [0, S) written.
+ * ---------------------------------------------------------------------------------------------- */
+int b200_attention_context(const void* qkv, const int32_t* input_lengths, void* out, void* kv_cache,
+    const float* kv_scale_orig_quant, int batch_size, int seq_len, int num_heads, int head_size, int max_seq_len,
+    int int8_kv_cache, float q_scaling, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cached cross-attention over the encoder frames with an int8 (or fp16) cross-KV cache
+ * [B, 2, H, S_enc, Dh] produced once per utterance by the cross_kv_cache_warping model.
+ * Reference: unfused path  T/tensorrt_llm/layers/attention.py:308-323,385-406 and CrossAttn_KV
+ * T/tensorrt_llm/models/whisper/model.py:469-555 (fp16 there; the int8 cache follows the MMHA int8 KV
+ * convention, decoderMaskedMultiheadAttentionUtils.h:2276-2286,2357-2390).  No reference CUDA kernel exists
+ * (Template.h:1283); the oracle is torch_model.py:88-103 with int8 round-tripped K/V.
+ * q [R, H*Dh] fp16; out [R, H*Dh] fp16; softmax(q K^T / sqrt(Dh)) V over all kv_len keys, no mask.
+ * R = num_q_rows query rows; row r attends to cache sequence r / q_rows_per_seq (1 per sequence in the
+ * generation phase, S_prompt per sequence in the context phase).  Workspace holds split-KV partials
+ * (size it with batch_size = R).
+ * ---------------------------------------------------------------------------------------------- */
+size_t b200_cross_attention_workspace_bytes(int batch_size, int num_heads, int head_size, int kv_len);
+int b200_cross_attention(const void* q, const void* cross_kv, const float* kv_scale_quant_orig, void* out,
+    int num_q_rows, int q_rows_per_seq, int num_heads, int head_size, int kv_len, int int8_kv_cache, void* workspace,
+    size_t workspace_bytes, b200_stream_t stream);
+/* Packs fp16 K and V projections [B, S, H*Dh] into the cross-KV cache layout, quantizing with
+ * cvt.rni.sat.s8.f32(scale * x) when int8_kv_cache (same rule as the self-attention cache). */
+int b200_cross_kv_pack(const void* k, const void* v, void* cross_kv, const float* kv_scale_orig_quant, int batch_size,
+    int kv_len, int num_heads, int head_size, int int8_kv_cache, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conv1d encoder stem (fp16, fp32 accumulate), optional fused GELU.
+ * Replaces  functional.conv1d -> TensorRT IConvolutionLayer  T/tensorrt_llm/functional.py:2202-2244,
+ *           layers.Conv1d T/tensorrt_llm/layers/conv.py:52-94 (use: T/tensorrt_llm/models/whisper/model.py:135-157).
+ * x [B, Cin, T]; w [Cout, Cin, ksize] (the reference's [out, in, k, 1] with the trailing 1 dropped);
+ * bias [Cout] or NULL; y [B, Cout, Tout], Tout = (T + 2*pad - ksize) / stride + 1.
+ * ---------------------------------------------------------------------------------------------- */
+int b200_conv1d_fp16(const void* x, const void* w, const void* bias, void* y, int batch_size, int c_in, int c_out,
+    int t_in, int ksize, int stride, int pad, int activation, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder-step glue (TensorRT-native layers in the reference:
+ * T/tensorrt_llm/models/whisper/model.py:74-118,257-292).
+ * ---------------------------------------------------------------------------------------------- */
+/* y = LayerNorm(x) * gamma + beta over the last dim; fp32 statistics like torch_model.py:25-27. */
+int b200_layernorm_fp16(const void* x, const void* gamma, const void* beta, void* y, int rows, int cols, float eps,
+    b200_stream_t stream);
+/* out[r, :] = tok_emb[tokens[r], :] + pos_emb[positions[r], :]   (torch_model.py:205-209) */
+int b200_embed_tokens_fp16(const int32_t* tokens, const int32_t* positions, const void* tok_emb, const void* pos_emb,
+    void* out, int rows, int cols, int vocab, int n_ctx, b200_stream_t stream);
+/* logits[r, v] = sum_k x[r, k] * emb[v, k]  (fp16 weights, not quantized: model.py:231,290), optionally also
+ * next_token[r] = argmax_v logits[r, v] (first index on ties, like torch.argmax on the fp32 logits).
+ * logits may be NULL when only the argmax is wanted.  workspace: b200_logits_workspace_bytes(). */
+size_t b200_logits_workspace_bytes(int rows, int vocab);
+int b200_logits_argmax_fp16(const void* x, const void* emb, void* logits_fp32, int32_t* next_token, int rows,
+    int cols, int vocab, void* workspace, size_t workspace_bytes, b200_stream_t stream);
+/* 0 = auto (tcgen05 fp16 GEMM), 1 = SIMT (tests / comparison). */
+int b200_logits_set_kernel_policy(int policy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_WHISPER_H */
