@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- decoder tokens/s of the quantized Whisper large-v2 decoder hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2]): Whisper large-v2 decoder, int8 weight-only + int8 self/cross KV cache
+(1500 encoder frames), batch 16 utterances per GPU, random-init weights and synthetic inputs.  A "step" is one
+greedy decoder step for the whole batch (16 tokens).  `value` = tokens/s with everything resident in HBM (CUDA-graph
+replays, token feedback on the device); `e2e` = the same through WhisperDecoding.step_host(): host token ids in
+(pinned, H2D), host token ids out (D2H) every step.  Each step streams ~2.9 GB (weights + cross-KV) >> 126 MB L2, so
+no explicit L2 flush is needed between steps.
+
+Multi-GPU: utterances are independent, so ranks run the identical per-GPU workload (weak scaling, no collective on the
+hot path); token ids are all-gathered once after the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decoder_tokens_per_s_large_v2_int8_bs16"
+UNIT = "tokens/s"
+BATCH = 16
+PROMPT = [50258, 50259, 50359]  # sot, <|en|>, <|transcribe|>  (T/examples/whisper/decoding.py:314-319)
+
+
+class Dims:
+    n_mels, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer = 80, 1500, 1280, 20, 32
+    n_vocab, n_text_ctx, n_text_state, n_text_head, n_text_layer = 51865, 448, 1280, 20, 32
+
+
+def gpu_state_dict(dims, device, seed=0):
+    """Random-init decoder weights with the checkpoint's key names, drawn directly on the GPU."""
+    import math
+
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    d = dims.n_text_state
+    sd = {}
+
+    def rn(*shape, std):
+        return (torch.randn(*shape, generator=g, device=device, dtype=torch.float32) * std).half()
+
+    sd["decoder.token_embedding.weight"] = rn(dims.n_vocab, d, std=0.1)
+    sd["decoder.positional_embedding"] = rn(dims.n_text_ctx, d, std=0.5)
+    for i in range(dims.n_text_layer):
+        p = f"decoder.blocks.{i}"
+        for a in ("attn", "cross_attn"):
+            for nm, bias in (("query", True), ("key", False), ("value", True), ("out", True)):
+                sd[f"{p}.{a}.{nm}.weight"] = rn(d, d, std=1 / math.sqrt(d))
+                if bias:
+                    sd[f"{p}.{a}.{nm}.bias"] = rn(d, std=0.02)
+            sd[f"{p}.{a}_ln.weight"] = 1 + rn(d, std=0.05)
+            sd[f"{p}.{a}_ln.bias"] = rn(d, std=0.02)
+        sd[f"{p}.mlp.0.weight"] = rn(4 * d, d, std=1 / math.sqrt(d))
+        sd[f"{p}.mlp.0.bias"] = rn(4 * d, std=0.02)
+        sd[f"{p}.mlp.2.weight"] = rn(d, 4 * d, std=1 / math.sqrt(4 * d))
+        sd[f"{p}.mlp.2.bias"] = rn(d, std=0.02)
+        sd[f"{p}.mlp_ln.weight"] = 1 + rn(d, std=0.05)
+        sd[f"{p}.mlp_ln.bias"] = rn(d, std=0.02)
+    sd["decoder.ln.weight"] = 1 + rn(d, std=0.05)
+    sd["decoder.ln.bias"] = rn(d, std=0.02)
+    return sd
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(steps, seconds_budget=25.0):
+    """The reference's PyTorch CPU path (summarize.py --test_torch -> torch_model + greedy loop), as restated by
+    oracle/whisper_oracle.py, fp32 on the host cores, large-v2 decoder, batch 16, cross K/V given (random), bounded
+    to `steps` generation steps.  Returns the cpu_baseline dict."""
+    import torch
+
+    from oracle import whisper_oracle as wo
+    torch.set_num_threads(os.cpu_count() or 1)
+    dims = wo.LARGE_V2
+    t0 = time.perf_counter()
+    sd = wo.synthetic_state_dict(dims, seed=0, decoder_only=True)
+    build_s = time.perf_counter() - t0
+    B = BATCH
+    state = wo.DecoderState(dims.n_text_layer)
+    g = torch.Generator().manual_seed(1)
+    for i in range(dims.n_text_layer):
+        state.ck[i] = torch.randn(B, dims.n_audio_ctx, dims.n_text_state, generator=g)
+        state.cv[i] = torch.randn(B, dims.n_audio_ctx, dims.n_text_state, generator=g)
+    xa = torch.zeros(B, 1, dims.n_text_state)  # unused: cross K/V are pre-filled
+    tokens = torch.tensor([PROMPT] * B)
+    with torch.no_grad():
+        logits, state = wo.decoder_forward(sd, dims, tokens, xa, state)  # context step, untimed
+        cur = logits[:, -1].argmax(-1)[:, None]
+        done = 0
+        t0 = time.perf_counter()
+        while done < steps and (time.perf_counter() - t0) < seconds_budget:
+            logits, state = wo.decoder_forward(sd, dims, cur, xa, state)
+            cur = logits[:, -1].argmax(-1)[:, None]
+            done += 1
+        dt = time.perf_counter() - t0
+    return {"value": B * done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} greedy decoder steps, batch {B}, large-v2 decoder fp32, cross K/V given; "
+                      f"oracle/whisper_oracle.py (restates T/examples/whisper/torch_model.py); weights built in {build_s:.1f}s",
+            "ms_per_step": 1e3 * dt / max(done, 1)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cb = cpu_baseline(max(args.steps, 1), seconds_budget=60.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "whisper-large-v2 decoder step, batch 16, 1500 encoder frames, CPU fp32 (reference PyTorch path)"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--layers", type=int, default=None, help="debug only: fewer decoder layers (result is INVALID)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import b200_whisper as bw
+    from b200_whisper.runtime import WhisperDecoding
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dims = Dims()
+    if args.layers:
+        dims.n_text_layer = args.layers
+    B = args.batch
+    lib = bw.load()
+    sd = gpu_state_dict(dims, dev, seed=rank)
+    L = dims.n_text_layer
+    dec = WhisperDecoding(dims, sd, B, kv_scales=[0.05] * L, cross_kv_scales=[0.03] * L, device=dev)
+    del sd
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    # synthetic int8 cross-KV cache (the encoder and CrossAttn_KV run once per utterance, outside the decoder step)
+    dec.set_cross_kv([torch.randint(-127, 128, (B, 2, dims.n_text_head, dims.n_audio_ctx, 64), generator=g, device=dev,
+                                    dtype=torch.int8) for _ in range(L)])
+    dec.reset()
+    dec.prefill([PROMPT] * B)
+    launches_before = lib.b200_launch_count()
+    if not args.no_graph:
+        dec.capture()
+    # capture() runs the step body twice (one warm-up, one captured)
+    launches_per_step = (lib.b200_launch_count() - launches_before) // 2 if not args.no_graph else None
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- value: device-resident steps -------------------------------------------------------------
+    for _ in range(args.warmup):
+        dec.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.b200_launch_count()
+    ev0.record()
+    for _ in range(args.steps):
+        dec.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    eager_launches = lib.b200_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # ---- e2e: host buffers in/out every step --------------------------------------------------------
+    import numpy as np
+    host_tokens = np.array(dec.next_tokens.cpu().numpy(), dtype=np.int32)
+    for _ in range(3):
+        host_tokens = dec.step_host(host_tokens).numpy().copy()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_tokens = dec.step_host(host_tokens).numpy().copy()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(te.item())
+
+    # ---- roofline of the dominant kernel (cross-attention: 68 % of the step's bytes at batch 16) -------
+    from b200_whisper import _lib as L_
+    q = torch.randn((B, dims.n_text_state), device=dev).half()
+    out = torch.empty_like(q)
+    reps = 3
+    def xattn(i):
+        lay = dec.layers[i % L]
+        L_.check(lib.b200_cross_attention(q.data_ptr(), dec.cross_kv[i % L].data_ptr(), lay["ckv_qo"].data_ptr(),
+                                          out.data_ptr(), B, 1, dims.n_text_head, 64, dims.n_audio_ctx, 1,
+                                          dec.ws.data_ptr(), dec.ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+    for i in range(L):
+        xattn(i)
+    torch.cuda.synchronize(dev)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for r in range(reps):
+        for i in range(L):  # 32 different caches (1.97 GB) per sweep: every launch misses L2
+            xattn(i)
+    k1.record()
+    torch.cuda.synchronize(dev)
+    xa_ms = k0.elapsed_time(k1) / (reps * L)
+    xa_bytes = 2 * dims.n_text_head * 64 * dims.n_audio_ctx * B  # 3.84 MB per sequence per call
+    peak, peak_src = measured_peak()
+    achieved = xa_bytes / (xa_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "cross_attention_kernel<int8> (+merge)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": xa_bytes, "avg_launch_ms": xa_ms}
+
+    # ---- per-GEMM numbers for the "GEMV HBM GB/s" half of the metric ------------------------------------
+    gemm_stats = {}
+    x16 = torch.randn((B, 5120), device=dev).half()
+    o16 = torch.empty((B, 5120), device=dev).half()
+    for name in ("qkv", "attn_out", "fc1", "fc2"):
+        lins = [lay[name] for lay in dec.layers]
+        def run(i):
+            lin = lins[i % L]
+            L_.check(lib.b200_woq_int8_gemm(x16.data_ptr(), B, lin.k, lin.weight.data_ptr(), lin.scales.data_ptr(), lin.n,
+                                            o16.data_ptr(), dec.ws.data_ptr(), dec.ws.numel(),
+                                            torch.cuda.current_stream(dev).cuda_stream))
+        for i in range(L):
+            run(i)
+        torch.cuda.synchronize(dev)
+        k0.record()
+        for r in range(reps):
+            for i in range(L):
+                run(i)
+        k1.record()
+        torch.cuda.synchronize(dev)
+        gms = k0.elapsed_time(k1) / (reps * L)
+        lin = lins[0]
+        gbytes = lin.k * lin.n + 2 * lin.n + 2 * B * lin.k + 2 * B * lin.n
+        gemm_stats[f"{name}_{lin.k}x{lin.n}_m{B}"] = {"avg_launch_us": 1e3 * gms, "GB/s": gbytes / (gms / 1e3) / 1e9,
+                                                     "frac_of_peak": gbytes / (gms / 1e3) / 1e9 / peak}
+
+    # algorithmic bytes of one whole step, for the step-level roofline fraction
+    d = dims.n_text_state
+    t_mid = len(PROMPT) + args.warmup + args.steps // 2
+    step_bytes = L * (12 * d * d) + L * 2 * (3 * d + 3 * d + 4 * d + 2 * d) + dims.n_vocab * d * 2 \
+        + B * L * 2 * d * dims.n_audio_ctx + B * L * 2 * d * t_mid
+    step_frac = step_bytes / (ms_max / args.steps / 1e3) / 1e9 / peak
+
+    if world > 1:
+        gathered = [torch.empty_like(dec.next_tokens) for _ in range(world)]
+        dist.all_gather(gathered, dec.next_tokens)  # the only collective: token ids, after the timed region
+
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(steps=8)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 activations x int8 weights, int8 KV (fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": "whisper-large-v2 decoder greedy step: int8 weight-only + int8 self/cross KV, "
+                                   f"batch {B} per GPU, 1500 encoder frames, {L} layers, fp16 logits over 51865 tokens",
+                       "batch_per_gpu": B, "l2": "inputs larger than L2 (about 2.9 GB streamed per step)",
+                       "cuda_graph": not args.no_graph, "valid": args.layers is None},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 4 * B},
+            "gpu_launches": int((launches_per_step or 0) * args.steps if launches_per_step else eager_launches),
+            "launches_per_step": launches_per_step,
+            "roofline": roofline,
+            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_peak": step_frac},
+            "kernels": gemm_stats,
+        }
+        if cb is not None:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,7 @@ from . import ops  # noqa: F401
 from . import functional  # noqa: F401
 from . import quantization  # noqa: F401
 from .quantization import QuantMode  # noqa: F401
+from . import runtime  # noqa: F401
 
 __all__ = ["ops", "functional", "quantization", "QuantMode", "load", "launch_count"]
 

@@ -1,0 +1,286 @@
+"""WhisperDecoding -- the quantized Whisper decoder (int8 weight-only + int8 self/cross KV cache) on one B200.
+
+Host-side counterpart of the reference's decoder runtime, T/examples/whisper/decoding.py (WhisperDecoding.decode
+:543-659, xa2cross_key_value :515-541, main_loop :785-821, GreedyDecoder :274-300) and of the graph the reference
+builds for it (T/tensorrt_llm/models/whisper/model.py:74-118 ResidualAttentionBlock, :201-300 WhisperDecoder,
+:469-555 CrossAttn_KV).  Differences that are the point of this repo:
+
+  * the GPTAttention plugin semantics are real here (preallocated int8 cache, in-place append, host/device scalars);
+    the reference's example builds the unfused graph by accident;
+  * cross-attention reads an int8 cross-KV cache through a split-KV streaming kernel;
+  * one decoder step is captured once in a CUDA graph and replayed; the greedy token feedback stays on the device
+    (the reference pays a Python engine launch and a stream synchronize per token, decoding.py:646-650).
+
+Everything numerical happens in libb200_whisper.so through the C ABI; torch provides device memory, streams and the
+CUDA-graph capture.  Batch elements are independent utterances (the multi-GPU sharding unit).
+"""
+import ctypes
+
+import torch
+
+from .. import _lib, ops
+from ..quantization.mode import QuantMode
+
+
+class _QLinear:
+    """Preprocessed int8 weight [K, N], fp16 per-channel scales [N], optional fp16 bias [N]."""
+
+    def __init__(self, weight_out_in, bias, device):
+        w_kn = weight_out_in.detach().to(device=device, dtype=torch.float16).t().contiguous()
+        self.k, self.n = w_kn.shape
+        self.weight, self.scales = ops.symmetric_quantize_last_axis_of_batched_matrix(w_kn, torch.int8)
+        self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float16).contiguous()
+
+
+def _cat_qkv(sd, p, device):
+    w = torch.cat([sd[p + ".query.weight"], sd[p + ".key.weight"], sd[p + ".value.weight"]], dim=0)
+    qb = sd[p + ".query.bias"]
+    b = torch.cat([qb, torch.zeros_like(qb), sd[p + ".value.bias"]], dim=0)  # key has no bias (weight.py:221-226)
+    return _QLinear(w, b, device)
+
+
+class WhisperDecoding:
+
+    def __init__(self, dims, state_dict, batch_size, kv_scales, cross_kv_scales, device="cuda",
+                 quant_mode=QuantMode.use_weight_only().set_int8_kv_cache(), n_audio_ctx=None):
+        """dims: object with n_vocab, n_text_ctx, n_text_state, n_text_head, n_text_layer, n_audio_ctx.
+        state_dict: OpenAI-style `model_state_dict` (decoder.* keys; fp32 or fp16 CPU/GPU tensors).
+        kv_scales / cross_kv_scales: per-layer scale_y_quant_orig (= max|y|/127, weight.py:236-243)."""
+        if not (quant_mode.is_int8_weight_only() and quant_mode.has_int8_kv_cache()):
+            raise ValueError("WhisperDecoding implements the int8 weight-only + int8 KV cache configuration")
+        self.lib = _lib.load()
+        _lib.check(self.lib.b200_init(), "b200_init")
+        self.dims = dims
+        self.B = batch_size
+        self.device = torch.device(device)
+        self.d = dims.n_text_state
+        self.H = dims.n_text_head
+        self.Dh = self.d // self.H
+        self.L = dims.n_text_layer
+        self.V = dims.n_vocab
+        self.Smax = dims.n_text_ctx
+        self.S_enc = n_audio_ctx or dims.n_audio_ctx
+        dev = self.device
+        sd = state_dict
+        f16 = lambda t: t.detach().to(device=dev, dtype=torch.float16).contiguous()  # noqa: E731
+
+        self.tok_emb = f16(sd["decoder.token_embedding.weight"])
+        self.pos_emb = f16(sd["decoder.positional_embedding"])
+        self.ln_w, self.ln_b = f16(sd["decoder.ln.weight"]), f16(sd["decoder.ln.bias"])
+        self.layers = []
+        for i in range(self.L):
+            p = f"decoder.blocks.{i}"
+            lay = {
+                "attn_ln": (f16(sd[p + ".attn_ln.weight"]), f16(sd[p + ".attn_ln.bias"])),
+                "qkv": _cat_qkv(sd, p + ".attn", dev),
+                "attn_out": _QLinear(sd[p + ".attn.out.weight"], sd[p + ".attn.out.bias"], dev),
+                "cross_ln": (f16(sd[p + ".cross_attn_ln.weight"]), f16(sd[p + ".cross_attn_ln.bias"])),
+                "cross_q": _QLinear(sd[p + ".cross_attn.query.weight"], sd[p + ".cross_attn.query.bias"], dev),
+                "cross_k": _QLinear(sd[p + ".cross_attn.key.weight"], None, dev),
+                "cross_v": _QLinear(sd[p + ".cross_attn.value.weight"], sd[p + ".cross_attn.value.bias"], dev),
+                "cross_out": _QLinear(sd[p + ".cross_attn.out.weight"], sd[p + ".cross_attn.out.bias"], dev),
+                "mlp_ln": (f16(sd[p + ".mlp_ln.weight"]), f16(sd[p + ".mlp_ln.bias"])),
+                "fc1": _QLinear(sd[p + ".mlp.0.weight"], sd[p + ".mlp.0.bias"], dev),
+                "fc2": _QLinear(sd[p + ".mlp.2.weight"], sd[p + ".mlp.2.bias"], dev),
+                # kv_orig_quant_scale = 1/t, kv_quant_orig_scale = t (weight.py:242-243)
+                "kv_oq": torch.tensor([1.0 / kv_scales[i]], dtype=torch.float32, device=dev),
+                "kv_qo": torch.tensor([kv_scales[i]], dtype=torch.float32, device=dev),
+                "ckv_oq": torch.tensor([1.0 / cross_kv_scales[i]], dtype=torch.float32, device=dev),
+                "ckv_qo": torch.tensor([cross_kv_scales[i]], dtype=torch.float32, device=dev),
+            }
+            self.layers.append(lay)
+
+        B, d = self.B, self.d
+        self.self_kv = [torch.zeros((B, 2, self.H, self.Smax, self.Dh), dtype=torch.int8, device=dev)
+                        for _ in range(self.L)]
+        self.cross_kv = [None] * self.L
+        self.seq_len = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.tokens = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.next_tokens = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.logits = torch.empty((B, self.V), dtype=torch.float32, device=dev)
+        self._bufs = {}
+        max_rows = B * 8
+        ws_bytes = max(self.lib.b200_woq_workspace_bytes(max(max_rows, B * self.S_enc), 4 * d, 4 * d),
+                       self.lib.b200_cross_attention_workspace_bytes(max_rows, self.H, self.Dh, self.S_enc), 1 << 20)
+        self.ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        self.graph = None
+        self._pinned_in = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
+        self._pinned_out = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
+
+    # ---- thin wrappers over the C ABI (pointers only; no torch math) --------------------------------------
+    def _st(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _gemm(self, x, rows, lin, out, bias=True, act=_lib.ACT_NONE, residual=None):
+        rc = self.lib.b200_woq_int8_gemm_fused(
+            x.data_ptr(), rows, lin.k, lin.weight.data_ptr(), lin.scales.data_ptr(), lin.n,
+            lin.bias.data_ptr() if (bias and lin.bias is not None) else None, act,
+            residual.data_ptr() if residual is not None else None, out.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+            self._st())
+        _lib.check(rc, "woq gemm")
+
+    def _ln(self, x, wb, out, rows):
+        _lib.check(self.lib.b200_layernorm_fp16(x.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), out.data_ptr(), rows,
+                                                self.d, 1e-5, self._st()), "layernorm")
+
+    def _buf(self, name, rows, cols):
+        key = (name, rows, cols)
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty((rows, cols), dtype=torch.float16, device=self.device)
+        return self._bufs[key]
+
+    # ---- cross-KV (the cross_kv_cache_warping model: CrossAttn_KV, model.py:469-555) ---------------------------
+    def set_encoder_output(self, xa):
+        """xa [B, S_enc, d] fp16: computes the int8 cross-KV cache of every layer (K has no bias, V has one,
+        torch_model.py:62-63)."""
+        B, S, d = xa.shape
+        assert B == self.B and S == self.S_enc and d == self.d
+        x = xa.to(device=self.device, dtype=torch.float16).contiguous().view(B * S, d)
+        k = torch.empty((B * S, d), dtype=torch.float16, device=self.device)
+        v = torch.empty_like(k)
+        for i, lay in enumerate(self.layers):
+            self._gemm(x, B * S, lay["cross_k"], k, bias=False)
+            self._gemm(x, B * S, lay["cross_v"], v)
+            if self.cross_kv[i] is None:
+                self.cross_kv[i] = torch.empty((B, 2, self.H, S, self.Dh), dtype=torch.int8, device=self.device)
+            rc = self.lib.b200_cross_kv_pack(k.data_ptr(), v.data_ptr(), self.cross_kv[i].data_ptr(),
+                                             lay["ckv_oq"].data_ptr(), B, S, self.H, self.Dh, 1, self._st())
+            _lib.check(rc, "cross_kv_pack")
+
+    def set_cross_kv(self, caches):
+        """Installs precomputed int8 cross-KV caches [B, 2, H, S_enc, Dh] (synthetic benchmarks)."""
+        assert len(caches) == self.L
+        self.cross_kv = [c.to(self.device) for c in caches]
+
+    def reset(self):
+        self.seq_len.zero_()
+
+    # ---- one pass over the decoder stack for `rows` query rows ----------------------------------------------
+    def _stack(self, x, rows, s_q, context, input_lengths=None):
+        d, H, Dh = self.d, self.H, self.Dh
+        h = self._buf("h", rows, d)
+        qkv = self._buf("qkv", rows, 3 * d)
+        ctx = self._buf("ctx", rows, d)
+        q = self._buf("q", rows, d)
+        u = self._buf("u", rows, 4 * d)
+        st = self._st()
+        for i, lay in enumerate(self.layers):
+            self._ln(x, lay["attn_ln"], h, rows)
+            self._gemm(h, rows, lay["qkv"], qkv)
+            if context:
+                rc = self.lib.b200_attention_context(
+                    qkv.data_ptr(), input_lengths.data_ptr() if input_lengths is not None else None, ctx.data_ptr(),
+                    self.self_kv[i].data_ptr(), lay["kv_oq"].data_ptr(), self.B, s_q, H, Dh, self.Smax, 1, 1.0, st)
+                _lib.check(rc, "attention_context")
+            else:
+                p = _lib.MmhaParams()
+                p.qkv, p.qkv_bias, p.out = qkv.data_ptr(), None, ctx.data_ptr()
+                p.kv_cache = self.self_kv[i].data_ptr()
+                p.sequence_lengths = self.seq_len.data_ptr()
+                p.masked_tokens = None
+                p.kv_scale_orig_quant = lay["kv_oq"].data_ptr()
+                p.kv_scale_quant_orig = lay["kv_qo"].data_ptr()
+                p.batch_size, p.num_heads, p.head_size = self.B, H, Dh
+                p.max_seq_len, p.past_kv_length, p.int8_kv_cache, p.q_scaling = self.Smax, 0, 1, 1.0
+                _lib.check(self.lib.b200_mmha_generation(ctypes.byref(p), st), "mmha_generation")
+            self._gemm(ctx, rows, lay["attn_out"], x, residual=x)
+            self._ln(x, lay["cross_ln"], h, rows)
+            self._gemm(h, rows, lay["cross_q"], q)
+            rc = self.lib.b200_cross_attention(q.data_ptr(), self.cross_kv[i].data_ptr(), lay["ckv_qo"].data_ptr(),
+                                               ctx.data_ptr(), rows, s_q, H, Dh, self.S_enc, 1, self.ws.data_ptr(),
+                                               self.ws.numel(), st)
+            _lib.check(rc, "cross_attention")
+            self._gemm(ctx, rows, lay["cross_out"], x, residual=x)
+            self._ln(x, lay["mlp_ln"], h, rows)
+            self._gemm(h, rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF)
+            self._gemm(u, rows, lay["fc2"], x, residual=x)
+        return x
+
+    def _head(self, x_rows, rows, logits, next_tokens):
+        h = self._buf("hf", rows, self.d)
+        self._ln(x_rows, (self.ln_w, self.ln_b), h, rows)
+        rc = self.lib.b200_logits_argmax_fp16(h.data_ptr(), self.tok_emb.data_ptr(), logits.data_ptr(),
+                                              next_tokens.data_ptr(), rows, self.d, self.V, None, 0, self._st())
+        _lib.check(rc, "logits_argmax")
+
+    # ---- public API ----------------------------------------------------------------------------------------
+    def prefill(self, prompt_tokens):
+        """Context phase: prompt_tokens [B, S] int (all sequences the same length, like the reference's
+        sot/language/task prompt, decoding.py:314-319).  Returns the first generated tokens [B] (device int32)."""
+        B = self.B
+        prompt = torch.as_tensor(prompt_tokens, dtype=torch.int32, device=self.device).view(B, -1).contiguous()
+        S = prompt.shape[1]
+        rows = B * S
+        pos = torch.arange(S, dtype=torch.int32, device=self.device).repeat(B)
+        x = self._buf("x", rows, self.d)
+        _lib.check(self.lib.b200_embed_tokens_fp16(prompt.data_ptr(), pos.data_ptr(), self.tok_emb.data_ptr(),
+                                                   self.pos_emb.data_ptr(), x.data_ptr(), rows, self.d, self.V,
+                                                   self.Smax, self._st()), "embed")
+        self._stack(x, rows, S, context=True)
+        last = x.view(B, S, self.d)[:, S - 1, :].contiguous()
+        self._head(last, B, self.logits, self.next_tokens)
+        self.seq_len.fill_(S)
+        self.tokens.copy_(self.next_tokens)
+        return self.next_tokens
+
+    def _step_body(self):
+        B = self.B
+        x = self._buf("x", B, self.d)
+        _lib.check(self.lib.b200_embed_tokens_fp16(self.tokens.data_ptr(), self.seq_len.data_ptr(),
+                                                   self.tok_emb.data_ptr(), self.pos_emb.data_ptr(), x.data_ptr(), B,
+                                                   self.d, self.V, self.Smax, self._st()), "embed")
+        self._stack(x, B, 1, context=False)
+        self._head(x, B, self.logits, self.next_tokens)
+        self.seq_len.add_(1)
+        self.tokens.copy_(self.next_tokens)
+
+    def capture(self):
+        """Captures one generation step in a CUDA graph (all shapes static; lengths and tokens live on the device)."""
+        # warm-up outside capture: sets function attributes, allocates buffers
+        saved = self.seq_len.clone()
+        saved_tokens = self.tokens.clone()
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._step_body()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.seq_len.copy_(saved)
+        self.tokens.copy_(saved_tokens)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body()
+        torch.cuda.synchronize(self.device)
+        self.seq_len.copy_(saved)
+        self.tokens.copy_(saved_tokens)
+        self.graph = g
+        return g
+
+    def step(self):
+        """One greedy generation step for the whole batch; consumes self.tokens, produces self.next_tokens."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        return self.next_tokens
+
+    def step_host(self, tokens_host=None):
+        """End-to-end step with HOST buffers: pinned token ids in -> pinned next-token ids out."""
+        if tokens_host is not None:
+            self._pinned_in.copy_(torch.as_tensor(tokens_host, dtype=torch.int32))
+            self.tokens.copy_(self._pinned_in, non_blocking=True)
+        self.step()
+        self._pinned_out.copy_(self.next_tokens, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._pinned_out
+
+    def decode(self, prompt_tokens, n_new, use_graph=True):
+        """Greedy decode (logit filters off): returns int32 [B, n_new] on the device."""
+        self.reset()
+        out = torch.empty((self.B, n_new), dtype=torch.int32, device=self.device)
+        out[:, 0] = self.prefill(prompt_tokens)
+        if use_graph and self.graph is None and n_new > 1:
+            self.capture()
+        for t in range(1, n_new):
+            out[:, t] = self.step() if use_graph else (self._step_body() or self.next_tokens)
+        return out

@@ -1,0 +1,85 @@
+"""CPU tests: the C-ABI library builds for sm_100a, loads, exports every symbol include/b200_whisper.h declares, and
+fails loudly (no fallback) without a GPU.  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    so = os.path.join(ROOT, "eddie-wang-hackathon2023_b200", "lib", "libb200_whisper.so")
+    if not os.path.exists(so):
+        __graft_entry__.build()
+    import b200_whisper
+    return b200_whisper.load()
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "b200_whisper.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200_whisper.h but not exported"
+    from b200_whisper import _lib
+    assert set(_lib.declared_symbols()) <= set(names) | {"b200_init"}
+
+
+def test_sass_is_blackwell_native():
+    so = os.path.join(ROOT, "eddie-wang-hackathon2023_b200", "lib", "libb200_whisper.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UBLKCP", "LDTM", "STTM"):
+        assert mnemonic in sass, f"{mnemonic} missing from SASS"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a GPU-less machine")
+def test_no_cpu_fallback(lib):
+    import b200_whisper as bw
+    with pytest.raises(RuntimeError, match="no CPU fallback|no sm_100"):
+        bw.ops.symmetric_quantize_last_axis_of_batched_matrix(torch.zeros((64, 64), dtype=torch.float16))
+    x = torch.zeros((1, 64), dtype=torch.float16)
+    rc = lib.b200_woq_int8_gemm(x.data_ptr(), 1, 64, x.data_ptr(), x.data_ptr(), 64, x.data_ptr(), None, 0, None)
+    assert rc == 3 and b"no CPU fallback" in lib.b200_last_error()
+
+
+def test_argument_validation_without_gpu(lib):
+    # argument errors are reported before any device work
+    rc = lib.b200_woq_int8_gemm(None, 1, 64, None, None, 64, None, None, 0, None)
+    assert rc == 1
+    assert lib.b200_woq_workspace_bytes(16, 1280, 1280) > 0
+    assert lib.b200_cross_attention_workspace_bytes(16, 20, 64, 1500) > 0
+
+
+def test_quant_mode_flags():
+    # T/tests/quantization/test_mode.py
+    from b200_whisper import QuantMode
+    qm = QuantMode.ACTIVATIONS | QuantMode.INT8_WEIGHTS
+    assert qm._all(QuantMode.ACTIVATIONS | QuantMode.INT8_WEIGHTS) and not qm._all(QuantMode.ACTIVATIONS)
+    assert qm._all(QuantMode.ACTIVATIONS, mask=QuantMode.ACTIVATIONS)
+    assert qm._any(QuantMode.ACTIVATIONS) and not qm._any(QuantMode.PER_TOKEN)
+    assert QuantMode.COUNT.value == 1 << 7
+    assert QuantMode.from_description(True, False, False, False) == QuantMode.INT8_WEIGHTS
+    assert QuantMode.use_weight_only() == QuantMode.INT8_WEIGHTS
+    assert QuantMode.use_weight_only(True) == QuantMode.INT4_WEIGHTS
+    assert QuantMode.from_description(True, True, False, False) == QuantMode.ACTIVATIONS | QuantMode.INT8_WEIGHTS
+    assert QuantMode.use_smooth_quant(True, True) == (QuantMode.ACTIVATIONS | QuantMode.INT8_WEIGHTS
+                                                      | QuantMode.PER_TOKEN | QuantMode.PER_CHANNEL)
+    with pytest.raises(ValueError):
+        QuantMode.from_description(False, True)
+    with pytest.raises(ValueError):
+        QuantMode.from_description(True, False, per_token=True)
+    m = QuantMode.use_weight_only().set_int8_kv_cache()
+    assert m.is_int8_weight_only() and m.is_weight_only() and m.has_int8_kv_cache() and not m.has_fp8_kv_cache()
+    assert m.has_any_quant() and not QuantMode(0).has_any_quant()

@@ -1,0 +1,178 @@
+"""GPU parity of the attention kernels through the operator API (gpt_attention / cross_attention).
+
+The generation/context procedure follows T/tests/attention/test_gpt_attention.py (:52-56 int8-KV cases, :325-331 scale
+ranges, :445-449 masked_tokens, :580-831 step loop): a context step over `in_len` tokens (half of them padding) and 7
+generation steps, batch 2, 4 heads x 64, max_seq_len = in_len + 24, inputs ~1e-3, tolerances ctx 5e-3 / gen 2e-3.
+The reference compares with HF GPT2Attention; here the fp32 torch attention below is that reference.
+int8 cache writes are checked bit-exactly like T/cpp/tests/runtime/transposeKVKernelTest.cpp:79-147.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import woq
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_attention(q, k, v, key_mask=None):
+    """q [B,H,Sq,D], k/v [B,H,Sk,D] fp32; key_mask [B,Sq,Sk] bool (True = visible)."""
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
+    if key_mask is not None:
+        s = s.masked_fill(~key_mask[:, None], float("-inf"))
+    return torch.softmax(s, dim=-1) @ v
+
+
+def split_heads(x, H):
+    B, S, hidden = x.shape
+    return x.view(B, S, H, hidden // H).permute(0, 2, 1, 3).float()
+
+
+@pytest.mark.parametrize("int8", [True, False])
+@pytest.mark.parametrize("in_len", [128, 4])
+def test_context_then_generation(int8, in_len):
+    from b200_whisper.functional import gpt_attention
+    torch.manual_seed(42)
+    B, H, D = 2, 4, 64
+    hidden = H * D
+    max_seq = in_len + 24
+    dev = "cuda"
+    scale_mag = 1e-3 if in_len == 128 else 1.0
+    kv_dequant = torch.tensor([5e-4 if in_len == 128 else 0.05], dtype=torch.float32, device=dev)
+    kv_quant = 1.0 / kv_dequant
+    cache = torch.zeros((B, 2, H, max_seq, D), dtype=torch.int8 if int8 else torch.float16, device=dev)
+    input_lengths = torch.full((B,), max(in_len // 2, 1), dtype=torch.int32, device=dev)
+    if in_len == 4:
+        input_lengths[:] = in_len  # Whisper prompts are not padded
+    masked_tokens = torch.zeros((B, max_seq), dtype=torch.int32, device=dev)
+    for i in range(B):
+        masked_tokens[i, int(input_lengths[i]):in_len] = 1
+    cache_ind = torch.zeros((B, 1, max_seq), dtype=torch.int32, device=dev)
+    max_in = torch.zeros((in_len,), dtype=torch.int32, device=dev)
+    L = int(input_lengths[0])
+
+    # ---- context ----
+    qkv = (torch.randn((B, in_len, 3 * hidden), device=dev) * scale_mag).half()
+    seq_len = torch.full((B,), in_len, dtype=torch.int32, device=dev)
+    out, cache = gpt_attention(qkv, cache, seq_len, torch.tensor([0, 1], dtype=torch.int32), masked_tokens,
+                               input_lengths, max_in, cache_ind, H, D, 1.0, 0, False, False, False, kv_quant, kv_dequant,
+                               int8)
+    torch.cuda.synchronize()
+    q, k, v = [split_heads(t, H) for t in qkv.float().split(hidden, dim=-1)]
+    causal = torch.tril(torch.ones(in_len, in_len, dtype=torch.bool, device=dev))
+    vis = causal[None] & (torch.arange(in_len, device=dev)[None, None, :] < input_lengths[:, None, None])
+    ref = ref_attention(q, k, v, vis).permute(0, 2, 1, 3).reshape(B, in_len, hidden)
+    err = (out.float()[:, :L] - ref[:, :L]).abs().max().item()
+    assert err <= 5e-3 * max(scale_mag, 1e-3) / 1e-3 * 1e-3 + 5e-3 * scale_mag, f"context err {err}"
+    # cache contents: bit-exact int8 quantization of the valid rows, zeros in the padded rows
+    kc = cache[:, 0, :, :in_len].cpu()
+    vc = cache[:, 1, :, :in_len].cpu()
+    if int8:
+        k16 = qkv[..., hidden:2 * hidden].view(B, in_len, H, D).permute(0, 2, 1, 3).cpu().numpy()
+        v16 = qkv[..., 2 * hidden:].view(B, in_len, H, D).permute(0, 2, 1, 3).cpu().numpy()
+        ek = woq.kv_quantize_int8(np.ascontiguousarray(k16), float(kv_quant))
+        ev = woq.kv_quantize_int8(np.ascontiguousarray(v16), float(kv_quant))
+        assert np.array_equal(kc.numpy()[:, :, :L], ek[:, :, :L])
+        assert np.array_equal(vc.numpy()[:, :, :L], ev[:, :, :L])
+        assert (kc.numpy()[:, :, L:] == 0).all()
+    past_k = k.clone()
+    past_v = v.clone()
+    if int8:
+        past_k = cache[:, 0, :, :in_len].float() * kv_dequant
+        past_v = cache[:, 1, :, :in_len].float() * kv_dequant
+        past_k = past_k.half().float()
+        past_v = past_v.half().float()
+
+    # ---- generation ----
+    for step in range(1, 8):
+        past_len = in_len + step - 1
+        qkv1 = (torch.randn((B, 1, 3 * hidden), device=dev) * scale_mag).half()
+        seq_len = torch.full((B,), past_len, dtype=torch.int32, device=dev)
+        out, cache = gpt_attention(qkv1, cache, seq_len, torch.tensor([past_len, 0], dtype=torch.int32), masked_tokens,
+                                   input_lengths, max_in, cache_ind, H, D, 1.0, 0, False, False, False, kv_quant,
+                                   kv_dequant, int8)
+        torch.cuda.synchronize()
+        q1, k1, v1 = [split_heads(t, H) for t in qkv1.float().split(hidden, dim=-1)]
+        k_all = torch.cat([past_k, k1], dim=2)
+        v_all = torch.cat([past_v, v1], dim=2)
+        vis = torch.ones((B, 1, past_len + 1), dtype=torch.bool, device=dev)
+        vis[:, 0, :past_len] = masked_tokens[:, :past_len] == 0
+        ref = ref_attention(q1, k_all, v_all, vis).permute(0, 2, 1, 3).reshape(B, 1, hidden)
+        err = (out.float() - ref).abs().max().item()
+        assert err <= 2e-3 * max(scale_mag / 1e-3 * 1e-3, 1e-3) + 2e-3 * scale_mag, f"generation step {step} err {err}"
+        # the new token must now be in the cache (quantized), and is what later steps attend to
+        if int8:
+            newk = cache[:, 0, :, past_len].float() * kv_dequant
+            newv = cache[:, 1, :, past_len].float() * kv_dequant
+            ek = woq.kv_quantize_int8(np.ascontiguousarray(k1[:, :, 0].half().cpu().numpy()), float(kv_quant))
+            assert np.array_equal(cache[:, 0, :, past_len].cpu().numpy(), ek)
+            past_k = torch.cat([past_k, newk.half().float()[:, :, None]], dim=2)
+            past_v = torch.cat([past_v, newv.half().float()[:, :, None]], dim=2)
+        else:
+            past_k, past_v = k_all, v_all
+
+
+@pytest.mark.parametrize("B,H,S", [(1, 20, 1500), (16, 20, 1500), (3, 6, 1500), (2, 2, 96), (5, 4, 333)])
+@pytest.mark.parametrize("int8", [True, False])
+def test_cross_attention(B, H, S, int8):
+    from b200_whisper.functional import cross_attention, cross_kv_pack
+    torch.manual_seed(B * 131 + S)
+    D = 64
+    dev = "cuda"
+    k = torch.randn((B, S, H * D), device=dev).half()
+    v = torch.randn((B, S, H * D), device=dev).half()
+    q = (torch.randn((B, H * D), device=dev) * 1.5).half()
+    t = float(max(k.abs().max(), v.abs().max())) / 127.0
+    oq = torch.tensor([1.0 / t], dtype=torch.float32, device=dev)
+    qo = torch.tensor([t], dtype=torch.float32, device=dev)
+    cache = cross_kv_pack(k, v, oq, H, D, int8)
+    if int8:
+        ek = woq.kv_quantize_int8(k.view(B, S, H, D).permute(0, 2, 1, 3).contiguous().cpu().numpy(), float(oq))
+        assert np.array_equal(cache[:, 0].cpu().numpy(), ek)
+        kd = (cache[:, 0].float() * qo).half().float()
+        vd = (cache[:, 1].float() * qo).half().float()
+    else:
+        kd, vd = cache[:, 0].float(), cache[:, 1].float()
+    out = cross_attention(q, cache, qo, H, D, int8)
+    torch.cuda.synchronize()
+    ref = ref_attention(q.float().view(B, H, 1, D), kd, vd).reshape(B, H * D)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"cross attention err {err}"
+
+
+def test_cross_attention_multi_query_rows():
+    """Context phase: S_q prompt rows per sequence attend to their sequence's cache."""
+    from b200_whisper.functional import cross_attention, cross_kv_pack
+    torch.manual_seed(5)
+    B, H, D, S, Sq = 3, 4, 64, 200, 4
+    dev = "cuda"
+    k = torch.randn((B, S, H * D), device=dev).half()
+    v = torch.randn((B, S, H * D), device=dev).half()
+    q = torch.randn((B * Sq, H * D), device=dev).half()
+    one = torch.ones((1,), dtype=torch.float32, device=dev)
+    cache = cross_kv_pack(k, v, one, H, D, False)
+    out = cross_attention(q, cache, one, H, D, False)
+    torch.cuda.synchronize()
+    qq = q.float().view(B, Sq, H, D).permute(0, 2, 1, 3)
+    ref = ref_attention(qq, cache[:, 0].float(), cache[:, 1].float()).permute(0, 2, 1, 3).reshape(B * Sq, H * D)
+    assert (out.float() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+def test_attention_argument_errors():
+    from b200_whisper.functional import gpt_attention
+    dev = "cuda"
+    qkv = torch.zeros((1, 1, 3 * 64), dtype=torch.float16, device=dev)
+    cache = torch.zeros((1, 2, 1, 8, 64), dtype=torch.float16, device=dev)
+    z = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ci = torch.zeros((1, 1, 8), dtype=torch.int32, device=dev)
+    with pytest.raises(ValueError):  # past_key_value_length on the GPU: the reference's example bug
+        gpt_attention(qkv, cache, z, torch.tensor([0, 1], dtype=torch.int32, device=dev), None, z, z, ci, 1, 64, 1.0, 0,
+                      False, False, False, None, None, False)
+    with pytest.raises(RuntimeError):  # past length beyond the cache capacity
+        gpt_attention(qkv, cache, z, torch.tensor([8, 0], dtype=torch.int32), None, z, z, ci, 1, 64, 1.0, 0, False,
+                      False, False, None, None, False)
+    with pytest.raises(NotImplementedError):
+        gpt_attention(qkv, cache, z, torch.tensor([0, 1], dtype=torch.int32), None, z, z, ci, 1, 64, 1.0, 32, False,
+                      False, False, None, None, False)

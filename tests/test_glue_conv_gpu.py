@@ -1,0 +1,73 @@
+"""GPU parity of the glue kernels and the Conv1d stem against torch fp32 (tolerances stated per test).
+Conv1d has no test in the reference ('parity unpinned'); the pin is torch.nn.functional.conv1d, which
+is what the oracle model uses (T/examples/whisper/torch_model.py:39-45,157-158)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1280), (16, 1280), (7, 384), (3, 128), (2, 5120)])
+def test_layernorm(rows, cols):
+    from b200_whisper.functional import layer_norm
+    torch.manual_seed(rows)
+    x = (torch.randn((rows, cols), device="cuda") * 3 + 0.5).half()
+    w = (1 + 0.1 * torch.randn(cols, device="cuda")).half()
+    b = (0.1 * torch.randn(cols, device="cuda")).half()
+    y = layer_norm(x, (cols,), w, b, 1e-5)
+    ref = F.layer_norm(x.float(), (cols,), w.float(), b.float(), 1e-5)
+    assert (y.float() - ref).abs().max().item() <= 4e-3  # fp16 output rounding of O(4) values
+
+
+def test_embedding():
+    from b200_whisper.functional import embedding_with_position
+    torch.manual_seed(0)
+    V, C, d = 1000, 64, 128
+    te = torch.randn((V, d), device="cuda").half()
+    pe = torch.randn((C, d), device="cuda").half()
+    tok = torch.tensor([0, 5, 999, 17], dtype=torch.int32, device="cuda")
+    pos = torch.tensor([0, 1, 63, 2], dtype=torch.int32, device="cuda")
+    out = embedding_with_position(tok, pos, te, pe)
+    assert torch.equal(out, te[tok.long()] + pe[pos.long()])
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("rows,cols,vocab", [(1, 1280, 51865), (16, 1280, 51865), (2, 128, 1024), (5, 384, 51865), (40, 128, 1000)])
+def test_logits_argmax(policy, rows, cols, vocab):
+    from b200_whisper import _lib
+    from b200_whisper.functional import logits_argmax
+    lib = _lib.load()
+    torch.manual_seed(rows + vocab)
+    x = torch.randn((rows, cols), device="cuda").half()
+    emb = (torch.randn((vocab, cols), device="cuda") * 0.1).half()
+    _lib.check(lib.b200_logits_set_kernel_policy(policy))
+    try:
+        logits, tok = logits_argmax(x, emb)
+        torch.cuda.synchronize()
+    finally:
+        lib.b200_logits_set_kernel_policy(0)
+    ref = x.float() @ emb.float().t()
+    assert (logits - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-4
+    assert torch.equal(tok.long(), logits.argmax(dim=-1))  # argmax consistent with the logits it was computed from
+    # and equal to the fp32 reference argmax wherever the top-2 margin is not a rounding tie
+    top2 = ref.topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+    assert torch.equal(tok.long()[clear], ref.argmax(dim=-1)[clear])
+
+
+@pytest.mark.parametrize("B,cin,cout,T,stride", [(1, 80, 1280, 3000, 1), (2, 80, 384, 3000, 1), (1, 1280, 1280, 3000, 2),
+                                                 (2, 128, 128, 192, 2), (1, 80, 128, 191, 1), (3, 48, 72, 77, 2)])
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_conv1d(B, cin, cout, T, stride, act):
+    from b200_whisper.functional import conv1d
+    torch.manual_seed(cin + T)
+    x = torch.randn((B, cin, T), device="cuda").clamp(-1, 1).half()
+    w = (torch.randn((cout, cin, 3), device="cuda") / (3 * cin) ** 0.5).half()
+    b = (torch.randn((cout,), device="cuda") * 0.02).half()
+    y = conv1d(x, w.unsqueeze(-1), b, stride=stride, padding=1, activation=act)  # reference weight shape [out,in,k,1]
+    ref = F.conv1d(x.float(), w.float(), b.float(), stride=stride, padding=1)
+    if act:
+        ref = F.gelu(ref)
+    assert y.shape == ref.shape
+    assert (y.float() - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())
