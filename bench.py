@@ -190,6 +190,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer decoder layers (result is INVALID)")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling aid: run ONE eager decoder step between cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,6 +229,16 @@ def main():
                                     dtype=torch.int8) for _ in range(L)])
     dec.reset()
     dec.prefill([PROMPT] * B)
+    if args.profile:
+        for _ in range(2):
+            dec.step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        dec.step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        print("profiled one eager decoder step", flush=True)
+        return
     launches_before = lib.b200_launch_count()
     if not args.no_graph:
         dec.capture()

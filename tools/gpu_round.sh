@@ -13,6 +13,7 @@ run() { # name, timeout, args...
   tail -n 3 gpurun_out/$name.log | tee -a gpurun_out/summary.txt
 }
 : > gpurun_out/summary.txt
+python __graft_entry__.py build > gpurun_out/build.log 2>&1; tail -n 2 gpurun_out/build.log | tee -a gpurun_out/summary.txt
 run quant 600 tests/test_quantize_gpu.py
 run woq_simt 600 tests/test_woq_matmul_gpu.py -k "simt or errors"
 run woq_tc 900 tests/test_woq_matmul_gpu.py -k "tc or auto or linearity"
