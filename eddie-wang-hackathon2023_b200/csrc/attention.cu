@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(128) mmha_generation_kernel(const b200_mmha_pa
     const int chunk = lane & 3, kl = lane >> 2;
 
     grid_dep_wait();
+    grid_dep_launch_dependents();
 
     int tlen = p.sequence_lengths ? p.sequence_lengths[b] : p.past_kv_length;
     tlen = min(tlen, Smax - 1);
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     grid_dep_wait();
+    grid_dep_launch_dependents();
 
     const int len = input_lengths ? min(input_lengths[b], S) : S;
     const float s_oq = INT8 ? kv_scale_orig_quant[0] : 1.f;
@@ -446,30 +448,63 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
 // =====================================================================================================
 // Cross-attention over a (typically int8) cross-KV cache [B, 2, H, S, 64]: the dominant byte stream of the
 // decoder step at batch >= 6 (3.84 MB per sequence per layer).  HBM-bound streaming design:
-//   * persistent CTAs, work item = (b, h, split): a contiguous key range, so K and V of an item are two
-//     contiguous byte ranges -> 1-D TMA bulk copies (UBLKCP) into a shared-memory ring by a producer warp,
-//     running ahead across items;
-//   * 8 consumer warps: all K stages of the item -> scores in shared memory -> softmax numerators -> all V
-//     stages -> fp32 (m, l, o[64]) partial;  partials of the splits are merged by a second tiny kernel
-//     (or written directly when nsplit == 1).
-// Scores use sum(q_d * k_int) * (scale * inv_sqrt_dh): the dequant multiply is hoisted out of the dot product.
+//   * persistent CTAs (up to 4 per SM), work item = (query row, head, split): a contiguous key range, so K and V
+//     of an item are two contiguous byte ranges -> 1-D TMA bulk copies (UBLKCP) into a shared-memory ring by a
+//     producer warp that runs ahead across items;
+//   * 8 consumer warps, lane geometry 4 lanes x 16 dims per key, 8 keys per warp instruction (a warp reads 512
+//     contiguous bytes): K stages -> scores in shared memory -> softmax numerators -> V stages -> fp32 (m, l, o[64])
+//     partial; the last split of a (row, head) to finish merges the partials (arrival counter), so there is no
+//     separate merge launch;
+//   * instruction economy (the first version was issue-bound at 6.7 thread-instructions per byte): int8 -> fp16 by
+//     xor 0x80 + PRMT + HSUB2 (exact integers), products chained four at a time with HFMA2 and flushed to fp32
+//     (same scheme as the GEMV), the dequant scale hoisted out of both dot products.
 // =====================================================================================================
 constexpr int kXaStageKeys = 128;
-constexpr int kXaStages = 6;
+constexpr int kXaStages = 5;
 constexpr int kXaWarps = 8;
+constexpr int kXaMaxCtasPerSm = 4;
 
 struct XAttnParams
 {
-    const __half* q;   // [B, H*64]
+    const __half* q;   // [R, H*64]
     const void* kv;    // [B, 2, H, S, 64]
     const float* scale_quant_orig;
-    __half* out;       // [B, H*64]
-    float* partials;   // [B*H*nsplit][66]
-    int B, H, S;      // B = number of query rows
-    int q_per_seq;    // query rows per cache sequence (1 in the generation phase, S_prompt in the context phase)
+    __half* out;       // [R, H*64]
+    float* partials;   // [R*H*nsplit][66]
+    int* counters;     // [R*H] arrival counters (library owned, self-resetting)
+    int B, H, S;       // B = number of query rows R
+    int q_per_seq;     // query rows per cache sequence (1 in the generation phase, S_prompt in the context phase)
     int nsplit, keys_per_split;
     float inv_sqrt_dh;
 };
+
+// 16 cache bytes (or 16 fp16) of one key -> 8 half2 in the pair order (d0,d2) (d1,d3) (d4,d6) (d5,d7) ...
+template <bool INT8>
+__device__ __forceinline__ void load16_h2(const uint8_t* p, __half2 (&w)[8])
+{
+    if constexpr (INT8)
+    {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        dequant_word(v.x ^ 0x80808080u, w[0], w[1]);
+        dequant_word(v.y ^ 0x80808080u, w[2], w[3]);
+        dequant_word(v.z ^ 0x80808080u, w[4], w[5]);
+        dequant_word(v.w ^ 0x80808080u, w[6], w[7]);
+    }
+    else
+    {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(p);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(p + 16);
+        const uint32_t u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}; // u[j] = (d2j, d2j+1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const uint32_t lo = __byte_perm(u[2 * i], u[2 * i + 1], 0x5410); // (d4i, d4i+2)
+            const uint32_t hi = __byte_perm(u[2 * i], u[2 * i + 1], 0x7632); // (d4i+1, d4i+3)
+            w[2 * i] = *reinterpret_cast<const __half2*>(&lo);
+            w[2 * i + 1] = *reinterpret_cast<const __half2*>(&hi);
+        }
+    }
+}
 
 template <bool INT8>
 __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(const XAttnParams p)
@@ -483,6 +518,7 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
     float* s_red = s_o + kXaWarps * kDh;                                     // [kXaWarps]
     uint64_t* full = reinterpret_cast<uint64_t*>(s_red + kXaWarps);
     uint64_t* empty = full + kXaStages;
+    int* s_flag = reinterpret_cast<int*>(empty + kXaStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.B * p.H * p.nsplit;
@@ -497,10 +533,11 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
         fence_mbar_init();
     }
     __syncthreads();
+    grid_dep_launch_dependents();
 
     if (warp == kXaWarps)
     {
-        // ===== producer =====
+        // ===== producer (the cross-KV cache is written once per utterance, long before: no dependency wait) =====
         if (lane == 0)
         {
             const uint64_t pol = policy_evict_first();
@@ -537,6 +574,7 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
     grid_dep_wait(); // q comes from the previous kernel
     const int chunk = lane & 3, kl = lane >> 2;
     const float s_qo = INT8 ? p.scale_quant_orig[0] : 1.f;
+    const float sscale = s_qo * p.inv_sqrt_dh;
     int slot = 0;
     uint32_t n_seen = 0;
     const int nthreads = kXaWarps * 32;
@@ -547,21 +585,18 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
         const int key0 = sp * p.keys_per_split;
         const int nkeys = min(p.keys_per_split, p.S - key0);
 
-        float q[16];
+        // this lane's 16 dims of q in the same pair order as load16_h2
+        __half2 q2[8];
         {
             __half qh[16];
             load16_half(p.q + (size_t) bh * kDh + chunk * 16, nullptr, qh);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
             {
-                // same dim permutation as load16_raw_perm
-                q[4 * i + 0] = __half2float(qh[4 * i + 0]);
-                q[4 * i + 1] = __half2float(qh[4 * i + 2]);
-                q[4 * i + 2] = __half2float(qh[4 * i + 1]);
-                q[4 * i + 3] = __half2float(qh[4 * i + 3]);
+                q2[2 * i] = __halves2half2(qh[4 * i], qh[4 * i + 2]);
+                q2[2 * i + 1] = __halves2half2(qh[4 * i + 1], qh[4 * i + 3]);
             }
         }
-        const float sscale = s_qo * p.inv_sqrt_dh;
 
         // ---- K stages: scores ----
         float lmax = -FLT_MAX;
@@ -570,17 +605,25 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
             const int nk = min(kXaStageKeys, nkeys - k0);
             mbar_wait(&full[slot], (n_seen / kXaStages) & 1);
             const uint8_t* st = ring + slot * kStageBytes;
+#pragma unroll 2
             for (int kk = warp * 8; kk < nk; kk += kXaWarps * 8)
             {
                 const int key = kk + kl;
                 float s = 0.f;
                 if (key < nk)
                 {
-                    float kf[16];
-                    load16_raw_perm<INT8>(st, (size_t) key * kDh + chunk * 16, kf); // integer values (int8) / fp16 values
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        s = fmaf(q[i], kf[i], s);
+                    __half2 w[8];
+                    load16_h2<INT8>(st + ((size_t) key * kDh + chunk * 16) * ESZ, w);
+                    __half2 h0 = __hmul2(q2[0], w[0]);
+                    __half2 h1 = __hmul2(q2[4], w[4]);
+                    h0 = __hfma2(q2[1], w[1], h0);
+                    h1 = __hfma2(q2[5], w[5], h1);
+                    h0 = __hfma2(q2[2], w[2], h0);
+                    h1 = __hfma2(q2[6], w[6], h1);
+                    h0 = __hfma2(q2[3], w[3], h0);
+                    h1 = __hfma2(q2[7], w[7], h1);
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                    s = (f0.x + f0.y) + (f1.x + f1.y);
                 }
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -622,11 +665,16 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
         if (lane == 0)
             s_red[warp] = lsum;
 
-        // ---- V stages: o = sum p * v_int ----
+        // ---- V stages: o = sum p * v_int; up to 4 keys chained in fp16, then flushed to fp32 ----
         float o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             o[i] = 0.f;
+        __half2 o2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            o2[i] = __float2half2_rn(0.f);
+        int pending = 0;
         for (int k0 = 0; k0 < nkeys; k0 += kXaStageKeys)
         {
             const int nk = min(kXaStageKeys, nkeys - k0);
@@ -637,12 +685,24 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
                 const int key = kk + kl;
                 if (key < nk)
                 {
-                    const float pt = s_p[k0 + key];
-                    float vf[16];
-                    load16_raw_perm<INT8>(st, (size_t) key * kDh + chunk * 16, vf);
+                    const __half2 p2 = __float2half2_rn(s_p[k0 + key]);
+                    __half2 w[8];
+                    load16_h2<INT8>(st + ((size_t) key * kDh + chunk * 16) * ESZ, w);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        o[i] = fmaf(pt, vf[i], o[i]);
+                    for (int i = 0; i < 8; ++i)
+                        o2[i] = __hfma2(p2, w[i], o2[i]);
+                }
+                if (++pending == 4) // warp-uniform
+                {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                    {
+                        const float2 f = __half22float2(o2[i]);
+                        o[2 * i] += f.x;
+                        o[2 * i + 1] += f.y;
+                        o2[i] = __float2half2_rn(0.f);
+                    }
+                    pending = 0;
                 }
             }
             __syncwarp();
@@ -650,6 +710,13 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
                 mbar_arrive(&empty[slot]);
             ++n_seen;
             slot = (slot + 1 == kXaStages) ? 0 : slot + 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            const float2 f = __half22float2(o2[i]);
+            o[2 * i] += f.x;
+            o[2 * i + 1] += f.y;
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -662,14 +729,15 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
         }
         if (lane < 4)
         {
+            // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j)
             {
-                // undo the dim permutation of load16_raw_perm
-                s_o[warp * kDh + chunk * 16 + 4 * i + 0] = o[4 * i + 0];
-                s_o[warp * kDh + chunk * 16 + 4 * i + 2] = o[4 * i + 1];
-                s_o[warp * kDh + chunk * 16 + 4 * i + 1] = o[4 * i + 2];
-                s_o[warp * kDh + chunk * 16 + 4 * i + 3] = o[4 * i + 3];
+                float* dst = s_o + warp * kDh + chunk * 16 + 4 * j;
+                dst[0] = o[4 * j + 0];
+                dst[2] = o[4 * j + 1];
+                dst[1] = o[4 * j + 2];
+                dst[3] = o[4 * j + 3];
             }
         }
         asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
@@ -690,36 +758,43 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
             else
             {
                 float* pr = p.partials + (size_t) item * (kDh + 2);
-                pr[2 + threadIdx.x] = acc;
+                __stcg(pr + 2 + threadIdx.x, acc);
                 if (threadIdx.x == 0)
                 {
-                    pr[0] = gmax;
-                    pr[1] = l;
+                    __stcg(pr, gmax);
+                    __stcg(pr + 1, l);
                 }
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); // s_p / s_o / s_red free for the next item
+        if (p.nsplit > 1)
+        {
+            // last split of this (row, head) to arrive merges all partials
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+            if (threadIdx.x == 0)
+                *s_flag = (atomicAdd(&p.counters[bh], 1) == p.nsplit - 1) ? 1 : 0;
+            asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+            if (*s_flag && threadIdx.x < kDh)
+            {
+                __threadfence();
+                const float* pr = p.partials + (size_t) bh * p.nsplit * (kDh + 2);
+                float m = -FLT_MAX;
+                for (int s2 = 0; s2 < p.nsplit; ++s2)
+                    m = fmaxf(m, __ldcg(pr + s2 * (kDh + 2)));
+                float l = 0.f, acc = 0.f;
+                for (int s2 = 0; s2 < p.nsplit; ++s2)
+                {
+                    const float w = __expf(__ldcg(pr + s2 * (kDh + 2)) - m);
+                    l += w * __ldcg(pr + s2 * (kDh + 2) + 1);
+                    acc += w * __ldcg(pr + s2 * (kDh + 2) + 2 + threadIdx.x);
+                }
+                p.out[(size_t) bh * kDh + threadIdx.x] = __float2half_rn(acc / l);
+                if (threadIdx.x == 0)
+                    p.counters[bh] = 0;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); // s_p / s_o / s_red / s_flag free for the next item
     }
-}
-
-// merge split partials: grid B*H, 64 threads
-__global__ void __launch_bounds__(kDh) cross_attention_merge_kernel(
-    const float* __restrict__ partials, __half* __restrict__ out, int nsplit)
-{
-    grid_dep_wait();
-    const int bh = blockIdx.x, d = threadIdx.x;
-    const float* pr = partials + (size_t) bh * nsplit * (kDh + 2);
-    float gmax = -FLT_MAX;
-    for (int s = 0; s < nsplit; ++s)
-        gmax = fmaxf(gmax, pr[s * (kDh + 2)]);
-    float l = 0.f, acc = 0.f;
-    for (int s = 0; s < nsplit; ++s)
-    {
-        const float w = __expf(pr[s * (kDh + 2)] - gmax);
-        l += w * pr[s * (kDh + 2) + 1];
-        acc += w * pr[s * (kDh + 2) + 2 + d];
-    }
-    out[(size_t) bh * kDh + d] = __float2half_rn(acc / l);
 }
 
 // fp16 K, V [B, S, H*64] -> cache [B, 2, H, S, 64] (int8-quantized or fp16).  grid (S, B), 128 threads... one
@@ -768,15 +843,14 @@ extern "C" int b200_mmha_generation(const b200_mmha_params* p, b200_stream_t str
     {
         if (smem > 48 * 1024)
             B200_CUDA(cudaFuncSetAttribute(mmha_generation_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        mmha_generation_kernel<true><<<grid, 128, smem, as_stream(stream)>>>(*p);
+        B200_LAUNCH(mmha_generation_kernel<true>, grid, dim3(128), smem, as_stream(stream), *p);
     }
     else
     {
         if (smem > 48 * 1024)
             B200_CUDA(cudaFuncSetAttribute(mmha_generation_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        mmha_generation_kernel<false><<<grid, 128, smem, as_stream(stream)>>>(*p);
+        B200_LAUNCH(mmha_generation_kernel<false>, grid, dim3(128), smem, as_stream(stream), *p);
     }
-    B200_LAUNCH_CHECK();
     return B200_OK;
 }
 
@@ -800,17 +874,16 @@ extern "C" int b200_attention_context(const void* qkv, const int32_t* input_leng
     {
         if (smem > 48 * 1024)
             B200_CUDA(cudaFuncSetAttribute(attention_context_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attention_context_kernel<true><<<grid, 128, smem, as_stream(stream)>>>(static_cast<const __half*>(qkv),
+        B200_LAUNCH(attention_context_kernel<true>, grid, dim3(128), smem, as_stream(stream), static_cast<const __half*>(qkv),
             input_lengths, static_cast<__half*>(out), kv_cache, kv_scale_orig_quant, seq_len, num_heads, max_seq_len, q_scaling);
     }
     else
     {
         if (smem > 48 * 1024)
             B200_CUDA(cudaFuncSetAttribute(attention_context_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attention_context_kernel<false><<<grid, 128, smem, as_stream(stream)>>>(static_cast<const __half*>(qkv),
+        B200_LAUNCH(attention_context_kernel<false>, grid, dim3(128), smem, as_stream(stream), static_cast<const __half*>(qkv),
             input_lengths, static_cast<__half*>(out), kv_cache, kv_scale_orig_quant, seq_len, num_heads, max_seq_len, q_scaling);
     }
-    B200_LAUNCH_CHECK();
     return B200_OK;
 }
 
@@ -818,10 +891,11 @@ namespace b200
 {
 static void xattn_plan(int B, int H, int S, int& nsplit, int& kps)
 {
-    const int sms = num_sms();
+    // Static round-robin over persistent CTAs is balanced when every CTA gets several equal items: aim for >= 6
+    // items per resident CTA slot, keep >= 96 keys per item (one K stage + one V stage of <= 128 keys is ideal).
+    const int slots = num_sms() * kXaMaxCtasPerSm;
     const int pairs = B * H;
-    // aim for >= 4 work items per SM so the persistent CTAs stay balanced, but keep >= 96 keys per item
-    int ns = (4 * sms + pairs - 1) / pairs;
+    int ns = (6 * slots + pairs - 1) / pairs;
     const int max_ns = (S + 95) / 96;
     if (ns > max_ns)
         ns = max_ns;
@@ -830,6 +904,8 @@ static void xattn_plan(int B, int H, int S, int& nsplit, int& kps)
     kps = (S + ns - 1) / ns;
     nsplit = (S + kps - 1) / kps;
 }
+
+int* tc_counter_slot(int needed);
 } // namespace b200
 
 extern "C" size_t b200_cross_attention_workspace_bytes(int batch_size, int num_heads, int head_size, int kv_len)
@@ -870,29 +946,42 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     B200_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), B200_ERR_WORKSPACE,
         "cross attention: workspace of %zu bytes needed, got %zu", need, workspace_bytes);
     const int items = batch_size * num_heads * p.nsplit;
+    if (p.nsplit > 1)
+    {
+        p.counters = tc_counter_slot(batch_size * num_heads);
+        B200_REQUIRE(p.counters != nullptr, B200_ERR_UNSUPPORTED, "cross attention: %d (row, head) pairs exceed the counter slot",
+            batch_size * num_heads);
+    }
     const int esz = int8_kv_cache ? 1 : 2;
     const size_t smem = (size_t) kXaStages * kXaStageKeys * kDh * esz + sizeof(float) * (((p.keys_per_split + 3) & ~3) + kXaWarps * kDh + kXaWarps)
-        + sizeof(uint64_t) * 2 * kXaStages;
-    int ctas_per_sm = (smem <= 100 * 1024) ? 2 : 1;
+        + sizeof(uint64_t) * 2 * kXaStages + 16;
+    int ctas_per_sm = (int) ((220 * 1024) / (smem + 1024));
+    if (ctas_per_sm > kXaMaxCtasPerSm)
+        ctas_per_sm = kXaMaxCtasPerSm;
+    if (ctas_per_sm < 1)
+        ctas_per_sm = 1;
     int grid = num_sms() * ctas_per_sm;
     if (grid > items)
         grid = items;
     cudaStream_t st = as_stream(stream);
+    static bool attr_set[2] = {false, false};
     if (int8_kv_cache)
     {
-        B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        cross_attention_kernel<true><<<grid, (kXaWarps + 1) * 32, smem, st>>>(p);
+        if (!attr_set[0])
+        {
+            B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[0] = true;
+        }
+        B200_LAUNCH(cross_attention_kernel<true>, dim3(grid), dim3((kXaWarps + 1) * 32), smem, st, p);
     }
     else
     {
-        B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        cross_attention_kernel<false><<<grid, (kXaWarps + 1) * 32, smem, st>>>(p);
-    }
-    B200_LAUNCH_CHECK();
-    if (p.nsplit > 1)
-    {
-        cross_attention_merge_kernel<<<batch_size * num_heads, kDh, 0, st>>>(p.partials, p.out, p.nsplit);
-        B200_LAUNCH_CHECK();
+        if (!attr_set[1])
+        {
+            B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[1] = true;
+        }
+        B200_LAUNCH(cross_attention_kernel<false>, dim3(grid), dim3((kXaWarps + 1) * 32), smem, st, p);
     }
     return B200_OK;
 }

@@ -54,6 +54,38 @@ static inline cudaStream_t as_stream(b200_stream_t s)
     return reinterpret_cast<cudaStream_t>(s);
 }
 
+bool pdl_enabled(); // programmatic dependent launch for the hot-path kernels (b200_set_pdl / env B200_PDL)
+
+#ifdef __CUDACC__
+// Launches `kernel` with cudaLaunchKernelEx; when PDL is enabled the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the grid may start while its predecessor on the stream is
+// still draining.  Every kernel launched through this helper calls griddepcontrol.wait before it touches memory
+// written by the predecessor, and only reads weights / cache data before that point.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(
+    void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                                                            \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        ::b200::count_launch();                                                                                        \
+        B200_CUDA(::b200::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__));                                 \
+    } while (0)
+
 #ifdef __CUDACC__
 // ---- device helpers ------------------------------------------------------------------------------
 

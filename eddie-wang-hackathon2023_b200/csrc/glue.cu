@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const __half* __restrict
     const __half* __restrict__ beta, __half* __restrict__ y, int cols, float eps)
 {
     grid_dep_wait();
+    grid_dep_launch_dependents();
     const int row = blockIdx.x;
     const __half* xr = x + (size_t) row * cols;
     __half* yr = y + (size_t) row * cols;
@@ -110,6 +111,7 @@ __global__ void embed_kernel(const int* __restrict__ tokens, const int* __restri
     int n_ctx)
 {
     grid_dep_wait();
+    grid_dep_launch_dependents();
     const int r = blockIdx.x;
     int tok = tokens[r];
     int pos = positions[r];
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(256) logits_simt_kernel(const __half* __restri
     extern __shared__ __align__(16) unsigned char s_raw[];
     __half* sx = reinterpret_cast<__half*>(s_raw); // [nr][cols]
     grid_dep_wait();
+    grid_dep_launch_dependents();
     const int nr = min(kLogitsRowsPerPass, rows - row0);
     for (int i = threadIdx.x; i < nr * cols / 8; i += blockDim.x)
         reinterpret_cast<uint4*>(sx)[i] = reinterpret_cast<const uint4*>(x + (size_t) row0 * cols)[i];
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(256) logits_simt_kernel(const __half* __restri
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int* __restrict__ next_token, int vocab)
 {
     grid_dep_wait();
+    grid_dep_launch_dependents();
     const int r = blockIdx.x;
     const float* lr = logits + (size_t) r * vocab;
     float best = -FLT_MAX;
@@ -246,6 +250,21 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
     }
 }
 
+// Fire-and-forget L2 prefetch of a byte range (cp.async.bulk.prefetch.L2): used on a side stream to pull the next
+// layer's cross-KV cache into the 126 MB L2 while the latency-bound small kernels of the current layer leave HBM idle.
+__global__ void l2_prefetch_kernel(const uint8_t* __restrict__ p, size_t bytes, uint32_t chunk)
+{
+    const size_t n = (bytes + chunk - 1) / chunk;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+    {
+        const size_t off = i * chunk;
+        const size_t left = bytes - off;
+        const uint32_t sz = (uint32_t) (left < chunk ? left : chunk) & ~15u;
+        if (sz != 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(sz) : "memory");
+    }
+}
+
 int logits_tc(const __half* x, const __half* emb, float* logits, int rows, int cols, int vocab, cudaStream_t stream);
 extern int g_logits_policy;
 int g_logits_policy = 0; // 0 auto (tcgen05), 1 simt
@@ -267,14 +286,13 @@ extern "C" int b200_layernorm_fp16(const void* x, const void* gamma, const void*
     const __half *xh = static_cast<const __half*>(x), *g = static_cast<const __half*>(gamma), *b = static_cast<const __half*>(beta);
     __half* yh = static_cast<__half*>(y);
     if (vpt <= 1)
-        layernorm_kernel<1><<<rows, 128, 0, st>>>(xh, g, b, yh, cols, eps);
+        B200_LAUNCH(layernorm_kernel<1>, dim3(rows), dim3(128), 0, st, xh, g, b, yh, cols, eps);
     else if (vpt <= 2)
-        layernorm_kernel<2><<<rows, 128, 0, st>>>(xh, g, b, yh, cols, eps);
+        B200_LAUNCH(layernorm_kernel<2>, dim3(rows), dim3(128), 0, st, xh, g, b, yh, cols, eps);
     else if (vpt <= 4)
-        layernorm_kernel<4><<<rows, 128, 0, st>>>(xh, g, b, yh, cols, eps);
+        B200_LAUNCH(layernorm_kernel<4>, dim3(rows), dim3(128), 0, st, xh, g, b, yh, cols, eps);
     else
-        layernorm_kernel<8><<<rows, 128, 0, st>>>(xh, g, b, yh, cols, eps);
-    B200_LAUNCH_CHECK();
+        B200_LAUNCH(layernorm_kernel<8>, dim3(rows), dim3(128), 0, st, xh, g, b, yh, cols, eps);
     return B200_OK;
 }
 
@@ -286,8 +304,25 @@ extern "C" int b200_embed_tokens_fp16(const int32_t* tokens, const int32_t* posi
     if (rows <= 0)
         return B200_OK;
     B200_REQUIRE_DEVICE();
-    embed_kernel<<<rows, 128, 0, as_stream(stream)>>>(tokens, positions, static_cast<const __half*>(tok_emb),
-        static_cast<const __half*>(pos_emb), static_cast<__half*>(out), cols, vocab, n_ctx);
+    B200_LAUNCH(embed_kernel, dim3(rows), dim3(128), 0, as_stream(stream), tokens, positions,
+        static_cast<const __half*>(tok_emb), static_cast<const __half*>(pos_emb), static_cast<__half*>(out), cols, vocab,
+        n_ctx);
+    return B200_OK;
+}
+
+extern "C" int b200_l2_prefetch(const void* ptr, size_t bytes, b200_stream_t stream)
+{
+    B200_REQUIRE(ptr != nullptr || bytes == 0, B200_ERR_INVALID_ARG, "null pointer");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, B200_ERR_INVALID_ARG, "pointer must be 16-byte aligned");
+    if (bytes < 16)
+        return B200_OK;
+    B200_REQUIRE_DEVICE();
+    const uint32_t chunk = 8192;
+    const size_t n = (bytes + chunk - 1) / chunk;
+    int blocks = (int) ((n + 63) / 64);
+    if (blocks > num_sms())
+        blocks = num_sms();
+    l2_prefetch_kernel<<<blocks, 64, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(ptr), bytes, chunk);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
@@ -336,15 +371,13 @@ extern "C" int b200_logits_argmax_fp16(const void* x, const void* emb, void* log
             B200_CUDA(cudaFuncSetAttribute(logits_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         for (int r0 = 0; r0 < rows; r0 += kLogitsRowsPerPass)
         {
-            logits_simt_kernel<<<(vocab + 7) / 8, 256, smem, st>>>(
-                static_cast<const __half*>(x), static_cast<const __half*>(emb), lg, rows, cols, vocab, r0);
-            B200_LAUNCH_CHECK();
+            B200_LAUNCH(logits_simt_kernel, dim3((vocab + 7) / 8), dim3(256), smem, st, static_cast<const __half*>(x),
+                static_cast<const __half*>(emb), lg, rows, cols, vocab, r0);
         }
     }
     if (next_token != nullptr)
     {
-        argmax_kernel<<<rows, 1024, 0, st>>>(lg, next_token, vocab);
-        B200_LAUNCH_CHECK();
+        B200_LAUNCH(argmax_kernel, dim3(rows), dim3(1024), 0, st, static_cast<const float*>(lg), next_token, vocab);
     }
     return B200_OK;
 }

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -54,6 +55,23 @@ bool device_ok()
     return g_dev_ok == 1;
 }
 
+static int g_pdl = -1;
+
+bool pdl_enabled()
+{
+    if (g_pdl < 0)
+    {
+        const char* e = getenv("B200_PDL");
+        g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl == 1;
+}
+
+void set_pdl(int on)
+{
+    g_pdl = on ? 1 : 0;
+}
+
 int num_sms()
 {
     if (g_dev_ok < 0)
@@ -79,5 +97,11 @@ int b200_abi_version(void)
 unsigned long long b200_launch_count(void)
 {
     return b200::g_launches.load(std::memory_order_relaxed);
+}
+
+int b200_set_pdl(int enabled)
+{
+    b200::set_pdl(enabled);
+    return B200_OK;
 }
 }

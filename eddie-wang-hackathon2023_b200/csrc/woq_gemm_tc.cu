@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(192, 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    grid_dep_launch_dependents(); // PDL: the next kernel may start its own prologue / weight prefetch now
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4)
@@ -282,32 +283,35 @@ __global__ void __launch_bounds__(192, 1)
         const int n_tiles = gridDim.x, m_tiles = gridDim.y;
         const int tile_id = m_tile * n_tiles + n_tile;
         const bool direct = (p.splits == 1);
-        float* slab = direct ? nullptr
-                             : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * (size_t) (128 * MT);
+        // split-K slab of this CTA: [128 n][MT m] fp32, i.e. thread T owns MT contiguous floats (128-bit accesses,
+        // consecutive threads consecutive 4*MT-byte rows: fully coalesced)
+        const size_t slab_elems = (size_t) 128 * MT;
+        float* slab = direct ? nullptr : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * slab_elems + (size_t) T * MT;
 #pragma unroll 1
         for (int c16 = 0; c16 < MT / 16; ++c16)
         {
             uint32_t acc[16];
             tc_ld_x16(tmem_base + lane_field + kDCol + c16 * 16, acc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
+            if (direct)
             {
-                const int ml = c16 * 16 + i;
-                const int m = m_tile * MT + ml;
-                const float val = __uint_as_float(acc[i]);
-                if (direct)
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
                 {
+                    const int m = m_tile * MT + c16 * 16 + i;
                     if (m < p.M && n < p.N)
                     {
                         const size_t idx = (size_t) m * p.ldc + n;
-                        p.C[idx] = epilogue_apply(val, 1.0f, p.bias, p.activation, p.residual, n, idx);
+                        p.C[idx] = epilogue_apply(__uint_as_float(acc[i]), 1.0f, p.bias, p.activation, p.residual, n, idx);
                     }
                 }
-                else if (m < p.M)
-                {
-                    slab[ml * 128 + T] = val;
-                }
+            }
+            else
+            {
+                uint4* dst = reinterpret_cast<uint4*>(slab + c16 * 16);
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    __stcg(dst + v, make_uint4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]));
             }
         }
         if (!direct)
@@ -323,17 +327,59 @@ __global__ void __launch_bounds__(192, 1)
             if (*last_flag)
             {
                 __threadfence();
+                // deterministic reduction in split order; all loads of a 16-column group are independent and issued
+                // before the adds (SPLIT_UNROLL splits x 4 x 128-bit loads in flight per thread)
+                const float* base = p.slabs + (size_t) tile_id * slab_elems + (size_t) T * MT;
+                const size_t split_stride = (size_t) m_tiles * n_tiles * slab_elems;
                 const int m_valid = min(MT, p.M - m_tile * MT);
-                if (n < p.N)
+#pragma unroll 1
+                for (int c16 = 0; c16 * 16 < m_valid; ++c16)
                 {
-                    for (int ml = 0; ml < m_valid; ++ml)
+                    float sum[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        sum[i] = 0.f;
+                    constexpr int SPLIT_UNROLL = 4;
+                    for (int s0 = 0; s0 < p.splits; s0 += SPLIT_UNROLL)
                     {
-                        float sum = 0.f;
-                        for (int s = 0; s < p.splits; ++s)
-                            sum += __ldcg(p.slabs + ((size_t) s * m_tiles * n_tiles + tile_id) * (size_t) (128 * MT)
-                                + ml * 128 + T);
-                        const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
-                        p.C[idx] = epilogue_apply(sum, 1.0f, p.bias, p.activation, p.residual, n, idx);
+                        uint4 v[SPLIT_UNROLL][4];
+#pragma unroll
+                        for (int u = 0; u < SPLIT_UNROLL; ++u)
+                        {
+                            const int sidx = min(s0 + u, p.splits - 1);
+                            const uint4* src = reinterpret_cast<const uint4*>(base + (size_t) sidx * split_stride + c16 * 16);
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4)
+                                v[u][q4] = __ldcg(src + q4);
+                        }
+#pragma unroll
+                        for (int u = 0; u < SPLIT_UNROLL; ++u)
+                        {
+                            if (s0 + u < p.splits)
+                            {
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4)
+                                {
+                                    sum[4 * q4 + 0] += __uint_as_float(v[u][q4].x);
+                                    sum[4 * q4 + 1] += __uint_as_float(v[u][q4].y);
+                                    sum[4 * q4 + 2] += __uint_as_float(v[u][q4].z);
+                                    sum[4 * q4 + 3] += __uint_as_float(v[u][q4].w);
+                                }
+                            }
+                        }
+                    }
+                    if (n < p.N)
+                    {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                        {
+                            const int ml = c16 * 16 + i;
+                            if (ml < m_valid)
+                            {
+                                const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
+                                p.C[idx] = epilogue_apply(sum[i], 1.0f, p.bias, p.activation, p.residual, n, idx);
+                            }
+                        }
                     }
                 }
                 if (T == 0)
@@ -423,6 +469,7 @@ __global__ void __launch_bounds__(192, 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    grid_dep_launch_dependents(); // PDL: the next kernel may start its own prologue / weight prefetch now
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4)
@@ -567,7 +614,7 @@ TcPlan plan_tc(int M, int N, int K)
 static int* g_counters = nullptr;
 static std::mutex g_counter_mu;
 static unsigned g_counter_slot = 0;
-constexpr int kCounterSlots = 64, kCounterSlotInts = 4096;
+constexpr int kCounterSlots = 64, kCounterSlotInts = 16384;
 
 int tc_init()
 {
@@ -578,6 +625,17 @@ int tc_init()
         B200_CUDA(cudaMemset(g_counters, 0, sizeof(int) * kCounterSlots * kCounterSlotInts));
     }
     return B200_OK;
+}
+
+// Hands out one self-resetting counter slot (kCounterSlotInts ints, all zero between launches) round-robin.
+int* tc_counter_slot(int needed)
+{
+    if (needed > kCounterSlotInts)
+        return nullptr;
+    if (g_counters == nullptr && tc_init() != B200_OK)
+        return nullptr;
+    std::lock_guard<std::mutex> lk(g_counter_mu);
+    return g_counters + (size_t) (g_counter_slot++ % kCounterSlots) * kCounterSlotInts;
 }
 
 template <int MT, int SS, int AS>
@@ -591,8 +649,7 @@ static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcPar
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr_set = true;
     }
-    kern<<<grid, 192, smem, stream>>>(tmW, tmX, p);
-    B200_LAUNCH_CHECK();
+    B200_LAUNCH(kern, grid, dim3(192), smem, stream, tmW, tmX, p);
     return B200_OK;
 }
 
@@ -623,10 +680,7 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     p.residual = residual;
     p.C = C;
     p.slabs = static_cast<float*>(workspace);
-    {
-        std::lock_guard<std::mutex> lk(g_counter_mu);
-        p.counters = g_counters + (size_t) (g_counter_slot++ % kCounterSlots) * kCounterSlotInts;
-    }
+    p.counters = tc_counter_slot(pl.m_tiles * pl.n_tiles <= kCounterSlotInts ? pl.m_tiles * pl.n_tiles : 1);
     p.M = M;
     p.N = N;
     p.K = K;
@@ -666,8 +720,7 @@ static int launch_logits(const CUtensorMap& tmE, const CUtensorMap& tmX, const L
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr_set = true;
     }
-    kern<<<grid, 192, smem, stream>>>(tmE, tmX, p);
-    B200_LAUNCH_CHECK();
+    B200_LAUNCH(kern, grid, dim3(192), smem, stream, tmE, tmX, p);
     return B200_OK;
 }
 

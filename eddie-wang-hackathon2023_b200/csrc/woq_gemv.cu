@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(672) woq_gemv_kernel(const GemvParams p)
         fence_mbar_init();
     }
     __syncthreads();
+    grid_dep_launch_dependents();
 
     if (warp == nw)
     {
@@ -216,8 +217,7 @@ static int launch_gemv(const GemvParams& p, int nw, int grid, size_t smem, cudaS
     auto kern = woq_gemv_kernel<M, PPW>;
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    kern<<<grid, (nw + 1) * 32, smem, stream>>>(p);
-    B200_LAUNCH_CHECK();
+    B200_LAUNCH(kern, dim3(grid), dim3((nw + 1) * 32), smem, stream, p);
     return B200_OK;
 }
 

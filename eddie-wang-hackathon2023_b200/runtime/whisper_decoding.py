@@ -15,6 +15,7 @@ Everything numerical happens in libb200_whisper.so through the C ABI; torch prov
 CUDA-graph capture.  Batch elements are independent utterances (the multi-GPU sharding unit).
 """
 import ctypes
+import os
 
 import torch
 
@@ -104,6 +105,9 @@ class WhisperDecoding:
                        self.lib.b200_cross_attention_workspace_bytes(max_rows, self.H, self.Dh, self.S_enc), 1 << 20)
         self.ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         self.graph = None
+        # side stream that pulls the next layer's cross-KV cache into L2 while the current layer's small kernels run
+        self.prefetch_cross_kv = os.environ.get("B200_XKV_PREFETCH", "1") != "0"
+        self._side = torch.cuda.Stream(device=dev) if torch.cuda.is_available() else None
         self._pinned_in = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
         self._pinned_out = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
 
@@ -164,6 +168,11 @@ class WhisperDecoding:
         q = self._buf("q", rows, d)
         u = self._buf("u", rows, 4 * d)
         st = self._st()
+        main = torch.cuda.current_stream(self.device)
+        prefetch = self.prefetch_cross_kv and not context and self._side is not None
+        if prefetch:
+            self._side.wait_stream(main)
+            self._prefetch(0)
         for i, lay in enumerate(self.layers):
             self._ln(x, lay["attn_ln"], h, rows)
             self._gemm(h, rows, lay["qkv"], qkv)
@@ -190,11 +199,23 @@ class WhisperDecoding:
                                                ctx.data_ptr(), rows, s_q, H, Dh, self.S_enc, 1, self.ws.data_ptr(),
                                                self.ws.numel(), st)
             _lib.check(rc, "cross_attention")
+            if prefetch and i + 1 < self.L:
+                # layer i's cross-KV is dead now: start pulling layer i+1's while the MLP and the next self-attention run
+                self._side.wait_stream(main)
+                self._prefetch(i + 1)
             self._gemm(ctx, rows, lay["cross_out"], x, residual=x)
             self._ln(x, lay["mlp_ln"], h, rows)
             self._gemm(h, rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF)
             self._gemm(u, rows, lay["fc2"], x, residual=x)
+        if prefetch:
+            main.wait_stream(self._side)
         return x
+
+    def _prefetch(self, i):
+        c = self.cross_kv[i]
+        with torch.cuda.stream(self._side):
+            _lib.check(self.lib.b200_l2_prefetch(c.data_ptr(), c.numel() * c.element_size(), self._side.cuda_stream),
+                       "l2_prefetch")
 
     def _head(self, x_rows, rows, logits, next_tokens):
         h = self._buf("hf", rows, self.d)

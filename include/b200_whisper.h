@@ -53,6 +53,11 @@ enum
 };
 
 const char* b200_last_error(void);
+/* Programmatic dependent launch for the hot-path kernels (default on; env B200_PDL=0 disables): each kernel may start
+ * while its predecessor on the stream drains and waits (griddepcontrol.wait) before touching the predecessor's output. */
+int b200_set_pdl(int enabled);
+/* Fire-and-forget prefetch of [ptr, ptr+bytes) into L2 (cp.async.bulk.prefetch.L2); ptr 16-byte aligned. */
+int b200_l2_prefetch(const void* ptr, size_t bytes, b200_stream_t stream);
 int b200_abi_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 unsigned long long b200_launch_count(void);
