@@ -447,22 +447,21 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
 
 // =====================================================================================================
 // Cross-attention over a (typically int8) cross-KV cache [B, 2, H, S, 64]: the dominant byte stream of the
-// decoder step at batch >= 6 (3.84 MB per sequence per layer).  HBM-bound streaming design:
-//   * persistent CTAs (up to 4 per SM), work item = (query row, head, split): a contiguous key range, so K and V
-//     of an item are two contiguous byte ranges -> 1-D TMA bulk copies (UBLKCP) into a shared-memory ring by a
-//     producer warp that runs ahead across items;
-//   * 8 consumer warps, lane geometry 4 lanes x 16 dims per key, 8 keys per warp instruction (a warp reads 512
-//     contiguous bytes): K stages -> scores in shared memory -> softmax numerators -> V stages -> fp32 (m, l, o[64])
-//     partial; the last split of a (row, head) to finish merges the partials (arrival counter), so there is no
-//     separate merge launch;
-//   * instruction economy (the first version was issue-bound at 6.7 thread-instructions per byte): int8 -> fp16 by
-//     xor 0x80 + PRMT + HSUB2 (exact integers), products chained four at a time with HFMA2 and flushed to fp32
-//     (same scheme as the GEMV), the dequant scale hoisted out of both dot products.
+// decoder step at batch >= 6 (3.84 MB per sequence per layer).  HBM-bound streaming design, third iteration
+// (v1: CTA-wide items with shared-memory scores, 6.7 thread-instructions per byte, issue-bound at 2.1 TB/s;
+//  v2: finer items + in-kernel merge, slower: five CTA barriers and a __threadfence per 16 KB item):
+//   * the work item is WARP-private: (query row, head, range of <= 128 keys).  A warp reads its K range with sixteen
+//     independent 128-bit loads per lane (512 contiguous bytes per warp instruction, 8 KB in flight per warp), keeps
+//     the 16 scores per lane in registers, does the softmax with shuffles only, then streams V the same way.
+//     No shared memory, no CTA barrier, no producer/consumer handshake: with 16 resident warps per SM there are
+//     128 KB of loads in flight per SM, several times what Little's law needs for HBM3e.
+//   * lane geometry: 4 lanes x 16 dims per key, 8 keys per warp instruction (the same lane owns the same key in the
+//     K and V phases, so probabilities never leave registers).
+//   * int8 -> fp16 by xor 0x80 + PRMT + HSUB2 (exact integers); products chained four at a time with HFMA2 and
+//     flushed to fp32 (same scheme as the GEMV); the dequant scale is hoisted out of both dot products.
+//   * the splits of one (row, head) are merged by the last warp to arrive (self-resetting counter).
 // =====================================================================================================
-constexpr int kXaStageKeys = 128;
-constexpr int kXaStages = 5;
 constexpr int kXaWarps = 8;
-constexpr int kXaMaxCtasPerSm = 4;
 
 struct XAttnParams
 {
@@ -475,25 +474,62 @@ struct XAttnParams
     int B, H, S;       // B = number of query rows R
     int q_per_seq;     // query rows per cache sequence (1 in the generation phase, S_prompt in the context phase)
     int nsplit, keys_per_split;
+    int items_per_warp;
     float inv_sqrt_dh;
 };
 
 // 16 cache bytes (or 16 fp16) of one key -> 8 half2 in the pair order (d0,d2) (d1,d3) (d4,d6) (d5,d7) ...
 template <bool INT8>
-__device__ __forceinline__ void load16_h2(const uint8_t* p, __half2 (&w)[8])
+struct XaChunk;
+
+template <>
+struct XaChunk<true>
 {
-    if constexpr (INT8)
+    uint4 v;
+
+    __device__ __forceinline__ void load(const uint8_t* p)
     {
-        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(p));
+    }
+
+    __device__ __forceinline__ void zero()
+    {
+        v = make_uint4(0, 0, 0, 0); // int8 zeros
+    }
+
+    __device__ __forceinline__ void unpack(__half2 (&w)[8]) const
+    {
         dequant_word(v.x ^ 0x80808080u, w[0], w[1]);
         dequant_word(v.y ^ 0x80808080u, w[2], w[3]);
         dequant_word(v.z ^ 0x80808080u, w[4], w[5]);
         dequant_word(v.w ^ 0x80808080u, w[6], w[7]);
     }
-    else
+};
+
+template <>
+struct XaChunk<false>
+{
+    uint4 v0, v1;
+
+    __device__ __forceinline__ void load(const uint8_t* p)
     {
-        const uint4 v0 = *reinterpret_cast<const uint4*>(p);
-        const uint4 v1 = *reinterpret_cast<const uint4*>(p + 16);
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v0.x), "=r"(v0.y), "=r"(v0.z), "=r"(v0.w)
+                     : "l"(p));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v1.x), "=r"(v1.y), "=r"(v1.z), "=r"(v1.w)
+                     : "l"(p + 16));
+    }
+
+    __device__ __forceinline__ void zero()
+    {
+        v0 = v1 = make_uint4(0, 0, 0, 0);
+    }
+
+    __device__ __forceinline__ void unpack(__half2 (&w)[8]) const
+    {
         const uint32_t u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}; // u[j] = (d2j, d2j+1)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -504,88 +540,53 @@ __device__ __forceinline__ void load16_h2(const uint8_t* p, __half2 (&w)[8])
             w[2 * i + 1] = *reinterpret_cast<const __half2*>(&hi);
         }
     }
-}
+};
 
 template <bool INT8>
-__global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(const XAttnParams p)
+__global__ void __launch_bounds__(kXaWarps * 32) cross_attention_kernel(const XAttnParams p)
 {
     constexpr int ESZ = INT8 ? 1 : 2;
-    constexpr int kStageBytes = kXaStageKeys * kDh * ESZ;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* ring = smem;
-    float* s_p = reinterpret_cast<float*>(smem + kXaStages * kStageBytes); // [keys_per_split]
-    float* s_o = s_p + ((p.keys_per_split + 3) & ~3);                        // [kXaWarps][64]
-    float* s_red = s_o + kXaWarps * kDh;                                     // [kXaWarps]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_red + kXaWarps);
-    uint64_t* empty = full + kXaStages;
-    int* s_flag = reinterpret_cast<int*>(empty + kXaStages);
-
+    constexpr int NIT = INT8 ? 16 : 8; // 8 keys per iteration: <= 128 (int8) / 64 (fp16) keys per item
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.B * p.H * p.nsplit;
-
-    if (threadIdx.x == 0)
-    {
-        for (int s = 0; s < kXaStages; ++s)
-        {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kXaWarps);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    grid_dep_launch_dependents();
-
-    if (warp == kXaWarps)
-    {
-        // ===== producer (the cross-KV cache is written once per utterance, long before: no dependency wait) =====
-        if (lane == 0)
-        {
-            const uint64_t pol = policy_evict_first();
-            int slot = 0;
-            uint32_t n_issued = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x)
-            {
-                const int bh = item / p.nsplit, sp = item % p.nsplit;
-                const int b = (bh / p.H) / p.q_per_seq, h = bh % p.H;
-                const int key0 = sp * p.keys_per_split;
-                const int nkeys = min(p.keys_per_split, p.S - key0);
-                for (int kv = 0; kv < 2; ++kv)
-                {
-                    const uint8_t* base = static_cast<const uint8_t*>(p.kv)
-                        + (((size_t) (b * 2 + kv) * p.H + h) * p.S + key0) * (size_t) (kDh * ESZ);
-                    for (int k0 = 0; k0 < nkeys; k0 += kXaStageKeys)
-                    {
-                        const int nk = min(kXaStageKeys, nkeys - k0);
-                        if (n_issued >= (uint32_t) kXaStages)
-                            mbar_wait(&empty[slot], ((n_issued / kXaStages) - 1) & 1);
-                        const uint32_t bytes = (uint32_t) nk * kDh * ESZ;
-                        mbar_arrive_expect_tx(&full[slot], bytes);
-                        bulk_g2s_hint(ring + slot * kStageBytes, base + (size_t) k0 * kDh * ESZ, bytes, &full[slot], pol);
-                        ++n_issued;
-                        slot = (slot + 1 == kXaStages) ? 0 : slot + 1;
-                    }
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== consumers =====
-    grid_dep_wait(); // q comes from the previous kernel
     const int chunk = lane & 3, kl = lane >> 2;
+    const int items = p.B * p.H * p.nsplit;
+    const int gw = blockIdx.x * kXaWarps + warp;
+
+    grid_dep_launch_dependents();
     const float s_qo = INT8 ? p.scale_quant_orig[0] : 1.f;
     const float sscale = s_qo * p.inv_sqrt_dh;
-    int slot = 0;
-    uint32_t n_seen = 0;
-    const int nthreads = kXaWarps * 32;
+    bool waited = false;
 
-    for (int item = blockIdx.x; item < items; item += gridDim.x)
+    for (int it_w = 0; it_w < p.items_per_warp; ++it_w)
     {
+        const int item = gw * p.items_per_warp + it_w;
+        if (item >= items)
+            break;
         const int bh = item / p.nsplit, sp = item % p.nsplit;
+        const int b = (bh / p.H) / p.q_per_seq, h = bh % p.H;
         const int key0 = sp * p.keys_per_split;
         const int nkeys = min(p.keys_per_split, p.S - key0);
+        const uint8_t* kbase = static_cast<const uint8_t*>(p.kv)
+            + ((((size_t) (b * 2 + 0) * p.H + h) * p.S + key0) * kDh + chunk * 16) * ESZ;
+        const uint8_t* vbase = static_cast<const uint8_t*>(p.kv)
+            + ((((size_t) (b * 2 + 1) * p.H + h) * p.S + key0) * kDh + chunk * 16) * ESZ;
 
-        // this lane's 16 dims of q in the same pair order as load16_h2
+        // ---- K: all loads of the item in flight before anything depends on them (cache data: no PDL wait needed)
+        XaChunk<INT8> kc[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            const int key = it * 8 + kl;
+            if (key < nkeys)
+                kc[it].load(kbase + (size_t) key * kDh * ESZ);
+            else
+                kc[it].zero();
+        }
+        if (!waited)
+        {
+            grid_dep_wait(); // q comes from the previous kernel
+            waited = true;
+        }
         __half2 q2[8];
         {
             __half qh[16];
@@ -597,126 +598,84 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
                 q2[2 * i + 1] = __halves2half2(qh[4 * i + 1], qh[4 * i + 3]);
             }
         }
-
-        // ---- K stages: scores ----
-        float lmax = -FLT_MAX;
-        for (int k0 = 0; k0 < nkeys; k0 += kXaStageKeys)
+        float sc[NIT];
+        float m = -FLT_MAX;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
         {
-            const int nk = min(kXaStageKeys, nkeys - k0);
-            mbar_wait(&full[slot], (n_seen / kXaStages) & 1);
-            const uint8_t* st = ring + slot * kStageBytes;
-#pragma unroll 2
-            for (int kk = warp * 8; kk < nk; kk += kXaWarps * 8)
-            {
-                const int key = kk + kl;
-                float s = 0.f;
-                if (key < nk)
-                {
-                    __half2 w[8];
-                    load16_h2<INT8>(st + ((size_t) key * kDh + chunk * 16) * ESZ, w);
-                    __half2 h0 = __hmul2(q2[0], w[0]);
-                    __half2 h1 = __hmul2(q2[4], w[4]);
-                    h0 = __hfma2(q2[1], w[1], h0);
-                    h1 = __hfma2(q2[5], w[5], h1);
-                    h0 = __hfma2(q2[2], w[2], h0);
-                    h1 = __hfma2(q2[6], w[6], h1);
-                    h0 = __hfma2(q2[3], w[3], h0);
-                    h1 = __hfma2(q2[7], w[7], h1);
-                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-                    s = (f0.x + f0.y) + (f1.x + f1.y);
-                }
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                if (key < nk && chunk == 0)
-                {
-                    s *= sscale;
-                    s_p[k0 + key] = s;
-                    lmax = fmaxf(lmax, s);
-                }
-            }
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(&empty[slot]);
-            ++n_seen;
-            slot = (slot + 1 == kXaStages) ? 0 : slot + 1;
+            __half2 w[8];
+            kc[it].unpack(w);
+            __half2 h0 = __hmul2(q2[0], w[0]);
+            __half2 h1 = __hmul2(q2[4], w[4]);
+            h0 = __hfma2(q2[1], w[1], h0);
+            h1 = __hfma2(q2[5], w[5], h1);
+            h0 = __hfma2(q2[2], w[2], h0);
+            h1 = __hfma2(q2[6], w[6], h1);
+            h0 = __hfma2(q2[3], w[3], h0);
+            h1 = __hfma2(q2[7], w[7], h1);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            float s = (f0.x + f0.y) + (f1.x + f1.y);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s = (it * 8 + kl < nkeys) ? s * sscale : -FLT_MAX;
+            sc[it] = s;
+            m = fmaxf(m, s);
         }
-        // block max over the consumer warps (named barrier 1)
+        // ---- V loads go out now; the softmax below overlaps their latency
+        XaChunk<INT8> vc[NIT];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1)
-            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        if (lane == 0)
-            s_red[warp] = lmax;
-        asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-        float gmax = s_red[0];
-#pragma unroll
-        for (int w = 1; w < kXaWarps; ++w)
-            gmax = fmaxf(gmax, s_red[w]);
-        float lsum = 0.f;
-        for (int t = threadIdx.x; t < nkeys; t += nthreads)
+        for (int it = 0; it < NIT; ++it)
         {
-            const float e = __expf(s_p[t] - gmax);
-            s_p[t] = e;
-            lsum += e;
+            const int key = it * 8 + kl;
+            if (key < nkeys)
+                vc[it].load(vbase + (size_t) key * kDh * ESZ);
+            else
+                vc[it].zero();
         }
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        float l = 0.f;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1)
-            lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-        asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); // everyone has read s_red (max) and written s_p
-        if (lane == 0)
-            s_red[warp] = lsum;
+        for (int it = 0; it < NIT; ++it)
+        {
+            const float e = (it * 8 + kl < nkeys) ? __expf(sc[it] - m) : 0.f;
+            sc[it] = e;
+            l += e;
+        }
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
 
-        // ---- V stages: o = sum p * v_int; up to 4 keys chained in fp16, then flushed to fp32 ----
+        // ---- P.V: four keys chained in fp16, then flushed to fp32
         float o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             o[i] = 0.f;
-        __half2 o2[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            o2[i] = __float2half2_rn(0.f);
-        int pending = 0;
-        for (int k0 = 0; k0 < nkeys; k0 += kXaStageKeys)
+        for (int it4 = 0; it4 < NIT; it4 += 4)
         {
-            const int nk = min(kXaStageKeys, nkeys - k0);
-            mbar_wait(&full[slot], (n_seen / kXaStages) & 1);
-            const uint8_t* st = ring + slot * kStageBytes;
-            for (int kk = warp * 8; kk < nk; kk += kXaWarps * 8)
+            __half2 o2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                o2[i] = __float2half2_rn(0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
             {
-                const int key = kk + kl;
-                if (key < nk)
-                {
-                    const __half2 p2 = __float2half2_rn(s_p[k0 + key]);
-                    __half2 w[8];
-                    load16_h2<INT8>(st + ((size_t) key * kDh + chunk * 16) * ESZ, w);
+                const __half2 p2 = __float2half2_rn(sc[it4 + j]);
+                __half2 w[8];
+                vc[it4 + j].unpack(w);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        o2[i] = __hfma2(p2, w[i], o2[i]);
-                }
-                if (++pending == 4) // warp-uniform
-                {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                    {
-                        const float2 f = __half22float2(o2[i]);
-                        o[2 * i] += f.x;
-                        o[2 * i + 1] += f.y;
-                        o2[i] = __float2half2_rn(0.f);
-                    }
-                    pending = 0;
-                }
+                for (int i = 0; i < 8; ++i)
+                    o2[i] = __hfma2(p2, w[i], o2[i]);
             }
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(&empty[slot]);
-            ++n_seen;
-            slot = (slot + 1 == kXaStages) ? 0 : slot + 1;
-        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-        {
-            const float2 f = __half22float2(o2[i]);
-            o[2 * i] += f.x;
-            o[2 * i + 1] += f.y;
+            for (int i = 0; i < 8; ++i)
+            {
+                const float2 f = __half22float2(o2[i]);
+                o[2 * i] += f.x;
+                o[2 * i + 1] += f.y;
+            }
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -725,75 +684,73 @@ __global__ void __launch_bounds__((kXaWarps + 1) * 32) cross_attention_kernel(co
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            o[i] = v;
+            o[i] = v * s_qo; // hoisted V dequant scale
         }
-        if (lane < 4)
+        // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
+        if (p.nsplit == 1)
         {
-            // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
+            if (kl == 0)
+            {
+                const float inv = 1.f / l;
+                __half* dst = p.out + (size_t) bh * kDh + chunk * 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    dst[4 * j + 0] = __float2half_rn(o[4 * j + 0] * inv);
+                    dst[4 * j + 2] = __float2half_rn(o[4 * j + 1] * inv);
+                    dst[4 * j + 1] = __float2half_rn(o[4 * j + 2] * inv);
+                    dst[4 * j + 3] = __float2half_rn(o[4 * j + 3] * inv);
+                }
+            }
+            continue;
+        }
+        float* pr = p.partials + (size_t) item * (kDh + 2);
+        if (kl == 0)
+        {
+            float* dst = pr + 2 + chunk * 16;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
-                float* dst = s_o + warp * kDh + chunk * 16 + 4 * j;
-                dst[0] = o[4 * j + 0];
-                dst[2] = o[4 * j + 1];
-                dst[1] = o[4 * j + 2];
-                dst[3] = o[4 * j + 3];
+                __stcg(dst + 4 * j + 0, o[4 * j + 0]);
+                __stcg(dst + 4 * j + 2, o[4 * j + 1]);
+                __stcg(dst + 4 * j + 1, o[4 * j + 2]);
+                __stcg(dst + 4 * j + 3, o[4 * j + 3]);
+            }
+            if (chunk == 0)
+            {
+                __stcg(pr, m);
+                __stcg(pr + 1, l);
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-        if (threadIdx.x < kDh)
+        // last split of this (row, head) to arrive merges all partials
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0)
+            last = (atomicAdd(&p.counters[bh], 1) == p.nsplit - 1) ? 1 : 0;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last)
         {
-            float acc = 0.f, l = 0.f;
-#pragma unroll
-            for (int w = 0; w < kXaWarps; ++w)
-            {
-                acc += s_o[w * kDh + threadIdx.x];
-                l += s_red[w];
-            }
-            acc *= s_qo; // hoisted V dequant scale
-            if (p.nsplit == 1)
-            {
-                p.out[(size_t) bh * kDh + threadIdx.x] = __float2half_rn(acc / l);
-            }
-            else
-            {
-                float* pr = p.partials + (size_t) item * (kDh + 2);
-                __stcg(pr + 2 + threadIdx.x, acc);
-                if (threadIdx.x == 0)
-                {
-                    __stcg(pr, gmax);
-                    __stcg(pr + 1, l);
-                }
-            }
-        }
-        if (p.nsplit > 1)
-        {
-            // last split of this (row, head) to arrive merges all partials
             __threadfence();
-            asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-            if (threadIdx.x == 0)
-                *s_flag = (atomicAdd(&p.counters[bh], 1) == p.nsplit - 1) ? 1 : 0;
-            asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-            if (*s_flag && threadIdx.x < kDh)
+            const float* pb = p.partials + (size_t) bh * p.nsplit * (kDh + 2);
+            float gm = -FLT_MAX;
+            for (int s2 = 0; s2 < p.nsplit; ++s2)
+                gm = fmaxf(gm, __ldcg(pb + s2 * (kDh + 2)));
+            float gl = 0.f, a0 = 0.f, a1 = 0.f;
+            for (int s2 = 0; s2 < p.nsplit; ++s2)
             {
-                __threadfence();
-                const float* pr = p.partials + (size_t) bh * p.nsplit * (kDh + 2);
-                float m = -FLT_MAX;
-                for (int s2 = 0; s2 < p.nsplit; ++s2)
-                    m = fmaxf(m, __ldcg(pr + s2 * (kDh + 2)));
-                float l = 0.f, acc = 0.f;
-                for (int s2 = 0; s2 < p.nsplit; ++s2)
-                {
-                    const float w = __expf(__ldcg(pr + s2 * (kDh + 2)) - m);
-                    l += w * __ldcg(pr + s2 * (kDh + 2) + 1);
-                    acc += w * __ldcg(pr + s2 * (kDh + 2) + 2 + threadIdx.x);
-                }
-                p.out[(size_t) bh * kDh + threadIdx.x] = __float2half_rn(acc / l);
-                if (threadIdx.x == 0)
-                    p.counters[bh] = 0;
+                const float* ps = pb + s2 * (kDh + 2);
+                const float w = __expf(__ldcg(ps) - gm);
+                gl += w * __ldcg(ps + 1);
+                a0 += w * __ldcg(ps + 2 + lane);
+                a1 += w * __ldcg(ps + 2 + 32 + lane);
             }
+            const float inv = 1.f / gl;
+            p.out[(size_t) bh * kDh + lane] = __float2half_rn(a0 * inv);
+            p.out[(size_t) bh * kDh + 32 + lane] = __float2half_rn(a1 * inv);
+            if (lane == 0)
+                p.counters[bh] = 0;
         }
-        asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); // s_p / s_o / s_red / s_flag free for the next item
     }
 }
 
@@ -889,20 +846,22 @@ extern "C" int b200_attention_context(const void* qkv, const int32_t* input_leng
 
 namespace b200
 {
-static void xattn_plan(int B, int H, int S, int& nsplit, int& kps)
+static void xattn_plan(int B, int H, int S, int int8, int& nsplit, int& kps, int& items_per_warp, int& blocks)
 {
-    // Static round-robin over persistent CTAs is balanced when every CTA gets several equal items: aim for >= 6
-    // items per resident CTA slot, keep >= 96 keys per item (one K stage + one V stage of <= 128 keys is ideal).
-    const int slots = num_sms() * kXaMaxCtasPerSm;
+    // warp-private items of <= 128 (int8) / 64 (fp16) keys; every warp gets the same number of items
+    const int max_keys = int8 ? 128 : 64;
     const int pairs = B * H;
-    int ns = (6 * slots + pairs - 1) / pairs;
-    const int max_ns = (S + 95) / 96;
-    if (ns > max_ns)
-        ns = max_ns;
-    if (ns < 1)
-        ns = 1;
-    kps = (S + ns - 1) / ns;
+    const int slots = num_sms() * 2 * kXaWarps; // two 8-warp CTAs per SM are resident (register-limited)
+    nsplit = (S + max_keys - 1) / max_keys;
+    // when there are fewer items than warp slots, split finer (down to 32 keys) so more SMs pull bytes
+    while (pairs * nsplit * 2 <= slots && (S + nsplit * 2 - 1) / (nsplit * 2) >= 32)
+        nsplit *= 2;
+    kps = (S + nsplit - 1) / nsplit;
+    kps = (kps + 7) & ~7; // whole 8-key warp iterations
     nsplit = (S + kps - 1) / kps;
+    const int items = pairs * nsplit;
+    items_per_warp = (items + slots - 1) / slots;
+    blocks = (items + items_per_warp * kXaWarps - 1) / (items_per_warp * kXaWarps);
 }
 
 int* tc_counter_slot(int needed);
@@ -912,9 +871,13 @@ extern "C" size_t b200_cross_attention_workspace_bytes(int batch_size, int num_h
 {
     if (batch_size <= 0 || num_heads <= 0 || kv_len <= 0 || head_size != kDh)
         return 0;
-    int ns, kps;
-    xattn_plan(batch_size, num_heads, kv_len, ns, kps);
-    return (size_t) batch_size * num_heads * ns * (kDh + 2) * sizeof(float);
+    int ns, kps, ipw, blocks, best = 0;
+    for (int int8 = 0; int8 < 2; ++int8)
+    {
+        xattn_plan(batch_size, num_heads, kv_len, int8, ns, kps, ipw, blocks);
+        best = ns > best ? ns : best;
+    }
+    return (size_t) batch_size * num_heads * best * (kDh + 2) * sizeof(float);
 }
 
 extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const float* kv_scale_quant_orig, void* out,
@@ -940,49 +903,23 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     p.H = num_heads;
     p.S = kv_len;
     p.q_per_seq = q_rows_per_seq;
-    xattn_plan(batch_size, num_heads, kv_len, p.nsplit, p.keys_per_split);
+    int blocks = 1;
+    xattn_plan(batch_size, num_heads, kv_len, int8_kv_cache, p.nsplit, p.keys_per_split, p.items_per_warp, blocks);
     p.inv_sqrt_dh = 1.f / sqrtf((float) kDh);
     const size_t need = p.nsplit > 1 ? (size_t) batch_size * num_heads * p.nsplit * (kDh + 2) * sizeof(float) : 0;
     B200_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), B200_ERR_WORKSPACE,
         "cross attention: workspace of %zu bytes needed, got %zu", need, workspace_bytes);
-    const int items = batch_size * num_heads * p.nsplit;
     if (p.nsplit > 1)
     {
         p.counters = tc_counter_slot(batch_size * num_heads);
         B200_REQUIRE(p.counters != nullptr, B200_ERR_UNSUPPORTED, "cross attention: %d (row, head) pairs exceed the counter slot",
             batch_size * num_heads);
     }
-    const int esz = int8_kv_cache ? 1 : 2;
-    const size_t smem = (size_t) kXaStages * kXaStageKeys * kDh * esz + sizeof(float) * (((p.keys_per_split + 3) & ~3) + kXaWarps * kDh + kXaWarps)
-        + sizeof(uint64_t) * 2 * kXaStages + 16;
-    int ctas_per_sm = (int) ((220 * 1024) / (smem + 1024));
-    if (ctas_per_sm > kXaMaxCtasPerSm)
-        ctas_per_sm = kXaMaxCtasPerSm;
-    if (ctas_per_sm < 1)
-        ctas_per_sm = 1;
-    int grid = num_sms() * ctas_per_sm;
-    if (grid > items)
-        grid = items;
     cudaStream_t st = as_stream(stream);
-    static bool attr_set[2] = {false, false};
     if (int8_kv_cache)
-    {
-        if (!attr_set[0])
-        {
-            B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set[0] = true;
-        }
-        B200_LAUNCH(cross_attention_kernel<true>, dim3(grid), dim3((kXaWarps + 1) * 32), smem, st, p);
-    }
+        B200_LAUNCH(cross_attention_kernel<true>, dim3(blocks), dim3(kXaWarps * 32), 0, st, p);
     else
-    {
-        if (!attr_set[1])
-        {
-            B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set[1] = true;
-        }
-        B200_LAUNCH(cross_attention_kernel<false>, dim3(grid), dim3((kXaWarps + 1) * 32), smem, st, p);
-    }
+        B200_LAUNCH(cross_attention_kernel<false>, dim3(blocks), dim3(kXaWarps * 32), 0, st, p);
     return B200_OK;
 }
 

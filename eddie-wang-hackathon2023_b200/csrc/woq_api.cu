@@ -10,7 +10,8 @@ namespace b200
 int woq_gemv_simt(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
     int activation, const __half* residual, __half* C, cudaStream_t stream);
 int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
-    int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+    int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+    const __half* ln_gamma, const __half* ln_beta, float ln_eps);
 size_t woq_tc_workspace_bytes(int max_m, int N, int K);
 int tc_init();
 
@@ -33,9 +34,9 @@ extern "C" size_t b200_woq_workspace_bytes(int max_m, int n, int k)
     return woq_tc_workspace_bytes(max_m, n, k);
 }
 
-extern "C" int b200_woq_int8_gemm_fused(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N,
-    const void* bias, int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes,
-    b200_stream_t stream)
+static int woq_dispatch(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N, const void* bias,
+    int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes, b200_stream_t stream,
+    const void* ln_gamma, const void* ln_beta, float ln_eps)
 {
     B200_REQUIRE(A && Wproc && scales && C, B200_ERR_INVALID_ARG, "null pointer (A/W/scales/C)");
     B200_REQUIRE(M >= 0, B200_ERR_INVALID_ARG, "M=%d must be >= 0", M);
@@ -48,12 +49,44 @@ extern "C" int b200_woq_int8_gemm_fused(const void* A, int M, int K, const int8_
     B200_REQUIRE_DEVICE();
     const bool simt = (g_policy == 1) || (g_policy == 0 && M <= 4);
     if (simt)
-        return woq_gemv_simt(static_cast<const __half*>(A), M, K, reinterpret_cast<const uint8_t*>(Wproc),
-            static_cast<const __half*>(scales), N, static_cast<const __half*>(bias), activation,
-            static_cast<const __half*>(residual), static_cast<__half*>(C), as_stream(stream));
+    {
+        const __half* a = static_cast<const __half*>(A);
+        if (ln_gamma != nullptr)
+        {
+            // the SIMT GEMV keeps its activations in registers: normalise into the workspace first
+            const size_t need = (size_t) M * K * sizeof(__half);
+            B200_REQUIRE(workspace != nullptr && workspace_bytes >= need, B200_ERR_WORKSPACE,
+                "woq gemm (LayerNorm + SIMT): workspace of %zu bytes needed", need);
+            if (int rc = b200_layernorm_fp16(A, ln_gamma, ln_beta, workspace, M, K, ln_eps, stream))
+                return rc;
+            a = static_cast<const __half*>(workspace);
+        }
+        return woq_gemv_simt(a, M, K, reinterpret_cast<const uint8_t*>(Wproc), static_cast<const __half*>(scales), N,
+            static_cast<const __half*>(bias), activation, static_cast<const __half*>(residual), static_cast<__half*>(C),
+            as_stream(stream));
+    }
     return woq_gemm_tc(static_cast<const __half*>(A), M, K, reinterpret_cast<const uint8_t*>(Wproc),
         static_cast<const __half*>(scales), N, static_cast<const __half*>(bias), activation,
-        static_cast<const __half*>(residual), static_cast<__half*>(C), workspace, workspace_bytes, as_stream(stream));
+        static_cast<const __half*>(residual), static_cast<__half*>(C), workspace, workspace_bytes, as_stream(stream),
+        static_cast<const __half*>(ln_gamma), static_cast<const __half*>(ln_beta), ln_eps);
+}
+
+extern "C" int b200_woq_int8_gemm_fused(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N,
+    const void* bias, int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes,
+    b200_stream_t stream)
+{
+    return woq_dispatch(A, M, K, Wproc, scales, N, bias, activation, residual, C, workspace, workspace_bytes, stream,
+        nullptr, nullptr, 0.f);
+}
+
+extern "C" int b200_woq_int8_gemm_ln_fused(const void* X, const void* ln_gamma, const void* ln_beta, float ln_eps, int M,
+    int K, const int8_t* Wproc, const void* scales, int N, const void* bias, int activation, const void* residual, void* C,
+    void* workspace, size_t workspace_bytes, b200_stream_t stream)
+{
+    B200_REQUIRE(ln_gamma && ln_beta, B200_ERR_INVALID_ARG, "null pointer (ln_gamma/ln_beta)");
+    B200_REQUIRE(workspace == nullptr || workspace != C, B200_ERR_INVALID_ARG, "workspace must not alias C");
+    return woq_dispatch(X, M, K, Wproc, scales, N, bias, activation, residual, C, workspace, workspace_bytes, stream,
+        ln_gamma, ln_beta, ln_eps);
 }
 
 extern "C" int b200_woq_int8_gemm(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N, void* C,

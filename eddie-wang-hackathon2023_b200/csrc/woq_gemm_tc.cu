@@ -27,6 +27,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -39,14 +40,57 @@ struct TcParams
     const __half* bias;
     const __half* residual;
     __half* C;
-    float* slabs;  // split-K partial tiles (workspace)
+    float* slabs;  // split-K partial tiles (workspace), global-memory reduction mode
     int* counters; // per-tile arrival counters (library owned, self-resetting)
+    // fused LayerNorm on the activation operand: x_raw != nullptr => B tiles are LN(x_raw) computed in-kernel
+    const __half* x_raw; // [M, K]
+    const __half* ln_gamma;
+    const __half* ln_beta;
+    float ln_eps;
     int M, N, K;
     int ldc;
     int activation;
     int kb_total; // K / 64
     int splits;
+    int cluster;  // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t cta_rank)
+{
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+// bias / activation / residual with the reference's per-layer fp16 rounding (see epilogue_apply in common.cuh);
+// the residual value is passed in so callers can issue all residual loads before the dependent stores.
+__device__ __forceinline__ __half finish_output(float acc, const __half* bias, int activation, bool has_res, float res, int n)
+{
+    __half o = __float2half_rn(acc);
+    if (bias != nullptr)
+        o = __float2half_rn(__half2float(o) + __half2float(bias[n]));
+    if (activation == B200_ACT_GELU_ERF)
+        o = __float2half_rn(gelu_erf(__half2float(o)));
+    else if (activation == B200_ACT_GELU_TANH)
+        o = __float2half_rn(gelu_tanh(__half2float(o)));
+    if (has_res)
+        o = __float2half_rn(__half2float(o) + res);
+    return o;
+}
 
 __device__ __forceinline__ void tc_fence_before()
 {
@@ -121,6 +165,7 @@ __global__ void __launch_bounds__(192, 1)
     constexpr int XTileBytes = MT * 128;
     constexpr uint32_t kTmemCols = tmem_cols_pow2(32 * AS + MT);
     constexpr uint32_t kDCol = 32 * AS;
+    constexpr int kRowGroups = MT / 16;
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=f16 (0), K-major both,
     // N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t) (MT >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
@@ -144,26 +189,29 @@ __global__ void __launch_bounds__(192, 1)
     const int kb_begin = (int) (((long long) split * p.kb_total) / p.splits);
     const int kb_end = (int) (((long long) (split + 1) * p.kb_total) / p.splits);
     const int nkb = kb_end - kb_begin;
+    const bool fused_ln = p.x_raw != nullptr;
 
-    if (threadIdx.x == 0)
     {
-        for (int s = 0; s < SS; ++s)
-        {
-            mbar_init(&full[s], 1);
-            mbar_init(&smem_free[s], 1);
-        }
-        for (int a = 0; a < AS; ++a)
-        {
-            mbar_init(&a_ready[a], 4);
-            mbar_init(&mma_done[a], 1);
-        }
-        mbar_init(acc_done, 1);
-        fence_mbar_init();
+        // one barrier per thread, initialised in parallel
+        const int t = threadIdx.x;
+        if (t < SS)
+            mbar_init(&full[t], fused_ln ? 5 : 1); // producer (+ the four LayerNorm warps writing the B tile)
+        else if (t < 2 * SS)
+            mbar_init(&smem_free[t - SS], 1);
+        else if (t < 2 * SS + AS)
+            mbar_init(&a_ready[t - 2 * SS], 4);
+        else if (t < 2 * SS + 2 * AS)
+            mbar_init(&mma_done[t - 2 * SS - AS], 1);
+        else if (t == 2 * SS + 2 * AS)
+            mbar_init(acc_done, 1);
+        if (t <= 2 * SS + 2 * AS)
+            fence_mbar_init();
     }
     if (warp == 4 && lane == 0)
     {
         tma_prefetch_desc(&tmW);
-        tma_prefetch_desc(&tmX);
+        if (!fused_ln)
+            tma_prefetch_desc(&tmX);
     }
     if (warp == 5)
     {
@@ -183,23 +231,28 @@ __global__ void __launch_bounds__(192, 1)
         // ===== TMA producer =====
         if (lane == 0)
         {
+            const uint32_t tx = kWTileBytes + (fused_ln ? 0 : XTileBytes);
             const int pre = nkb < SS ? nkb : SS;
             // weights first: they do not depend on the previous kernel
             for (int i = 0; i < pre; ++i)
             {
-                mbar_arrive_expect_tx(&full[i], kWTileBytes + XTileBytes);
+                mbar_arrive_expect_tx(&full[i], tx);
                 tma_load_2d(smW + i * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[i]);
             }
-            grid_dep_wait();
-            for (int i = 0; i < pre; ++i)
-                tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &full[i]);
+            if (!fused_ln)
+            {
+                grid_dep_wait();
+                for (int i = 0; i < pre; ++i)
+                    tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &full[i]);
+            }
             for (int i = pre; i < nkb; ++i)
             {
                 const int ss = i % SS;
                 mbar_wait(&smem_free[ss], ((i / SS) - 1) & 1);
-                mbar_arrive_expect_tx(&full[ss], kWTileBytes + XTileBytes);
+                mbar_arrive_expect_tx(&full[ss], tx);
                 tma_load_2d(smW + ss * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[ss]);
-                tma_load_2d(smX + ss * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &full[ss]);
+                if (!fused_ln)
+                    tma_load_2d(smX + ss * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &full[ss]);
             }
         }
     }
@@ -230,7 +283,7 @@ __global__ void __launch_bounds__(192, 1)
     }
     else
     {
-        // ===== dequant warps 0..3, then epilogue =====
+        // ===== warps 0..3: (LayerNorm of the activation tile,) dequant, then epilogue =====
         const int T = threadIdx.x; // weight column inside the tile == TMEM lane
         const int n = n_tile * 128 + T;
         const int jl = T >> 1, hf = T & 1, sw = jl & 7;
@@ -238,9 +291,95 @@ __global__ void __launch_bounds__(192, 1)
         const __half2 sc2 = __half2half2(sc);
         const uint32_t lane_field = (uint32_t) (warp * 32) << 16;
 
+        // fused LayerNorm: 8 threads per activation row, 16 rows per pass; statistics stay in registers
+        const int rsub = T >> 3, csub = T & 7;
+        float ln_mean[kRowGroups], ln_rstd[kRowGroups];
+        if (fused_ln)
+        {
+            grid_dep_wait(); // x_raw is the previous kernel's output
+            const int nchunks = p.K >> 3;
+#pragma unroll
+            for (int g = 0; g < kRowGroups; ++g)
+            {
+                const int row = m_tile * MT + g * 16 + rsub;
+                const uint4* xr = reinterpret_cast<const uint4*>(p.x_raw + (size_t) (row < p.M ? row : 0) * p.K);
+                float sum = 0.f;
+                for (int c = csub; c < nchunks; c += 8)
+                {
+                    const uint4 u = __ldg(xr + c);
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        const float2 f = __half22float2(h[j]);
+                        sum += f.x + f.y;
+                    }
+                }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                const float mean = sum / (float) p.K;
+                float sq = 0.f;
+                for (int c = csub; c < nchunks; c += 8)
+                {
+                    const uint4 u = __ldg(xr + c); // L1 hit: same lines as the first pass
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        const float2 f = __half22float2(h[j]);
+                        sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+                    }
+                }
+                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                ln_mean[g] = mean;
+                ln_rstd[g] = rsqrtf(sq / (float) p.K + p.ln_eps);
+            }
+        }
+
         for (int i = 0; i < nkb; ++i)
         {
             const int ss = i % SS, as = i % AS;
+            if (fused_ln)
+            {
+                // write LN(x)[rows of this m-tile][64 k of this block] into the SW128 K-major B tile
+                if (i >= SS)
+                    mbar_wait(&smem_free[ss], ((i / SS) - 1) & 1);
+                const int kcol = (kb_begin + i) * 64 + csub * 8;
+                const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(p.ln_gamma + kcol));
+                const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(p.ln_beta + kcol));
+                const __half2* gh = reinterpret_cast<const __half2*>(&g4);
+                const __half2* bh = reinterpret_cast<const __half2*>(&b4);
+#pragma unroll
+                for (int g = 0; g < kRowGroups; ++g)
+                {
+                    const int rl = g * 16 + rsub;
+                    const int row = m_tile * MT + rl;
+                    uint4 o = make_uint4(0, 0, 0, 0);
+                    if (row < p.M)
+                    {
+                        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.x_raw + (size_t) row * p.K + kcol));
+                        const __half2* h = reinterpret_cast<const __half2*>(&u);
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            const float2 f = __half22float2(h[j]);
+                            const float2 gf = __half22float2(gh[j]);
+                            const float2 bf = __half22float2(bh[j]);
+                            oh[j] = __floats2half2_rn((f.x - ln_mean[g]) * ln_rstd[g] * gf.x + bf.x,
+                                (f.y - ln_mean[g]) * ln_rstd[g] * gf.y + bf.y);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(smX + ss * XTileBytes + rl * 128 + ((csub ^ (rl & 7)) << 4)) = o;
+                }
+                fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&full[ss]);
+            }
             mbar_wait(&full[ss], (i / SS) & 1);
             const uint8_t* rowp = smW + ss * kWTileBytes + jl * 128;
             uint4 v[4];
@@ -283,10 +422,14 @@ __global__ void __launch_bounds__(192, 1)
         const int n_tiles = gridDim.x, m_tiles = gridDim.y;
         const int tile_id = m_tile * n_tiles + n_tile;
         const bool direct = (p.splits == 1);
-        // split-K slab of this CTA: [128 n][MT m] fp32, i.e. thread T owns MT contiguous floats (128-bit accesses,
-        // consecutive threads consecutive 4*MT-byte rows: fully coalesced)
+        const bool has_res = p.residual != nullptr;
+        const int m_valid = min(MT, p.M - m_tile * MT);
+        // global split-K slab of this CTA: [128 n][MT m] fp32, thread T owns MT contiguous floats
         const size_t slab_elems = (size_t) 128 * MT;
-        float* slab = direct ? nullptr : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * slab_elems + (size_t) T * MT;
+        float* slab = (direct || p.cluster)
+            ? nullptr
+            : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * slab_elems + (size_t) T * MT;
+        float* part = reinterpret_cast<float*>(smW); // cluster mode: this CTA's partial tile [128][MT] (ring is drained)
 #pragma unroll 1
         for (int c16 = 0; c16 < MT / 16; ++c16)
         {
@@ -295,26 +438,40 @@ __global__ void __launch_bounds__(192, 1)
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (direct)
             {
+                float res[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                 {
-                    const int m = m_tile * MT + c16 * 16 + i;
-                    if (m < p.M && n < p.N)
-                    {
-                        const size_t idx = (size_t) m * p.ldc + n;
-                        p.C[idx] = epilogue_apply(__uint_as_float(acc[i]), 1.0f, p.bias, p.activation, p.residual, n, idx);
-                    }
+                    const int ml = c16 * 16 + i;
+                    res[i] = (has_res && ml < m_valid && n < p.N)
+                        ? __half2float(p.residual[(size_t) (m_tile * MT + ml) * p.ldc + n])
+                        : 0.f;
                 }
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                {
+                    const int ml = c16 * 16 + i;
+                    if (ml < m_valid && n < p.N)
+                        p.C[(size_t) (m_tile * MT + ml) * p.ldc + n]
+                            = finish_output(__uint_as_float(acc[i]), p.bias, p.activation, has_res, res[i], n);
+                }
+            }
+            else if (p.cluster)
+            {
+                uint4* dst = reinterpret_cast<uint4*>(part + (size_t) T * MT + c16 * 16);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4)
+                    dst[v4] = make_uint4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2], acc[4 * v4 + 3]);
             }
             else
             {
                 uint4* dst = reinterpret_cast<uint4*>(slab + c16 * 16);
 #pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    __stcg(dst + v, make_uint4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]));
+                for (int v4 = 0; v4 < 4; ++v4)
+                    __stcg(dst + v4, make_uint4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2], acc[4 * v4 + 3]));
             }
         }
-        if (!direct)
+        if (!direct && !p.cluster)
         {
             __threadfence();
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -331,14 +488,19 @@ __global__ void __launch_bounds__(192, 1)
                 // before the adds (SPLIT_UNROLL splits x 4 x 128-bit loads in flight per thread)
                 const float* base = p.slabs + (size_t) tile_id * slab_elems + (size_t) T * MT;
                 const size_t split_stride = (size_t) m_tiles * n_tiles * slab_elems;
-                const int m_valid = min(MT, p.M - m_tile * MT);
 #pragma unroll 1
                 for (int c16 = 0; c16 * 16 < m_valid; ++c16)
                 {
-                    float sum[16];
+                    float sum[16], res[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
+                    {
                         sum[i] = 0.f;
+                        const int ml = c16 * 16 + i;
+                        res[i] = (has_res && ml < m_valid && n < p.N)
+                            ? __half2float(p.residual[(size_t) (m_tile * MT + ml) * p.ldc + n])
+                            : 0.f;
+                    }
                     constexpr int SPLIT_UNROLL = 4;
                     for (int s0 = 0; s0 < p.splits; s0 += SPLIT_UNROLL)
                     {
@@ -375,10 +537,8 @@ __global__ void __launch_bounds__(192, 1)
                         {
                             const int ml = c16 * 16 + i;
                             if (ml < m_valid)
-                            {
-                                const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
-                                p.C[idx] = epilogue_apply(sum[i], 1.0f, p.bias, p.activation, p.residual, n, idx);
-                            }
+                                p.C[(size_t) (m_tile * MT + ml) * p.ldc + n]
+                                    = finish_output(sum[i], p.bias, p.activation, has_res, res[i], n);
                         }
                     }
                 }
@@ -386,6 +546,46 @@ __global__ void __launch_bounds__(192, 1)
                     p.counters[tile_id] = 0; // self-reset for the next launch using this slot
             }
         }
+    }
+
+    if (p.cluster)
+    {
+        // ---- split-K reduction through distributed shared memory: every CTA of the cluster finishes a slice of
+        // the 128-column tile by summing the partial tiles of all ranks in rank order (deterministic) ----
+        __syncwarp();
+        cluster_sync_all(); // partial tiles of all CTAs are written
+        if (warp < 4)
+        {
+            const int T = threadIdx.x;
+            const uint32_t S = (uint32_t) p.splits;
+            const uint32_t rank = cluster_ctarank();
+            const int nslice = 128 / (int) S;
+            const int n_lo = (int) rank * nslice;
+            const int m_valid = min(MT, p.M - m_tile * MT);
+            const bool has_res = p.residual != nullptr;
+            const float* part = reinterpret_cast<const float*>(smW);
+            for (int e = T; e < nslice * m_valid; e += 128)
+            {
+                const int ml = e / nslice;
+                const int nl = n_lo + e % nslice;
+                const int n = n_tile * 128 + nl;
+                const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
+                const float res = (has_res && n < p.N) ? __half2float(p.residual[idx]) : 0.f;
+                const uint32_t laddr = smem_u32(part + (size_t) nl * MT + ml);
+                float v[8];
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q)
+                    v[q] = (q < S) ? ld_dsmem_f32(laddr, q) : 0.f;
+                float sum = 0.f;
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q)
+                    sum += v[q];
+                if (n < p.N)
+                    p.C[idx] = finish_output(sum, p.bias, p.activation, has_res, res, n);
+            }
+        }
+        __syncwarp();
+        cluster_sync_all(); // nobody exits (and frees its shared memory) while peers may still read it
     }
 
     // ---- teardown ----
@@ -584,11 +784,19 @@ int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uin
 struct TcPlan
 {
     int MT, m_tiles, n_tiles, splits;
+    int cluster; // 1: splits CTAs per tile form a cluster (DSMEM reduction); 0: global fp32 slabs
     size_t slab_bytes;
 };
 
+static int g_splitk_mode = -1; // -1 auto (env B200_SPLITK: "cluster" | "global"), 0 global slabs, 1 cluster
+
 TcPlan plan_tc(int M, int N, int K)
 {
+    if (g_splitk_mode < 0)
+    {
+        const char* e = getenv("B200_SPLITK");
+        g_splitk_mode = (e != nullptr && e[0] == 'g') ? 0 : 1;
+    }
     TcPlan pl{};
     pl.MT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     pl.m_tiles = (M + pl.MT - 1) / pl.MT;
@@ -597,17 +805,32 @@ TcPlan plan_tc(int M, int N, int K)
     const int tiles = pl.m_tiles * pl.n_tiles;
     const int sms = num_sms();
     int splits = 1;
+    int cluster = 0;
     if (tiles < sms && tiles <= 4096)
     {
-        splits = sms / tiles;
-        // keep at least 2 k-blocks per split so the per-CTA fixed cost is amortised
-        if (splits > kb_total / 2)
-            splits = kb_total / 2;
-        if (splits < 1)
-            splits = 1;
+        if (g_splitk_mode == 1 && pl.MT <= 64)
+        {
+            // cluster split-K: power-of-two cluster (<= 8, portable) along z; up to two CTAs per SM overall, at least
+            // two k-blocks per CTA
+            int s2 = 8;
+            while (s2 > 1 && (tiles * s2 > 2 * sms || kb_total < 2 * s2))
+                s2 >>= 1;
+            splits = s2;
+            cluster = s2 > 1 ? 1 : 0;
+        }
+        else
+        {
+            splits = sms / tiles;
+            // keep at least 2 k-blocks per split so the per-CTA fixed cost is amortised
+            if (splits > kb_total / 2)
+                splits = kb_total / 2;
+            if (splits < 1)
+                splits = 1;
+        }
     }
     pl.splits = splits;
-    pl.slab_bytes = splits > 1 ? (size_t) splits * tiles * 128 * pl.MT * sizeof(float) : 0;
+    pl.cluster = cluster;
+    pl.slab_bytes = (splits > 1 && !cluster) ? (size_t) splits * tiles * 128 * pl.MT * sizeof(float) : 0;
     return pl;
 }
 
@@ -649,13 +872,38 @@ static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcPar
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr_set = true;
     }
-    B200_LAUNCH(kern, grid, dim3(192), smem, stream, tmW, tmX, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl_enabled())
+    {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (p.cluster)
+    {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = (unsigned) p.splits;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    count_launch();
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmW, tmX, p));
     return B200_OK;
 }
 
-// tcgen05 path entry: any M >= 1.
+// tcgen05 path entry: any M >= 1.  ln_gamma != nullptr: A is the raw residual stream and LayerNorm(A) is the operand.
 int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
-    int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream)
+    int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+    const __half* ln_gamma, const __half* ln_beta, float ln_eps)
 {
     const TcPlan pl = plan_tc(M, N, K);
     B200_REQUIRE(pl.slab_bytes == 0 || (workspace != nullptr && workspace_bytes >= pl.slab_bytes), B200_ERR_WORKSPACE,
@@ -681,6 +929,13 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     p.C = C;
     p.slabs = static_cast<float*>(workspace);
     p.counters = tc_counter_slot(pl.m_tiles * pl.n_tiles <= kCounterSlotInts ? pl.m_tiles * pl.n_tiles : 1);
+    if (ln_gamma != nullptr)
+    {
+        p.x_raw = A;
+        p.ln_gamma = ln_gamma;
+        p.ln_beta = ln_beta;
+        p.ln_eps = ln_eps;
+    }
     p.M = M;
     p.N = N;
     p.K = K;
@@ -688,6 +943,7 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     p.activation = activation;
     p.kb_total = K / 64;
     p.splits = pl.splits;
+    p.cluster = pl.cluster;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     switch (pl.MT)
     {

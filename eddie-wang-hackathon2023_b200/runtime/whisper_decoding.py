@@ -106,7 +106,8 @@ class WhisperDecoding:
         self.ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         self.graph = None
         # side stream that pulls the next layer's cross-KV cache into L2 while the current layer's small kernels run
-        self.prefetch_cross_kv = os.environ.get("B200_XKV_PREFETCH", "1") != "0"
+        self.prefetch_cross_kv = os.environ.get("B200_XKV_PREFETCH", "0") != "0"
+        self.fuse_ln = os.environ.get("B200_FUSE_LN", "1") != "0"
         self._side = torch.cuda.Stream(device=dev) if torch.cuda.is_available() else None
         self._pinned_in = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
         self._pinned_out = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
@@ -122,6 +123,14 @@ class WhisperDecoding:
             residual.data_ptr() if residual is not None else None, out.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
             self._st())
         _lib.check(rc, "woq gemm")
+
+    def _gemm_ln(self, x, wb, rows, lin, out, act=_lib.ACT_NONE):
+        """out = act(LayerNorm(x; wb) @ W + bias): the LayerNorm is folded into the GEMM kernel's operand path."""
+        rc = self.lib.b200_woq_int8_gemm_ln_fused(
+            x.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), 1e-5, rows, lin.k, lin.weight.data_ptr(),
+            lin.scales.data_ptr(), lin.n, lin.bias.data_ptr() if lin.bias is not None else None, act, None,
+            out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self._st())
+        _lib.check(rc, "woq gemm (fused LayerNorm)")
 
     def _ln(self, x, wb, out, rows):
         _lib.check(self.lib.b200_layernorm_fp16(x.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), out.data_ptr(), rows,
@@ -174,8 +183,11 @@ class WhisperDecoding:
             self._side.wait_stream(main)
             self._prefetch(0)
         for i, lay in enumerate(self.layers):
-            self._ln(x, lay["attn_ln"], h, rows)
-            self._gemm(h, rows, lay["qkv"], qkv)
+            if self.fuse_ln:
+                self._gemm_ln(x, lay["attn_ln"], rows, lay["qkv"], qkv)
+            else:
+                self._ln(x, lay["attn_ln"], h, rows)
+                self._gemm(h, rows, lay["qkv"], qkv)
             if context:
                 rc = self.lib.b200_attention_context(
                     qkv.data_ptr(), input_lengths.data_ptr() if input_lengths is not None else None, ctx.data_ptr(),
@@ -193,8 +205,11 @@ class WhisperDecoding:
                 p.max_seq_len, p.past_kv_length, p.int8_kv_cache, p.q_scaling = self.Smax, 0, 1, 1.0
                 _lib.check(self.lib.b200_mmha_generation(ctypes.byref(p), st), "mmha_generation")
             self._gemm(ctx, rows, lay["attn_out"], x, residual=x)
-            self._ln(x, lay["cross_ln"], h, rows)
-            self._gemm(h, rows, lay["cross_q"], q)
+            if self.fuse_ln:
+                self._gemm_ln(x, lay["cross_ln"], rows, lay["cross_q"], q)
+            else:
+                self._ln(x, lay["cross_ln"], h, rows)
+                self._gemm(h, rows, lay["cross_q"], q)
             rc = self.lib.b200_cross_attention(q.data_ptr(), self.cross_kv[i].data_ptr(), lay["ckv_qo"].data_ptr(),
                                                ctx.data_ptr(), rows, s_q, H, Dh, self.S_enc, 1, self.ws.data_ptr(),
                                                self.ws.numel(), st)
@@ -204,8 +219,11 @@ class WhisperDecoding:
                 self._side.wait_stream(main)
                 self._prefetch(i + 1)
             self._gemm(ctx, rows, lay["cross_out"], x, residual=x)
-            self._ln(x, lay["mlp_ln"], h, rows)
-            self._gemm(h, rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF)
+            if self.fuse_ln:
+                self._gemm_ln(x, lay["mlp_ln"], rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF)
+            else:
+                self._ln(x, lay["mlp_ln"], h, rows)
+                self._gemm(h, rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF)
             self._gemm(u, rows, lay["fc2"], x, residual=x)
         if prefetch:
             main.wait_stream(self._side)

@@ -104,6 +104,13 @@ int b200_woq_int8_gemm(const void* A, int M, int K, const int8_t* Wproc, const v
 int b200_woq_int8_gemm_fused(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N,
     const void* bias, int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes,
     b200_stream_t stream);
+/* LayerNorm folded into the matmul: C = epilogue( LN(X; gamma, beta, eps) x W ).  X [M, K] fp16 is the raw residual
+ * stream; the normalised activations (rounded to fp16 exactly like b200_layernorm_fp16) are produced inside the GEMM
+ * kernel while the first weight tiles are in flight, saving the separate LayerNorm launch of the reference graph
+ * (T/tensorrt_llm/models/whisper/model.py:86-118).  With M <= 4 (SIMT path) the workspace must hold M*K fp16. */
+int b200_woq_int8_gemm_ln_fused(const void* X, const void* ln_gamma, const void* ln_beta, float ln_eps, int M, int K,
+    const int8_t* Wproc, const void* scales, int N, const void* bias, int activation, const void* residual, void* C,
+    void* workspace, size_t workspace_bytes, b200_stream_t stream);
 /* Forces a kernel family for tests/benchmarks: 0 = auto, 1 = SIMT GEMV, 2 = tcgen05 GEMM. */
 int b200_woq_set_kernel_policy(int policy);
 /* One-time allocation of library-owned device state (split-K tile counters).  Call before CUDA-graph capture. */

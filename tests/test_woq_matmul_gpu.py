@@ -165,3 +165,69 @@ def test_errors_and_empty():
     assert rc == 0  # empty batch is a no-op
     rc = lib.b200_woq_int8_gemm(None, 1, 64, w.data_ptr(), s.data_ptr(), 64, o.data_ptr(), None, 0, None)
     assert rc == 1
+
+
+@pytest.mark.parametrize("policy,m,k,n", [("tc", 16, 1280, 3840), ("tc", 16, 1280, 5120), ("tc", 5, 384, 1152),
+                                          ("tc", 48, 1280, 1280), ("tc", 100, 1280, 1280), ("tc", 300, 1280, 1280),
+                                          ("simt", 3, 1280, 1280)])
+def test_layernorm_fused_gemm(policy, m, k, n):
+    """b200_woq_int8_gemm_ln_fused == LayerNorm kernel followed by the plain GEMM (same fp16 rounding of LN(x))."""
+    import b200_whisper as bw
+    from b200_whisper import _lib
+    from b200_whisper.functional import layer_norm
+    lib = _lib.load()
+    torch.manual_seed(m + n)
+    x = (torch.randn((m, k)) * 2 + 0.3).half().cuda()
+    gamma = (1 + 0.1 * torch.randn(k)).half().cuda()
+    beta = (0.1 * torch.randn(k)).half().cuda()
+    weight = gen((k, n), seed=11) * 0.05
+    bias = gen((n,), seed=12).cuda()
+    raw, proc, scales = bw.ops._symmetric_quantize_last_axis_of_batched_matrix(weight.cuda(), torch.int8)
+    h = layer_norm(x, (k,), gamma, beta, 1e-5)
+    ref = run_plugin(h.cpu(), proc.cpu(), scales.cpu(), policy, bias=bias, activation="gelu")
+    out = torch.empty((m, n), dtype=torch.float16, device="cuda")
+    ws = torch.empty((lib.b200_woq_workspace_bytes(m, n, k) + m * k * 2,), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.b200_woq_set_kernel_policy(POLICIES[policy]))
+    try:
+        rc = lib.b200_woq_int8_gemm_ln_fused(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, m, k, proc.data_ptr(),
+                                             scales.data_ptr(), n, bias.data_ptr(), _lib.ACT_GELU_ERF, None, out.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "ln fused gemm")
+        torch.cuda.synchronize()
+    finally:
+        lib.b200_woq_set_kernel_policy(0)
+    # LN(x) is rounded to fp16 the same way in both paths; accumulation order is identical -> tiny differences only
+    assert (out.cpu().float() - ref.float()).abs().max().item() <= 2e-3 * ref.float().abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("mode", ["cluster", "global"])
+def test_splitk_modes_agree(mode, monkeypatch):
+    """Cluster (DSMEM) and global-slab split-K reductions are both deterministic and agree to fp32 rounding."""
+    import subprocess
+    import sys
+    code = r"""
+import torch, sys
+sys.path.insert(0, '.')
+import b200_whisper as bw
+from b200_whisper.quantization.functional import weight_only_quant_matmul
+torch.manual_seed(0)
+k, n, m = 5120, 1280, 16
+a = (torch.rand((m, k)) * 2 - 1).half().cuda()
+w = ((torch.rand((k, n)) * 2 - 1) * 0.05).half().cuda()
+proc, scales = bw.ops.symmetric_quantize_last_axis_of_batched_matrix(w, torch.int8)
+o1 = weight_only_quant_matmul(a, proc, scales, 1).clone()
+o2 = weight_only_quant_matmul(a, proc, scales, 1).clone()
+torch.cuda.synchronize()
+assert torch.equal(o1, o2)
+w16 = None
+print(float(o1.float().abs().sum()))
+"""
+    import os
+    env = dict(os.environ, B200_SPLITK=mode)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert r.returncode == 0, r.stderr[-2000:]
+    test_splitk_modes_agree.results = getattr(test_splitk_modes_agree, "results", {})
+    test_splitk_modes_agree.results[mode] = float(r.stdout.strip().splitlines()[-1])
+    if len(test_splitk_modes_agree.results) == 2:
+        a, b = test_splitk_modes_agree.results.values()
+        assert abs(a - b) <= 1e-3 * abs(a)
