@@ -46,6 +46,7 @@ _SIGS = {
     "b200_woq_int8_gemm_fused": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200_woq_int8_gemm_ln_fused": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200_woq_set_kernel_policy": (_i, [_i]),
+    "b200_debug_tc_timing": (_i, [_vp]),
     "b200_mmha_generation": (_i, [ctypes.POINTER(MmhaParams), _vp]),
     "b200_attention_context": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "b200_cross_attention_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -14,6 +14,8 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     const __half* ln_gamma, const __half* ln_beta, float ln_eps);
 size_t woq_tc_workspace_bytes(int max_m, int N, int K);
 int tc_init();
+void tc_set_debug_buffer(long long* p);
+bool woq_tc_can_fuse_ln(int M, int K);
 
 static int g_policy = 0; // 0 auto, 1 simt, 2 tcgen05
 } // namespace b200
@@ -48,7 +50,7 @@ static int woq_dispatch(const void* A, int M, int K, const int8_t* Wproc, const 
         return B200_OK; // empty batch: nothing to do (the reference would launch an empty grid)
     B200_REQUIRE_DEVICE();
     const bool simt = (g_policy == 1) || (g_policy == 0 && M <= 4);
-    if (simt)
+    if (simt || (ln_gamma != nullptr && !woq_tc_can_fuse_ln(M, K)))
     {
         const __half* a = static_cast<const __half*>(A);
         if (ln_gamma != nullptr)
@@ -56,14 +58,22 @@ static int woq_dispatch(const void* A, int M, int K, const int8_t* Wproc, const 
             // the SIMT GEMV keeps its activations in registers: normalise into the workspace first
             const size_t need = (size_t) M * K * sizeof(__half);
             B200_REQUIRE(workspace != nullptr && workspace_bytes >= need, B200_ERR_WORKSPACE,
-                "woq gemm (LayerNorm + SIMT): workspace of %zu bytes needed", need);
+                "woq gemm (separate LayerNorm): workspace of %zu bytes needed", need);
             if (int rc = b200_layernorm_fp16(A, ln_gamma, ln_beta, workspace, M, K, ln_eps, stream))
                 return rc;
             a = static_cast<const __half*>(workspace);
+            // the rest of the workspace stays available for split-K slabs
+            const size_t used = (need + 255) & ~size_t(255);
+            workspace = static_cast<char*>(workspace) + used;
+            workspace_bytes = workspace_bytes > used ? workspace_bytes - used : 0;
         }
-        return woq_gemv_simt(a, M, K, reinterpret_cast<const uint8_t*>(Wproc), static_cast<const __half*>(scales), N,
+        if (simt)
+            return woq_gemv_simt(a, M, K, reinterpret_cast<const uint8_t*>(Wproc), static_cast<const __half*>(scales), N,
+                static_cast<const __half*>(bias), activation, static_cast<const __half*>(residual),
+                static_cast<__half*>(C), as_stream(stream));
+        return woq_gemm_tc(a, M, K, reinterpret_cast<const uint8_t*>(Wproc), static_cast<const __half*>(scales), N,
             static_cast<const __half*>(bias), activation, static_cast<const __half*>(residual), static_cast<__half*>(C),
-            as_stream(stream));
+            workspace, workspace_bytes, as_stream(stream), nullptr, nullptr, 0.f);
     }
     return woq_gemm_tc(static_cast<const __half*>(A), M, K, reinterpret_cast<const uint8_t*>(Wproc),
         static_cast<const __half*>(scales), N, static_cast<const __half*>(bias), activation,
@@ -100,4 +110,12 @@ extern "C" int b200_init(void)
 {
     B200_REQUIRE_DEVICE();
     return tc_init();
+}
+
+// Debug aid: device buffer of >= 16 int64 that receives clock64() stamps of CTA (0,0,0) of every following tcgen05
+// GEMM launch (phase boundaries, see TC_STAMP in woq_gemm_tc.cu); NULL switches it off.
+extern "C" int b200_debug_tc_timing(void* device_buffer)
+{
+    tc_set_debug_buffer(static_cast<long long*>(device_buffer));
+    return B200_OK;
 }

@@ -53,7 +53,15 @@ struct TcParams
     int kb_total; // K / 64
     int splits;
     int cluster;  // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
+    long long* dbg; // optional: clock64() stamps of CTA (0,0,0) at the phase boundaries (b200_debug_tc_timing)
 };
+
+#define TC_STAMP(slot)                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)                                 \
+            p.dbg[slot] = clock64();                                                                                   \
+    } while (0)
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -158,17 +166,76 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
     return (uint64_t) ((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+__device__ __forceinline__ void tc_st_x16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_ld_x8(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// remote (or own) shared-memory store that completes `bytes` on the destination CTA's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar)
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "r"(__float_as_uint(v)), "r"(remote_mbar)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+    return remote;
+}
+
+constexpr int kTcDequantWarps = 8;
+constexpr int kTcThreads = (kTcDequantWarps + 2) * 32; // + TMA producer warp + MMA/TMEM warp
+
+// Shared-memory carve-up, shared by the kernel and the host-side size computation.
 template <int MT, int SS, int AS>
-__global__ void __launch_bounds__(192, 1)
+struct TcSmem
+{
+    static constexpr int XTileBytes = MT * 128;
+    static constexpr size_t ring = (size_t) SS * (kWTileBytes + XTileBytes);
+    static constexpr size_t rbuf = (size_t) 128 * MT * sizeof(float); // cluster reduction inbox [S][MT][128/S]
+    static constexpr size_t bars = sizeof(uint64_t) * (2 * SS + 2 * AS + 2) + 16;
+
+    static constexpr size_t ln_bytes(int K)
+    {
+        return (size_t) MT * K * 2 + (size_t) 2 * K * 2 + (size_t) MT * 2 * sizeof(float);
+    }
+
+    static constexpr size_t total(bool cluster, bool ln, int K)
+    {
+        return 1024 + ring + bars + (cluster ? rbuf : 0) + (ln ? ln_bytes(K) : 0);
+    }
+};
+
+template <int MT, int SS, int AS>
+__global__ void __launch_bounds__(kTcThreads, 1)
     woq_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const TcParams p)
 {
-    constexpr int XTileBytes = MT * 128;
+    using L = TcSmem<MT, SS, AS>;
+    constexpr int XTileBytes = L::XTileBytes;
     constexpr uint32_t kTmemCols = tmem_cols_pow2(32 * AS + MT);
     constexpr uint32_t kDCol = 32 * AS;
-    constexpr int kRowGroups = MT / 16;
+    constexpr int kHalfCols = MT / 2; // accumulator columns handled by one k-half warp group in the epilogue
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=f16 (0), K-major both,
     // N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t) (MT >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+    constexpr int kProducerWarp = kTcDequantWarps, kMmaWarp = kTcDequantWarps + 1;
+    constexpr int kDq = kTcDequantWarps * 32;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms (TMA and UMMA agree on address bits 7..9)
@@ -180,8 +247,16 @@ __global__ void __launch_bounds__(192, 1)
     uint64_t* a_ready = smem_free + SS;
     uint64_t* mma_done = a_ready + AS;
     uint64_t* acc_done = mma_done + AS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+    uint64_t* red_bar = acc_done + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 1);
     int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+    uint8_t* extra = reinterpret_cast<uint8_t*>(full) + L::bars;
+    float* rbuf = reinterpret_cast<float*>(extra);                       // cluster mode: [S][MT][128/S]
+    uint8_t* ln_base = extra + (p.cluster ? L::rbuf : 0);
+    __half* ln_x = reinterpret_cast<__half*>(ln_base);                   // fused LN: [MT][K] raw rows
+    __half* ln_g = ln_x + (size_t) MT * p.K;                             // [K]
+    __half* ln_b = ln_g + p.K;                                           // [K]
+    float* ln_stat = reinterpret_cast<float*>(ln_b + p.K);               // [MT][2] mean, rstd
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -190,55 +265,74 @@ __global__ void __launch_bounds__(192, 1)
     const int kb_end = (int) (((long long) (split + 1) * p.kb_total) / p.splits);
     const int nkb = kb_end - kb_begin;
     const bool fused_ln = p.x_raw != nullptr;
+    if (threadIdx.x == 0)
+        TC_STAMP(0);
 
+    // ---- prologue.  The producer thread owns the `full` barriers: it initialises them and immediately starts the
+    // weight stream (weights never depend on the previous kernel), while the other warps set up the rest. ----
+    const int pre = nkb < SS ? nkb : SS;
+    const uint32_t tx = kWTileBytes + (fused_ln ? 0 : XTileBytes);
+    if (warp == kProducerWarp && lane == 0)
     {
-        // one barrier per thread, initialised in parallel
+        for (int s = 0; s < SS; ++s)
+            mbar_init(&full[s], fused_ln ? 1 + kTcDequantWarps : 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+        for (int i = 0; i < pre; ++i)
+        {
+            mbar_arrive_expect_tx(&full[i], tx);
+            tma_load_2d(smW + i * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[i]);
+        }
+        TC_STAMP(2);
+    }
+    {
         const int t = threadIdx.x;
         if (t < SS)
-            mbar_init(&full[t], fused_ln ? 5 : 1); // producer (+ the four LayerNorm warps writing the B tile)
-        else if (t < 2 * SS)
-            mbar_init(&smem_free[t - SS], 1);
-        else if (t < 2 * SS + AS)
-            mbar_init(&a_ready[t - 2 * SS], 4);
-        else if (t < 2 * SS + 2 * AS)
-            mbar_init(&mma_done[t - 2 * SS - AS], 1);
-        else if (t == 2 * SS + 2 * AS)
+            mbar_init(&smem_free[t], 1);
+        else if (t < SS + AS)
+            mbar_init(&a_ready[t - SS], kTcDequantWarps);
+        else if (t < SS + 2 * AS)
+            mbar_init(&mma_done[t - SS - AS], 1);
+        else if (t == SS + 2 * AS)
             mbar_init(acc_done, 1);
-        if (t <= 2 * SS + 2 * AS)
+        else if (t == SS + 2 * AS + 1)
+        {
+            mbar_init(red_bar, 1);
+            if (p.cluster)
+                mbar_arrive_expect_tx(red_bar, (uint32_t) (128 * MT * sizeof(float))); // inbox bytes from all ranks
+        }
+        if (t <= SS + 2 * AS + 1)
             fence_mbar_init();
     }
-    if (warp == 4 && lane == 0)
-    {
-        tma_prefetch_desc(&tmW);
-        if (!fused_ln)
-            tma_prefetch_desc(&tmX);
-    }
-    if (warp == 5)
+    if (warp == kMmaWarp)
     {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // dequant threads: column scale requested early so its latency hides behind the barrier
+    const int T = ((warp & 3) << 5) | lane; // weight column inside the tile == TMEM lane (warps 0-3 and 4-7 alias)
+    const int kh = (warp >> 2) & 1;         // which half of the 64-wide k-block / of the accumulator columns
+    const int n = n_tile * 128 + T;
+    __half sc = __float2half(0.f);
+    if (warp < kTcDequantWarps && n < p.N)
+        sc = __ldg(p.scales + n);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.cluster)
+        cluster_sync_all(); // every rank's inbox barrier is armed before anybody can push into it
     grid_dep_launch_dependents(); // PDL: the next kernel may start its own prologue / weight prefetch now
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0)
+        TC_STAMP(1);
 
-    if (warp == 4)
+    if (warp == kProducerWarp)
     {
-        // ===== TMA producer =====
+        // ===== TMA producer (continued) =====
         if (lane == 0)
         {
-            const uint32_t tx = kWTileBytes + (fused_ln ? 0 : XTileBytes);
-            const int pre = nkb < SS ? nkb : SS;
-            // weights first: they do not depend on the previous kernel
-            for (int i = 0; i < pre; ++i)
-            {
-                mbar_arrive_expect_tx(&full[i], tx);
-                tma_load_2d(smW + i * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[i]);
-            }
             if (!fused_ln)
             {
                 grid_dep_wait();
@@ -256,7 +350,7 @@ __global__ void __launch_bounds__(192, 1)
             }
         }
     }
-    else if (warp == 5)
+    else if (warp == kMmaWarp)
     {
         // ===== MMA issuer =====
         if (lane == 0)
@@ -277,36 +371,49 @@ __global__ void __launch_bounds__(192, 1)
                 }
                 tc_commit(&mma_done[as]);
                 tc_commit(&smem_free[ss]);
+                if (i == 0)
+                    TC_STAMP(5);
             }
             tc_commit(acc_done);
+            TC_STAMP(6);
         }
     }
     else
     {
-        // ===== warps 0..3: (LayerNorm of the activation tile,) dequant, then epilogue =====
-        const int T = threadIdx.x; // weight column inside the tile == TMEM lane
-        const int n = n_tile * 128 + T;
+        // ===== warps 0..7: (LayerNorm of the activation tile,) dequant, then epilogue =====
+        const int tq = threadIdx.x; // 0..255
         const int jl = T >> 1, hf = T & 1, sw = jl & 7;
-        const __half sc = (n < p.N) ? p.scales[n] : __float2half(0.f);
         const __half2 sc2 = __half2half2(sc);
-        const uint32_t lane_field = (uint32_t) (warp * 32) << 16;
+        const uint32_t lane_field = (uint32_t) ((warp & 3) * 32) << 16;
 
-        // fused LayerNorm: 8 threads per activation row, 16 rows per pass; statistics stay in registers
-        const int rsub = T >> 3, csub = T & 7;
-        float ln_mean[kRowGroups], ln_rstd[kRowGroups];
         if (fused_ln)
         {
+            // stage the raw rows of this m-tile, gamma and beta in shared memory (coalesced, all loads in flight),
+            // then two-pass statistics per row (one warp per row) -- this runs while the weight tiles are in flight
             grid_dep_wait(); // x_raw is the previous kernel's output
-            const int nchunks = p.K >> 3;
-#pragma unroll
-            for (int g = 0; g < kRowGroups; ++g)
+            const int cpr = p.K >> 3; // 16-byte chunks per row
+            for (int idx = tq; idx < MT * cpr; idx += kDq)
             {
-                const int row = m_tile * MT + g * 16 + rsub;
-                const uint4* xr = reinterpret_cast<const uint4*>(p.x_raw + (size_t) (row < p.M ? row : 0) * p.K);
+                const int rl = idx / cpr, c = idx - rl * cpr;
+                const int row = m_tile * MT + rl;
+                uint4 u = make_uint4(0, 0, 0, 0);
+                if (row < p.M)
+                    u = __ldg(reinterpret_cast<const uint4*>(p.x_raw + (size_t) row * p.K) + c);
+                reinterpret_cast<uint4*>(ln_x)[idx] = u;
+            }
+            for (int idx = tq; idx < 2 * cpr; idx += kDq)
+            {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(idx < cpr ? p.ln_gamma : p.ln_beta) + (idx < cpr ? idx : idx - cpr));
+                reinterpret_cast<uint4*>(ln_g)[idx] = u; // gamma then beta, contiguous
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
+            for (int rl = warp; rl < MT; rl += kTcDequantWarps)
+            {
+                const uint4* xr = reinterpret_cast<const uint4*>(ln_x + (size_t) rl * p.K);
                 float sum = 0.f;
-                for (int c = csub; c < nchunks; c += 8)
+                for (int c = lane; c < cpr; c += 32)
                 {
-                    const uint4 u = __ldg(xr + c);
+                    const uint4 u = xr[c];
                     const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -315,14 +422,14 @@ __global__ void __launch_bounds__(192, 1)
                         sum += f.x + f.y;
                     }
                 }
-                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1)
+                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 const float mean = sum / (float) p.K;
                 float sq = 0.f;
-                for (int c = csub; c < nchunks; c += 8)
+                for (int c = lane; c < cpr; c += 32)
                 {
-                    const uint4 u = __ldg(xr + c); // L1 hit: same lines as the first pass
+                    const uint4 u = xr[c];
                     const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -331,64 +438,84 @@ __global__ void __launch_bounds__(192, 1)
                         sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
                     }
                 }
-                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                ln_mean[g] = mean;
-                ln_rstd[g] = rsqrtf(sq / (float) p.K + p.ln_eps);
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1)
+                    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                if (lane == 0)
+                {
+                    ln_stat[2 * rl] = mean;
+                    ln_stat[2 * rl + 1] = rsqrtf(sq / (float) p.K + p.ln_eps);
+                }
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
         }
 
-        for (int i = 0; i < nkb; ++i)
+        // writes LN(x)[rows of this m-tile][64 k of block i] into the SW128 K-major B tile of stage i % SS
+        auto write_ln_tile = [&](int i)
         {
-            const int ss = i % SS, as = i % AS;
-            if (fused_ln)
+            const int ss = i % SS;
+            if (i >= SS)
+                mbar_wait(&smem_free[ss], ((i / SS) - 1) & 1);
+            for (int idx = tq; idx < MT * 8; idx += kDq)
             {
-                // write LN(x)[rows of this m-tile][64 k of this block] into the SW128 K-major B tile
-                if (i >= SS)
-                    mbar_wait(&smem_free[ss], ((i / SS) - 1) & 1);
-                const int kcol = (kb_begin + i) * 64 + csub * 8;
-                const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(p.ln_gamma + kcol));
-                const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(p.ln_beta + kcol));
+                const int rl = idx >> 3, c = idx & 7;
+                const int kcol = (kb_begin + i) * 64 + c * 8;
+                const uint4 u = *reinterpret_cast<const uint4*>(ln_x + (size_t) rl * p.K + kcol);
+                const uint4 g4 = *reinterpret_cast<const uint4*>(ln_g + kcol);
+                const uint4 b4 = *reinterpret_cast<const uint4*>(ln_b + kcol);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
                 const __half2* gh = reinterpret_cast<const __half2*>(&g4);
                 const __half2* bh = reinterpret_cast<const __half2*>(&b4);
-#pragma unroll
-                for (int g = 0; g < kRowGroups; ++g)
+                const float mean = ln_stat[2 * rl], rstd = ln_stat[2 * rl + 1];
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (m_tile * MT + rl < p.M)
                 {
-                    const int rl = g * 16 + rsub;
-                    const int row = m_tile * MT + rl;
-                    uint4 o = make_uint4(0, 0, 0, 0);
-                    if (row < p.M)
-                    {
-                        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.x_raw + (size_t) row * p.K + kcol));
-                        const __half2* h = reinterpret_cast<const __half2*>(&u);
-                        __half2* oh = reinterpret_cast<__half2*>(&o);
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                        {
-                            const float2 f = __half22float2(h[j]);
-                            const float2 gf = __half22float2(gh[j]);
-                            const float2 bf = __half22float2(bh[j]);
-                            oh[j] = __floats2half2_rn((f.x - ln_mean[g]) * ln_rstd[g] * gf.x + bf.x,
-                                (f.y - ln_mean[g]) * ln_rstd[g] * gf.y + bf.y);
-                        }
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        const float2 f = __half22float2(h[j]);
+                        const float2 gf = __half22float2(gh[j]);
+                        const float2 bf = __half22float2(bh[j]);
+                        oh[j] = __floats2half2_rn((f.x - mean) * rstd * gf.x + bf.x, (f.y - mean) * rstd * gf.y + bf.y);
                     }
-                    *reinterpret_cast<uint4*>(smX + ss * XTileBytes + rl * 128 + ((csub ^ (rl & 7)) << 4)) = o;
                 }
-                fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(&full[ss]);
+                *reinterpret_cast<uint4*>(smX + ss * XTileBytes + rl * 128 + ((c ^ (rl & 7)) << 4)) = o;
             }
+            fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&full[ss]);
+        };
+
+        // this thread's 32 bytes of k-block i: chunks 2*kh and 2*kh+1 of its 64-byte column slice
+        uint4 v[2];
+        auto load_w = [&](int i)
+        {
+            const int ss = i % SS;
             mbar_wait(&full[ss], (i / SS) & 1);
             const uint8_t* rowp = smW + ss * kWTileBytes + jl * 128;
-            uint4 v[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                v[c] = *reinterpret_cast<const uint4*>(rowp + (((4 * hf + c) ^ sw) << 4));
-            uint32_t r[32];
+            for (int c = 0; c < 2; ++c)
+                v[c] = *reinterpret_cast<const uint4*>(rowp + (((4 * hf + 2 * kh + c) ^ sw) << 4));
+        };
+
+        if (nkb > 0)
+        {
+            if (fused_ln)
+                write_ln_tile(0);
+            if (tq == 0)
+                TC_STAMP(13);
+            load_w(0);
+            if (tq == 0)
+                TC_STAMP(3);
+        }
+        for (int i = 0; i < nkb; ++i)
+        {
+            const int as = i % AS;
+            uint32_t r[16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 2; ++c)
             {
                 const uint32_t words[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
 #pragma unroll
@@ -398,7 +525,7 @@ __global__ void __launch_bounds__(192, 1)
                     dequant_word(words[w], lo, hi);
                     lo = __hmul2(lo, sc2);
                     hi = __hmul2(hi, sc2);
-                    // chunk c = k-slice [16c, 16c+16): column 8c+w holds k = 2w, 2w+1; column 8c+4+w holds 8+2w, 8+2w+1
+                    // chunk = k-slice of 16: column 8c+w holds k = 2w, 2w+1; column 8c+4+w holds 8+2w, 8+2w+1
                     r[8 * c + w] = *reinterpret_cast<uint32_t*>(&lo);
                     r[8 * c + 4 + w] = *reinterpret_cast<uint32_t*>(&hi);
                 }
@@ -408,111 +535,155 @@ __global__ void __launch_bounds__(192, 1)
                 mbar_wait(&mma_done[as], ((i / AS) - 1) & 1);
                 tc_fence_after();
             }
-            tc_st_x32(tmem_base + lane_field + as * 32, r);
+            tc_st_x16(tmem_base + lane_field + as * 32 + kh * 16, r);
+            // overlap the TMEM store with fetching the next block
+            if (i + 1 < nkb)
+            {
+                if (fused_ln)
+                    write_ln_tile(i + 1);
+                load_w(i + 1);
+            }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&a_ready[as]);
+            if (i == 0 && tq == 0)
+                TC_STAMP(4);
         }
 
-        // ---- epilogue ----
+        // ---- epilogue: thread (T, kh) owns accumulator row T, columns [kh*MT/2, (kh+1)*MT/2) ----
         mbar_wait(acc_done, 0);
         tc_fence_after();
+        if (tq == 0)
+            TC_STAMP(7);
         const int n_tiles = gridDim.x, m_tiles = gridDim.y;
         const int tile_id = m_tile * n_tiles + n_tile;
         const bool direct = (p.splits == 1);
         const bool has_res = p.residual != nullptr;
         const int m_valid = min(MT, p.M - m_tile * MT);
-        // global split-K slab of this CTA: [128 n][MT m] fp32, thread T owns MT contiguous floats
         const size_t slab_elems = (size_t) 128 * MT;
         float* slab = (direct || p.cluster)
             ? nullptr
-            : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * slab_elems + (size_t) T * MT;
-        float* part = reinterpret_cast<float*>(smW); // cluster mode: this CTA's partial tile [128][MT] (ring is drained)
-#pragma unroll 1
-        for (int c16 = 0; c16 < MT / 16; ++c16)
+            : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * slab_elems + (size_t) T * MT + kh * kHalfCols;
+        // cluster mode: element (ml, n) goes to the rank that owns column slice n / nslice
+        const uint32_t S = (uint32_t) p.splits;
+        const int nslice = 128 / (int) S;
+        uint32_t push_addr = 0, push_bar = 0;
+        if (p.cluster)
         {
-            uint32_t acc[16];
-            tc_ld_x16(tmem_base + lane_field + kDCol + c16 * 16, acc);
+            const uint32_t owner = (uint32_t) (T / nslice);
+            const uint32_t rank = cluster_ctarank();
+            // inbox layout [sender rank][ml][nl]
+            push_addr = mapa_u32(smem_u32(rbuf + ((size_t) rank * MT) * nslice + (T % nslice)), owner);
+            push_bar = mapa_u32(smem_u32(red_bar), owner);
+        }
+#pragma unroll 1
+        for (int c8 = 0; c8 < kHalfCols / 8; ++c8)
+        {
+            uint32_t acc[8];
+            tc_ld_x8(tmem_base + lane_field + kDCol + kh * kHalfCols + c8 * 8, acc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int ml0 = kh * kHalfCols + c8 * 8;
             if (direct)
             {
-                float res[16];
+                float res[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                {
-                    const int ml = c16 * 16 + i;
-                    res[i] = (has_res && ml < m_valid && n < p.N)
-                        ? __half2float(p.residual[(size_t) (m_tile * MT + ml) * p.ldc + n])
+                for (int i = 0; i < 8; ++i)
+                    res[i] = (has_res && ml0 + i < m_valid && n < p.N)
+                        ? __half2float(p.residual[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n])
                         : 0.f;
-                }
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                {
-                    const int ml = c16 * 16 + i;
-                    if (ml < m_valid && n < p.N)
-                        p.C[(size_t) (m_tile * MT + ml) * p.ldc + n]
+                for (int i = 0; i < 8; ++i)
+                    if (ml0 + i < m_valid && n < p.N)
+                        p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
                             = finish_output(__uint_as_float(acc[i]), p.bias, p.activation, has_res, res[i], n);
-                }
             }
             else if (p.cluster)
             {
-                uint4* dst = reinterpret_cast<uint4*>(part + (size_t) T * MT + c16 * 16);
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4)
-                    dst[v4] = make_uint4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2], acc[4 * v4 + 3]);
+                for (int i = 0; i < 8; ++i)
+                    st_async_f32(push_addr + (uint32_t) ((ml0 + i) * nslice) * 4u, __uint_as_float(acc[i]), push_bar);
             }
             else
             {
-                uint4* dst = reinterpret_cast<uint4*>(slab + c16 * 16);
-#pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4)
-                    __stcg(dst + v4, make_uint4(acc[4 * v4], acc[4 * v4 + 1], acc[4 * v4 + 2], acc[4 * v4 + 3]));
+                uint4* dst = reinterpret_cast<uint4*>(slab + c8 * 8);
+                __stcg(dst, make_uint4(acc[0], acc[1], acc[2], acc[3]));
+                __stcg(dst + 1, make_uint4(acc[4], acc[5], acc[6], acc[7]));
             }
         }
-        if (!direct && !p.cluster)
+        if (tq == 0)
+            TC_STAMP(8);
+        if (p.cluster)
+        {
+            // ---- split-K reduction through distributed shared memory: every rank received the partial values of its
+            // column slice from all ranks (st.async + complete_tx on its inbox barrier) and sums them in rank order ----
+            mbar_wait(red_bar, 0);
+            if (tq == 0)
+                TC_STAMP(9);
+            const int n_lo = (int) cluster_ctarank() * nslice;
+            for (int e = tq; e < nslice * m_valid; e += kDq)
+            {
+                const int ml = e / nslice;
+                const int nl = e - ml * nslice;
+                const int nn = n_tile * 128 + n_lo + nl;
+                const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + nn;
+                const float res = (has_res && nn < p.N) ? __half2float(p.residual[idx]) : 0.f;
+                const float* src = rbuf + (size_t) ml * nslice + nl;
+                float sum = 0.f;
+#pragma unroll
+                for (uint32_t q = 0; q < 8; ++q)
+                    if (q < S)
+                        sum += src[(size_t) q * MT * nslice];
+                if (nn < p.N)
+                    p.C[idx] = finish_output(sum, p.bias, p.activation, has_res, res, nn);
+            }
+            if (tq == 0)
+                TC_STAMP(10);
+        }
+        else if (!direct)
         {
             __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (T == 0)
+            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
+            if (tq == 0)
             {
                 const int old = atomicAdd(&p.counters[tile_id], 1);
                 *last_flag = (old == p.splits - 1) ? 1 : 0;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
             if (*last_flag)
             {
                 __threadfence();
-                // deterministic reduction in split order; all loads of a 16-column group are independent and issued
-                // before the adds (SPLIT_UNROLL splits x 4 x 128-bit loads in flight per thread)
-                const float* base = p.slabs + (size_t) tile_id * slab_elems + (size_t) T * MT;
+                // deterministic reduction in split order; all loads of an 8-column group are independent and issued
+                // before the adds (SPLIT_UNROLL splits x 2 x 128-bit loads in flight per thread)
+                const float* base = p.slabs + (size_t) tile_id * slab_elems + (size_t) T * MT + kh * kHalfCols;
                 const size_t split_stride = (size_t) m_tiles * n_tiles * slab_elems;
 #pragma unroll 1
-                for (int c16 = 0; c16 * 16 < m_valid; ++c16)
+                for (int c8 = 0; c8 < kHalfCols / 8; ++c8)
                 {
-                    float sum[16], res[16];
+                    const int ml0 = kh * kHalfCols + c8 * 8;
+                    if (ml0 >= m_valid)
+                        break;
+                    float sum[8], res[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
+                    for (int i = 0; i < 8; ++i)
                     {
                         sum[i] = 0.f;
-                        const int ml = c16 * 16 + i;
-                        res[i] = (has_res && ml < m_valid && n < p.N)
-                            ? __half2float(p.residual[(size_t) (m_tile * MT + ml) * p.ldc + n])
+                        res[i] = (has_res && ml0 + i < m_valid && n < p.N)
+                            ? __half2float(p.residual[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n])
                             : 0.f;
                     }
                     constexpr int SPLIT_UNROLL = 4;
                     for (int s0 = 0; s0 < p.splits; s0 += SPLIT_UNROLL)
                     {
-                        uint4 v[SPLIT_UNROLL][4];
+                        uint4 w4[SPLIT_UNROLL][2];
 #pragma unroll
                         for (int u = 0; u < SPLIT_UNROLL; ++u)
                         {
                             const int sidx = min(s0 + u, p.splits - 1);
-                            const uint4* src = reinterpret_cast<const uint4*>(base + (size_t) sidx * split_stride + c16 * 16);
-#pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4)
-                                v[u][q4] = __ldcg(src + q4);
+                            const uint4* src = reinterpret_cast<const uint4*>(base + (size_t) sidx * split_stride + c8 * 8);
+                            w4[u][0] = __ldcg(src);
+                            w4[u][1] = __ldcg(src + 1);
                         }
 #pragma unroll
                         for (int u = 0; u < SPLIT_UNROLL; ++u)
@@ -520,12 +691,12 @@ __global__ void __launch_bounds__(192, 1)
                             if (s0 + u < p.splits)
                             {
 #pragma unroll
-                                for (int q4 = 0; q4 < 4; ++q4)
+                                for (int q4 = 0; q4 < 2; ++q4)
                                 {
-                                    sum[4 * q4 + 0] += __uint_as_float(v[u][q4].x);
-                                    sum[4 * q4 + 1] += __uint_as_float(v[u][q4].y);
-                                    sum[4 * q4 + 2] += __uint_as_float(v[u][q4].z);
-                                    sum[4 * q4 + 3] += __uint_as_float(v[u][q4].w);
+                                    sum[4 * q4 + 0] += __uint_as_float(w4[u][q4].x);
+                                    sum[4 * q4 + 1] += __uint_as_float(w4[u][q4].y);
+                                    sum[4 * q4 + 2] += __uint_as_float(w4[u][q4].z);
+                                    sum[4 * q4 + 3] += __uint_as_float(w4[u][q4].w);
                                 }
                             }
                         }
@@ -533,68 +704,27 @@ __global__ void __launch_bounds__(192, 1)
                     if (n < p.N)
                     {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                        {
-                            const int ml = c16 * 16 + i;
-                            if (ml < m_valid)
-                                p.C[(size_t) (m_tile * MT + ml) * p.ldc + n]
+                        for (int i = 0; i < 8; ++i)
+                            if (ml0 + i < m_valid)
+                                p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
                                     = finish_output(sum[i], p.bias, p.activation, has_res, res[i], n);
-                        }
                     }
                 }
-                if (T == 0)
+                if (tq == 0)
                     p.counters[tile_id] = 0; // self-reset for the next launch using this slot
             }
         }
     }
 
-    if (p.cluster)
-    {
-        // ---- split-K reduction through distributed shared memory: every CTA of the cluster finishes a slice of
-        // the 128-column tile by summing the partial tiles of all ranks in rank order (deterministic) ----
-        __syncwarp();
-        cluster_sync_all(); // partial tiles of all CTAs are written
-        if (warp < 4)
-        {
-            const int T = threadIdx.x;
-            const uint32_t S = (uint32_t) p.splits;
-            const uint32_t rank = cluster_ctarank();
-            const int nslice = 128 / (int) S;
-            const int n_lo = (int) rank * nslice;
-            const int m_valid = min(MT, p.M - m_tile * MT);
-            const bool has_res = p.residual != nullptr;
-            const float* part = reinterpret_cast<const float*>(smW);
-            for (int e = T; e < nslice * m_valid; e += 128)
-            {
-                const int ml = e / nslice;
-                const int nl = n_lo + e % nslice;
-                const int n = n_tile * 128 + nl;
-                const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
-                const float res = (has_res && n < p.N) ? __half2float(p.residual[idx]) : 0.f;
-                const uint32_t laddr = smem_u32(part + (size_t) nl * MT + ml);
-                float v[8];
-#pragma unroll
-                for (uint32_t q = 0; q < 8; ++q)
-                    v[q] = (q < S) ? ld_dsmem_f32(laddr, q) : 0.f;
-                float sum = 0.f;
-#pragma unroll
-                for (uint32_t q = 0; q < 8; ++q)
-                    sum += v[q];
-                if (n < p.N)
-                    p.C[idx] = finish_output(sum, p.bias, p.activation, has_res, res, n);
-            }
-        }
-        __syncwarp();
-        cluster_sync_all(); // nobody exits (and frees its shared memory) while peers may still read it
-    }
-
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 5)
+    if (warp == kMmaWarp)
     {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (lane == 0)
+            TC_STAMP(12);
     }
 }
 
@@ -788,6 +918,12 @@ struct TcPlan
     size_t slab_bytes;
 };
 
+static long long* g_tc_dbg = nullptr;
+void tc_set_debug_buffer(long long* p)
+{
+    g_tc_dbg = p;
+}
+
 static int g_splitk_mode = -1; // -1 auto (env B200_SPLITK: "cluster" | "global"), 0 global slabs, 1 cluster
 
 TcPlan plan_tc(int M, int N, int K)
@@ -865,16 +1001,17 @@ template <int MT, int SS, int AS>
 static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcParams& p, dim3 grid, cudaStream_t stream)
 {
     auto kern = woq_gemm_tc_kernel<MT, SS, AS>;
-    const size_t smem = 1024 + (size_t) SS * (kWTileBytes + MT * 128) + sizeof(uint64_t) * (2 * SS + 2 * AS + 1) + 16;
-    static bool attr_set = false;
-    if (!attr_set)
+    const size_t smem = TcSmem<MT, SS, AS>::total(p.cluster != 0, p.x_raw != nullptr, p.K);
+    B200_REQUIRE(smem <= 227 * 1024, B200_ERR_UNSUPPORTED, "woq gemm: %zu bytes of shared memory needed", smem);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem)
     {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        attr_set = true;
+        attr_smem = smem;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -898,6 +1035,14 @@ static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcPar
     count_launch();
     B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmW, tmX, p));
     return B200_OK;
+}
+
+// Can LayerNorm be folded into the GEMM for this shape?  (the raw rows of one m-tile are staged in shared memory)
+bool woq_tc_can_fuse_ln(int M, int K)
+{
+    if (M > 32)
+        return false;
+    return M <= 16 ? TcSmem<16, 8, 6>::total(true, true, K) <= 200 * 1024 : TcSmem<32, 8, 6>::total(true, true, K) <= 200 * 1024;
 }
 
 // tcgen05 path entry: any M >= 1.  ln_gamma != nullptr: A is the raw residual stream and LayerNorm(A) is the operand.
@@ -944,6 +1089,7 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     p.kb_total = K / 64;
     p.splits = pl.splits;
     p.cluster = pl.cluster;
+    p.dbg = g_tc_dbg;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     switch (pl.MT)
     {

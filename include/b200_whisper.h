@@ -113,6 +113,9 @@ int b200_woq_int8_gemm_ln_fused(const void* X, const void* ln_gamma, const void*
     void* workspace, size_t workspace_bytes, b200_stream_t stream);
 /* Forces a kernel family for tests/benchmarks: 0 = auto, 1 = SIMT GEMV, 2 = tcgen05 GEMM. */
 int b200_woq_set_kernel_policy(int policy);
+/* Debug aid: device buffer of >= 16 int64 receiving clock64() stamps of CTA (0,0,0) of each following tcgen05 GEMM
+ * launch at its phase boundaries; NULL switches it off. */
+int b200_debug_tc_timing(void* device_buffer);
 /* One-time allocation of library-owned device state (split-K tile counters).  Call before CUDA-graph capture. */
 int b200_init(void);
 
