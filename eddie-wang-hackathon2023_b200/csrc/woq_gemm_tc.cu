@@ -100,6 +100,20 @@ __device__ __forceinline__ __half finish_output(float acc, const __half* bias, i
     return o;
 }
 
+// true in exactly one (converged) lane of the warp
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before()
 {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -209,7 +223,8 @@ struct TcSmem
     static constexpr int XTileBytes = MT * 128;
     static constexpr size_t ring = (size_t) SS * (kWTileBytes + XTileBytes);
     static constexpr size_t rbuf = (size_t) 128 * MT * sizeof(float); // cluster reduction inbox [S][MT][128/S]
-    static constexpr size_t bars = sizeof(uint64_t) * (2 * SS + 2 * AS + 2) + 16;
+    static_assert(AS == SS, "one ring: smem stage s and TMEM A stage s are released together");
+    static constexpr size_t bars = sizeof(uint64_t) * (3 * SS + 2) + 16;
 
     static constexpr size_t ln_bytes(int K)
     {
@@ -243,10 +258,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint8_t* smW = smem;
     uint8_t* smX = smem + SS * kWTileBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smX + SS * XTileBytes);
-    uint64_t* smem_free = full + SS;
-    uint64_t* a_ready = smem_free + SS;
-    uint64_t* mma_done = a_ready + AS;
-    uint64_t* acc_done = mma_done + AS;
+    uint64_t* stage_free = full + SS;  // MMA of the block done: smem stage and TMEM A stage reusable
+    uint64_t* a_ready = stage_free + SS; // dequantized A tile is in TMEM (and the X tile has landed)
+    uint64_t* acc_done = a_ready + SS;
     uint64_t* red_bar = acc_done + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 1);
     int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // weight stream (weights never depend on the previous kernel), while the other warps set up the rest. ----
     const int pre = nkb < SS ? nkb : SS;
     const uint32_t tx = kWTileBytes + (fused_ln ? 0 : XTileBytes);
-    if (warp == kProducerWarp && lane == 0)
+    if (warp == kProducerWarp && elect_one_sync())
     {
         for (int s = 0; s < SS; ++s)
             mbar_init(&full[s], fused_ln ? 1 + kTcDequantWarps : 1);
@@ -288,20 +302,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     {
         const int t = threadIdx.x;
         if (t < SS)
-            mbar_init(&smem_free[t], 1);
-        else if (t < SS + AS)
+            mbar_init(&stage_free[t], 1);
+        else if (t < 2 * SS)
             mbar_init(&a_ready[t - SS], kTcDequantWarps);
-        else if (t < SS + 2 * AS)
-            mbar_init(&mma_done[t - SS - AS], 1);
-        else if (t == SS + 2 * AS)
+        else if (t == 2 * SS)
             mbar_init(acc_done, 1);
-        else if (t == SS + 2 * AS + 1)
+        else if (t == 2 * SS + 1)
         {
             mbar_init(red_bar, 1);
             if (p.cluster)
                 mbar_arrive_expect_tx(red_bar, (uint32_t) (128 * MT * sizeof(float))); // inbox bytes from all ranks
         }
-        if (t <= SS + 2 * AS + 1)
+        if (t <= 2 * SS + 1)
             fence_mbar_init();
     }
     if (warp == kMmaWarp)
@@ -324,14 +336,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (p.cluster)
         cluster_sync_all(); // every rank's inbox barrier is armed before anybody can push into it
     grid_dep_launch_dependents(); // PDL: the next kernel may start its own prologue / weight prefetch now
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     if (threadIdx.x == 0)
         TC_STAMP(1);
 
     if (warp == kProducerWarp)
     {
         // ===== TMA producer (continued) =====
-        if (lane == 0)
+        if (elect_one_sync())
         {
             if (!fused_ln)
             {
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int i = pre; i < nkb; ++i)
             {
                 const int ss = i % SS;
-                mbar_wait(&smem_free[ss], ((i / SS) - 1) & 1);
+                mbar_wait(&stage_free[ss], ((i / SS) - 1) & 1);
                 mbar_arrive_expect_tx(&full[ss], tx);
                 tma_load_2d(smW + ss * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[ss]);
                 if (!fused_ln)
@@ -352,38 +364,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     else if (warp == kMmaWarp)
     {
-        // ===== MMA issuer =====
-        if (lane == 0)
+        // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
+        const uint32_t d_tmem = tmem_base + kDCol;
+        for (int i = 0; i < nkb; ++i)
         {
-            const uint32_t d_tmem = tmem_base + kDCol;
-            for (int i = 0; i < nkb; ++i)
+            const int ss = i % SS;
+            // a_ready implies full[ss]: the dequant warps arrive on it only after they observed the TMA completion
+            mbar_wait(&a_ready[ss], (i / SS) & 1);
+            tc_fence_after();
+            if (lane == 0 && i < 12)
+                TC_STAMP(16 + 4 * i + 2);
+            const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smX + ss * XTileBytes));
+            if (elect_one_sync())
             {
-                const int ss = i % SS, as = i % AS;
-                mbar_wait(&full[ss], (i / SS) & 1);
-                mbar_wait(&a_ready[as], (i / AS) & 1);
-                tc_fence_after();
-                const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smX + ss * XTileBytes));
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
                 {
                     // K advance inside the 128-byte swizzle atom: 16 halves = 32 bytes = 2 descriptor units
-                    tc_mma_ts(d_tmem, tmem_base + as * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
+                    tc_mma_ts(d_tmem, tmem_base + ss * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
                 }
-                tc_commit(&mma_done[as]);
-                tc_commit(&smem_free[ss]);
-                if (i == 0)
-                    TC_STAMP(5);
+                tc_commit(&stage_free[ss]);
+                if (i == nkb - 1)
+                    tc_commit(acc_done);
             }
-            tc_commit(acc_done);
-            TC_STAMP(6);
+            __syncwarp();
+            if (lane == 0 && i < 12)
+                TC_STAMP(16 + 4 * i + 3);
         }
+        if (lane == 0)
+            TC_STAMP(6);
     }
     else
     {
         // ===== warps 0..7: (LayerNorm of the activation tile,) dequant, then epilogue =====
         const int tq = threadIdx.x; // 0..255
         const int jl = T >> 1, hf = T & 1, sw = jl & 7;
-        const __half2 sc2 = __half2half2(sc);
+        const float scf = __half2float(sc); // per-column dequant scale, applied in the epilogue
         const uint32_t lane_field = (uint32_t) ((warp & 3) * 32) << 16;
 
         if (fused_ln)
@@ -392,14 +408,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // then two-pass statistics per row (one warp per row) -- this runs while the weight tiles are in flight
             grid_dep_wait(); // x_raw is the previous kernel's output
             const int cpr = p.K >> 3; // 16-byte chunks per row
-            for (int idx = tq; idx < MT * cpr; idx += kDq)
+            // the rows of an m-tile are contiguous in x_raw: chunk idx of the tile is chunk (m_tile*MT*cpr + idx) of x_raw;
+            // loads are issued in independent batches of 10 so one L2 round trip covers a whole batch
             {
-                const int rl = idx / cpr, c = idx - rl * cpr;
-                const int row = m_tile * MT + rl;
-                uint4 u = make_uint4(0, 0, 0, 0);
-                if (row < p.M)
-                    u = __ldg(reinterpret_cast<const uint4*>(p.x_raw + (size_t) row * p.K) + c);
-                reinterpret_cast<uint4*>(ln_x)[idx] = u;
+                const uint4* src = reinterpret_cast<const uint4*>(p.x_raw) + (size_t) m_tile * MT * cpr;
+                const int valid = max(0, min(MT, p.M - m_tile * MT)) * cpr;
+                constexpr int LB = 10;
+                for (int base = 0; base < MT * cpr; base += LB * kDq)
+                {
+                    uint4 u[LB];
+#pragma unroll
+                    for (int j = 0; j < LB; ++j)
+                    {
+                        const int idx = base + j * kDq + tq;
+                        u[j] = (idx < valid) ? __ldg(src + idx) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < LB; ++j)
+                    {
+                        const int idx = base + j * kDq + tq;
+                        if (idx < MT * cpr)
+                            reinterpret_cast<uint4*>(ln_x)[idx] = u[j];
+                    }
+                }
             }
             for (int idx = tq; idx < 2 * cpr; idx += kDq)
             {
@@ -455,7 +486,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         {
             const int ss = i % SS;
             if (i >= SS)
-                mbar_wait(&smem_free[ss], ((i / SS) - 1) & 1);
+                mbar_wait(&stage_free[ss], ((i / SS) - 1) & 1);
             for (int idx = tq; idx < MT * 8; idx += kDq)
             {
                 const int rl = idx >> 3, c = idx & 7;
@@ -512,7 +543,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         for (int i = 0; i < nkb; ++i)
         {
-            const int as = i % AS;
+            const int as = i % SS;
             uint32_t r[16];
 #pragma unroll
             for (int c = 0; c < 2; ++c)
@@ -522,17 +553,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int w = 0; w < 4; ++w)
                 {
                     __half2 lo, hi;
-                    dequant_word(words[w], lo, hi);
-                    lo = __hmul2(lo, sc2);
-                    hi = __hmul2(hi, sc2);
+                    dequant_word(words[w], lo, hi); // exact integers; the column scale is applied to the fp32 accumulator
                     // chunk = k-slice of 16: column 8c+w holds k = 2w, 2w+1; column 8c+4+w holds 8+2w, 8+2w+1
                     r[8 * c + w] = *reinterpret_cast<uint32_t*>(&lo);
                     r[8 * c + 4 + w] = *reinterpret_cast<uint32_t*>(&hi);
                 }
             }
-            if (i >= AS)
+            if (i >= SS)
             {
-                mbar_wait(&mma_done[as], ((i / AS) - 1) & 1);
+                mbar_wait(&stage_free[as], ((i / SS) - 1) & 1);
                 tc_fence_after();
             }
             tc_st_x16(tmem_base + lane_field + as * 32 + kh * 16, r);
@@ -543,11 +572,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     write_ln_tile(i + 1);
                 load_w(i + 1);
             }
+            if (tq == 0 && i < 12)
+                TC_STAMP(16 + 4 * i + 0);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&a_ready[as]);
+            if (tq == 0 && i < 12)
+                TC_STAMP(16 + 4 * i + 1);
             if (i == 0 && tq == 0)
                 TC_STAMP(4);
         }
@@ -597,19 +630,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int i = 0; i < 8; ++i)
                     if (ml0 + i < m_valid && n < p.N)
                         p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
-                            = finish_output(__uint_as_float(acc[i]), p.bias, p.activation, has_res, res[i], n);
+                            = finish_output(__uint_as_float(acc[i]) * scf, p.bias, p.activation, has_res, res[i], n);
             }
             else if (p.cluster)
             {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    st_async_f32(push_addr + (uint32_t) ((ml0 + i) * nslice) * 4u, __uint_as_float(acc[i]), push_bar);
+                    st_async_f32(push_addr + (uint32_t) ((ml0 + i) * nslice) * 4u, __uint_as_float(acc[i]) * scf, push_bar);
             }
             else
             {
-                uint4* dst = reinterpret_cast<uint4*>(slab + c8 * 8);
-                __stcg(dst, make_uint4(acc[0], acc[1], acc[2], acc[3]));
-                __stcg(dst + 1, make_uint4(acc[4], acc[5], acc[6], acc[7]));
+                float4* dst = reinterpret_cast<float4*>(slab + c8 * 8);
+                __stcg(dst, make_float4(__uint_as_float(acc[0]) * scf, __uint_as_float(acc[1]) * scf,
+                                __uint_as_float(acc[2]) * scf, __uint_as_float(acc[3]) * scf));
+                __stcg(dst + 1, make_float4(__uint_as_float(acc[4]) * scf, __uint_as_float(acc[5]) * scf,
+                                    __uint_as_float(acc[6]) * scf, __uint_as_float(acc[7]) * scf));
             }
         }
         if (tq == 0)
@@ -800,11 +835,11 @@ __global__ void __launch_bounds__(192, 1)
     __syncthreads();
     tc_fence_after();
     grid_dep_launch_dependents(); // PDL: the next kernel may start its own prologue / weight prefetch now
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 4)
     {
-        if (lane == 0)
+        if (elect_one_sync())
         {
             const int pre = nkb < SS ? nkb : SS;
             for (int i = 0; i < pre; ++i)
@@ -827,21 +862,24 @@ __global__ void __launch_bounds__(192, 1)
     }
     else if (warp == 5)
     {
-        if (lane == 0)
+        // the whole warp runs the warp-uniform loop; one elected lane issues the tensor-core instructions
+        for (int i = 0; i < nkb; ++i)
         {
-            for (int i = 0; i < nkb; ++i)
+            const int ss = i % SS;
+            mbar_wait(&full[ss], (i / SS) & 1);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_k_sw128(smem_u32(smE + ss * ETileBytes));
+            const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smX + ss * XTileBytes));
+            if (elect_one_sync())
             {
-                const int ss = i % SS;
-                mbar_wait(&full[ss], (i / SS) & 1);
-                tc_fence_after();
-                const uint64_t adesc = umma_desc_k_sw128(smem_u32(smE + ss * ETileBytes));
-                const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smX + ss * XTileBytes));
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
                     tc_mma_ss(tmem_base, adesc + 2 * k4, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
                 tc_commit(&smem_free[ss]);
+                if (i == nkb - 1)
+                    tc_commit(acc_done);
             }
-            tc_commit(acc_done);
+            __syncwarp();
         }
     }
     else
@@ -1042,7 +1080,7 @@ bool woq_tc_can_fuse_ln(int M, int K)
 {
     if (M > 32)
         return false;
-    return M <= 16 ? TcSmem<16, 8, 6>::total(true, true, K) <= 200 * 1024 : TcSmem<32, 8, 6>::total(true, true, K) <= 200 * 1024;
+    return M <= 16 ? TcSmem<16, 6, 6>::total(true, true, K) <= 200 * 1024 : TcSmem<32, 6, 6>::total(true, true, K) <= 200 * 1024;
 }
 
 // tcgen05 path entry: any M >= 1.  ln_gamma != nullptr: A is the raw residual stream and LayerNorm(A) is the operand.
@@ -1093,11 +1131,11 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     switch (pl.MT)
     {
-    case 16: return launch_tc<16, 8, 6>(tmW, tmX, p, grid, stream);
-    case 32: return launch_tc<32, 8, 6>(tmW, tmX, p, grid, stream);
-    case 64: return launch_tc<64, 8, 6>(tmW, tmX, p, grid, stream);
-    case 128: return launch_tc<128, 6, 4>(tmW, tmX, p, grid, stream);
-    default: return launch_tc<256, 4, 8>(tmW, tmX, p, grid, stream);
+    case 16: return launch_tc<16, 6, 6>(tmW, tmX, p, grid, stream);
+    case 32: return launch_tc<32, 6, 6>(tmW, tmX, p, grid, stream);
+    case 64: return launch_tc<64, 6, 6>(tmW, tmX, p, grid, stream);
+    case 128: return launch_tc<128, 4, 4>(tmW, tmX, p, grid, stream);
+    default: return launch_tc<256, 4, 4>(tmW, tmX, p, grid, stream);
     }
 }
 

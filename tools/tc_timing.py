@@ -9,7 +9,7 @@ lib = _lib.load()
 names = {0: "entry", 1: "prologue done", 2: "TMA issued", 13: "dequant ready to wait", 3: "first tile landed", 4: "first A tile in TMEM",
          5: "first MMA committed", 6: "last MMA committed", 7: "accumulator ready", 8: "partial stored", 9: "cluster sync 1",
          10: "slice reduced+stored", 12: "TMEM freed"}
-dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(80, dtype=torch.int64, device="cuda")
 for (m, k, n, ln, res) in [(16, 1280, 1280, False, False), (16, 1280, 1280, False, True), (16, 1280, 3840, True, False),
                            (16, 1280, 5120, True, False), (16, 5120, 1280, False, True)]:
     torch.manual_seed(0)
@@ -40,4 +40,9 @@ for (m, k, n, ln, res) in [(16, 1280, 1280, False, False), (16, 1280, 1280, Fals
     for sl in [0, 1, 2, 13, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12]:
         if t[sl]:
             print(f"   {names[sl]:26s} +{t[sl]-t[0]:7d} cycles")
+    print("   per k-block (cycles since entry): dequant thread0 [loaded next, arrived]  mma thread [woke, committed]")
+    for i in range(12):
+        q = t[16 + 4 * i: 20 + 4 * i]
+        if any(q):
+            print("     kb %2d: deq %7d %7d   mma %7d %7d" % (i, *[v - t[0] if v else 0 for v in q]))
     dbg.zero_()
