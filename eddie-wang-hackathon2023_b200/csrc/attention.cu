@@ -447,21 +447,26 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
 
 // =====================================================================================================
 // Cross-attention over a (typically int8) cross-KV cache [B, 2, H, S, 64]: the dominant byte stream of the
-// decoder step at batch >= 6 (3.84 MB per sequence per layer).  HBM-bound streaming design, third iteration
-// (v1: CTA-wide items with shared-memory scores, 6.7 thread-instructions per byte, issue-bound at 2.1 TB/s;
-//  v2: finer items + in-kernel merge, slower: five CTA barriers and a __threadfence per 16 KB item):
-//   * the work item is WARP-private: (query row, head, range of <= 128 keys).  A warp reads its K range with sixteen
-//     independent 128-bit loads per lane (512 contiguous bytes per warp instruction, 8 KB in flight per warp), keeps
-//     the 16 scores per lane in registers, does the softmax with shuffles only, then streams V the same way.
-//     No shared memory, no CTA barrier, no producer/consumer handshake: with 16 resident warps per SM there are
-//     128 KB of loads in flight per SM, several times what Little's law needs for HBM3e.
-//   * lane geometry: 4 lanes x 16 dims per key, 8 keys per warp instruction (the same lane owns the same key in the
-//     K and V phases, so probabilities never leave registers).
-//   * int8 -> fp16 by xor 0x80 + PRMT + HSUB2 (exact integers); products chained four at a time with HFMA2 and
-//     flushed to fp32 (same scheme as the GEMV); the dequant scale is hoisted out of both dot products.
-//   * the splits of one (row, head) are merged by the last warp to arrive (self-resetting counter).
+// decoder step at batch >= 6 (3.84 MB per sequence per layer).  HBM-bound streaming design, fourth iteration:
+//   v1 CTA-wide items + shared scores: 6.7 thread-instructions/byte, issue-bound at 2.1 TB/s;
+//   v2 finer items + in-kernel merge: slower (five CTA barriers and a __threadfence per 16 KB item);
+//   v3 warp-private items, register-staged LDG: 2.6 instructions/byte but latency-bound (long-scoreboard stalls,
+//      only ~13 warps/SM with 8 KB in flight each, loads not overlapped with the math of the same warp): 2.6 TB/s.
+//   v4 (this): warp-private work AND a warp-private shared-memory ring filled by 1-D TMA bulk copies (UBLKCP):
+//      * a chunk = 64 keys (int8: 4 KB of K + 4 KB of V, both contiguous) -> two bulk copies onto one mbarrier;
+//        each warp keeps 3 chunks in flight (24 KB), 8 warps per CTA, one CTA per SM: 192 KB in flight per SM, and
+//        the copies of chunk i+3 are issued before the math of chunk i+1 starts -- no load latency on the warp's
+//        critical path, no CTA barrier, no producer/consumer handshake across warps;
+//      * every warp owns a CONTIGUOUS range of chunks of the flattened (row, head, chunk) space and carries the
+//        online-softmax state (m, l, o) across consecutive chunks of the same (row, head); the cross-lane reduction
+//        of o (48 shuffles) happens once per (row, head) range, not per chunk;
+//      * lane geometry 4 lanes x 16 dims per key, 8 keys per warp instruction; int8 -> fp16 by xor 0x80 + PRMT +
+//        HSUB2 (exact integers), products chained 4 (q.k) / 8 (p.v) at a time with HFMA2 and flushed to fp32, the
+//        dequant scale hoisted out of both dot products;
+//      * the ranges of a (row, head) are merged by the last warp to arrive (self-resetting counter).
 // =====================================================================================================
 constexpr int kXaWarps = 8;
+constexpr int kXaStages = 3;
 
 struct XAttnParams
 {
@@ -469,67 +474,33 @@ struct XAttnParams
     const void* kv;    // [B, 2, H, S, 64]
     const float* scale_quant_orig;
     __half* out;       // [R, H*64]
-    float* partials;   // [R*H*nsplit][66]
+    float* partials;   // [R*H][max_parts][66]
     int* counters;     // [R*H] arrival counters (library owned, self-resetting)
     int B, H, S;       // B = number of query rows R
     int q_per_seq;     // query rows per cache sequence (1 in the generation phase, S_prompt in the context phase)
-    int nsplit, keys_per_split;
-    int items_per_warp;
+    int nch;           // chunks per (row, head) = ceil(S / keys per chunk)
+    int chunks_per_warp;
+    int max_parts;
     float inv_sqrt_dh;
 };
 
-// 16 cache bytes (or 16 fp16) of one key -> 8 half2 in the pair order (d0,d2) (d1,d3) (d4,d6) (d5,d7) ...
+// 16 cache bytes (or 16 fp16) of one key, read from shared memory -> 8 half2 in the pair order
+// (d0,d2) (d1,d3) (d4,d6) (d5,d7) ...
 template <bool INT8>
-struct XaChunk;
-
-template <>
-struct XaChunk<true>
+__device__ __forceinline__ void xa_load16(const uint8_t* p, __half2 (&w)[8])
 {
-    uint4 v;
-
-    __device__ __forceinline__ void load(const uint8_t* p)
+    if constexpr (INT8)
     {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "l"(p));
-    }
-
-    __device__ __forceinline__ void zero()
-    {
-        v = make_uint4(0, 0, 0, 0); // int8 zeros
-    }
-
-    __device__ __forceinline__ void unpack(__half2 (&w)[8]) const
-    {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
         dequant_word(v.x ^ 0x80808080u, w[0], w[1]);
         dequant_word(v.y ^ 0x80808080u, w[2], w[3]);
         dequant_word(v.z ^ 0x80808080u, w[4], w[5]);
         dequant_word(v.w ^ 0x80808080u, w[6], w[7]);
     }
-};
-
-template <>
-struct XaChunk<false>
-{
-    uint4 v0, v1;
-
-    __device__ __forceinline__ void load(const uint8_t* p)
+    else
     {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(v0.x), "=r"(v0.y), "=r"(v0.z), "=r"(v0.w)
-                     : "l"(p));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(v1.x), "=r"(v1.y), "=r"(v1.z), "=r"(v1.w)
-                     : "l"(p + 16));
-    }
-
-    __device__ __forceinline__ void zero()
-    {
-        v0 = v1 = make_uint4(0, 0, 0, 0);
-    }
-
-    __device__ __forceinline__ void unpack(__half2 (&w)[8]) const
-    {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(p);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(p + 16);
         const uint32_t u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}; // u[j] = (d2j, d2j+1)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -540,143 +511,76 @@ struct XaChunk<false>
             w[2 * i + 1] = *reinterpret_cast<const __half2*>(&hi);
         }
     }
-};
+}
 
 template <bool INT8>
-__global__ void __launch_bounds__(kXaWarps * 32) cross_attention_kernel(const XAttnParams p)
+__global__ void __launch_bounds__(kXaWarps * 32, 1) cross_attention_kernel(const XAttnParams p)
 {
     constexpr int ESZ = INT8 ? 1 : 2;
-    constexpr int NIT = INT8 ? 16 : 8; // 8 keys per iteration: <= 128 (int8) / 64 (fp16) keys per item
+    constexpr int CK = INT8 ? 64 : 32;      // keys per chunk
+    constexpr int NIT = CK / 8;             // warp iterations per chunk
+    constexpr int kHalfBytes = CK * kDh * ESZ; // bytes of K (or V) per chunk: 4096
+    constexpr int kStageBytes = 2 * kHalfBytes;
+    extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = lane & 3, kl = lane >> 2;
-    const int items = p.B * p.H * p.nsplit;
-    const int gw = blockIdx.x * kXaWarps + warp;
+    uint8_t* ring = smem + (size_t) warp * kXaStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) kXaWarps * kXaStages * kStageBytes) + warp * kXaStages;
 
+    const int total = p.B * p.H * p.nch;
+    const int gw = blockIdx.x * kXaWarps + warp;
+    const int c_begin = min(gw * p.chunks_per_warp, total);
+    const int c_end = min(c_begin + p.chunks_per_warp, total);
+
+    if (lane == 0)
+    {
+        for (int s = 0; s < kXaStages; ++s)
+            mbar_init(&bars[s], 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+    }
+    __syncwarp();
     grid_dep_launch_dependents();
+
+    // bulk copies of chunk c (K half then V half) into stage s; the cache is static data: no dependency wait needed
+    const uint64_t pol = policy_evict_first();
+    auto issue = [&](int c, int s)
+    {
+        const int bh = c / p.nch, ch = c - bh * p.nch;
+        const int b = (bh / p.H) / p.q_per_seq, h = bh % p.H;
+        const int key0 = ch * CK;
+        const int nk = min(CK, p.S - key0);
+        const uint32_t bytes = (uint32_t) nk * kDh * ESZ;
+        const uint8_t* kb = static_cast<const uint8_t*>(p.kv) + (((size_t) (b * 2 + 0) * p.H + h) * p.S + key0) * (size_t) (kDh * ESZ);
+        const uint8_t* vb = static_cast<const uint8_t*>(p.kv) + (((size_t) (b * 2 + 1) * p.H + h) * p.S + key0) * (size_t) (kDh * ESZ);
+        mbar_arrive_expect_tx(&bars[s], 2 * bytes);
+        bulk_g2s_hint(ring + s * kStageBytes, kb, bytes, &bars[s], pol);
+        bulk_g2s_hint(ring + s * kStageBytes + kHalfBytes, vb, bytes, &bars[s], pol);
+    };
+    if (lane == 0)
+    {
+        for (int j = 0; j < kXaStages && c_begin + j < c_end; ++j)
+            issue(c_begin + j, j);
+    }
+    if (c_begin >= c_end)
+        return;
+    grid_dep_wait(); // q comes from the previous kernel
+
     const float s_qo = INT8 ? p.scale_quant_orig[0] : 1.f;
     const float sscale = s_qo * p.inv_sqrt_dh;
-    bool waited = false;
 
-    for (int it_w = 0; it_w < p.items_per_warp; ++it_w)
+    int cur_bh = -1;
+    __half2 q2[8];
+    float m_run = -FLT_MAX, l_run = 0.f; // l_run: this lane group's share of the denominator
+    float o[16];
+
+    auto flush = [&](int bh)
     {
-        const int item = gw * p.items_per_warp + it_w;
-        if (item >= items)
-            break;
-        const int bh = item / p.nsplit, sp = item % p.nsplit;
-        const int b = (bh / p.H) / p.q_per_seq, h = bh % p.H;
-        const int key0 = sp * p.keys_per_split;
-        const int nkeys = min(p.keys_per_split, p.S - key0);
-        const uint8_t* kbase = static_cast<const uint8_t*>(p.kv)
-            + ((((size_t) (b * 2 + 0) * p.H + h) * p.S + key0) * kDh + chunk * 16) * ESZ;
-        const uint8_t* vbase = static_cast<const uint8_t*>(p.kv)
-            + ((((size_t) (b * 2 + 1) * p.H + h) * p.S + key0) * kDh + chunk * 16) * ESZ;
-
-        // ---- K: all loads of the item in flight before anything depends on them (cache data: no PDL wait needed)
-        XaChunk<INT8> kc[NIT];
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            const int key = it * 8 + kl;
-            if (key < nkeys)
-                kc[it].load(kbase + (size_t) key * kDh * ESZ);
-            else
-                kc[it].zero();
-        }
-        if (!waited)
-        {
-            grid_dep_wait(); // q comes from the previous kernel
-            waited = true;
-        }
-        __half2 q2[8];
-        {
-            __half qh[16];
-            load16_half(p.q + (size_t) bh * kDh + chunk * 16, nullptr, qh);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-            {
-                q2[2 * i] = __halves2half2(qh[4 * i], qh[4 * i + 2]);
-                q2[2 * i + 1] = __halves2half2(qh[4 * i + 1], qh[4 * i + 3]);
-            }
-        }
-        float sc[NIT];
-        float m = -FLT_MAX;
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            __half2 w[8];
-            kc[it].unpack(w);
-            __half2 h0 = __hmul2(q2[0], w[0]);
-            __half2 h1 = __hmul2(q2[4], w[4]);
-            h0 = __hfma2(q2[1], w[1], h0);
-            h1 = __hfma2(q2[5], w[5], h1);
-            h0 = __hfma2(q2[2], w[2], h0);
-            h1 = __hfma2(q2[6], w[6], h1);
-            h0 = __hfma2(q2[3], w[3], h0);
-            h1 = __hfma2(q2[7], w[7], h1);
-            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-            float s = (f0.x + f0.y) + (f1.x + f1.y);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s = (it * 8 + kl < nkeys) ? s * sscale : -FLT_MAX;
-            sc[it] = s;
-            m = fmaxf(m, s);
-        }
-        // ---- V loads go out now; the softmax below overlaps their latency
-        XaChunk<INT8> vc[NIT];
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            const int key = it * 8 + kl;
-            if (key < nkeys)
-                vc[it].load(vbase + (size_t) key * kDh * ESZ);
-            else
-                vc[it].zero();
-        }
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-        float l = 0.f;
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            const float e = (it * 8 + kl < nkeys) ? __expf(sc[it] - m) : 0.f;
-            sc[it] = e;
-            l += e;
-        }
+        // reduce this warp's running state over the 8 key groups and publish / merge it
+        float l = l_run;
         l += __shfl_xor_sync(0xffffffffu, l, 4);
         l += __shfl_xor_sync(0xffffffffu, l, 8);
         l += __shfl_xor_sync(0xffffffffu, l, 16);
-
-        // ---- P.V: four keys chained in fp16, then flushed to fp32
-        float o[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            o[i] = 0.f;
-#pragma unroll
-        for (int it4 = 0; it4 < NIT; it4 += 4)
-        {
-            __half2 o2[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                o2[i] = __float2half2_rn(0.f);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-            {
-                const __half2 p2 = __float2half2_rn(sc[it4 + j]);
-                __half2 w[8];
-                vc[it4 + j].unpack(w);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    o2[i] = __hfma2(p2, w[i], o2[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-            {
-                const float2 f = __half22float2(o2[i]);
-                o[2 * i] += f.x;
-                o[2 * i + 1] += f.y;
-            }
-        }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
         {
@@ -686,8 +590,12 @@ __global__ void __launch_bounds__(kXaWarps * 32) cross_attention_kernel(const XA
             v += __shfl_xor_sync(0xffffffffu, v, 16);
             o[i] = v * s_qo; // hoisted V dequant scale
         }
+        // which warps hold a part of this (row, head)?
+        const int first = (bh * p.nch) / p.chunks_per_warp;
+        const int last = ((bh + 1) * p.nch - 1) / p.chunks_per_warp;
+        const int nparts = last - first + 1;
         // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
-        if (p.nsplit == 1)
+        if (nparts == 1)
         {
             if (kl == 0)
             {
@@ -702,9 +610,9 @@ __global__ void __launch_bounds__(kXaWarps * 32) cross_attention_kernel(const XA
                     dst[4 * j + 3] = __float2half_rn(o[4 * j + 3] * inv);
                 }
             }
-            continue;
+            return;
         }
-        float* pr = p.partials + (size_t) item * (kDh + 2);
+        float* pr = p.partials + ((size_t) bh * p.max_parts + (gw - first)) * (kDh + 2);
         if (kl == 0)
         {
             float* dst = pr + 2 + chunk * 16;
@@ -718,26 +626,25 @@ __global__ void __launch_bounds__(kXaWarps * 32) cross_attention_kernel(const XA
             }
             if (chunk == 0)
             {
-                __stcg(pr, m);
+                __stcg(pr, m_run);
                 __stcg(pr + 1, l);
             }
         }
-        // last split of this (row, head) to arrive merges all partials
         __threadfence();
         __syncwarp();
-        int last = 0;
+        int is_last = 0;
         if (lane == 0)
-            last = (atomicAdd(&p.counters[bh], 1) == p.nsplit - 1) ? 1 : 0;
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last)
+            is_last = (atomicAdd(&p.counters[bh], 1) == nparts - 1) ? 1 : 0;
+        is_last = __shfl_sync(0xffffffffu, is_last, 0);
+        if (is_last)
         {
             __threadfence();
-            const float* pb = p.partials + (size_t) bh * p.nsplit * (kDh + 2);
+            const float* pb = p.partials + (size_t) bh * p.max_parts * (kDh + 2);
             float gm = -FLT_MAX;
-            for (int s2 = 0; s2 < p.nsplit; ++s2)
+            for (int s2 = 0; s2 < nparts; ++s2)
                 gm = fmaxf(gm, __ldcg(pb + s2 * (kDh + 2)));
             float gl = 0.f, a0 = 0.f, a1 = 0.f;
-            for (int s2 = 0; s2 < p.nsplit; ++s2)
+            for (int s2 = 0; s2 < nparts; ++s2)
             {
                 const float* ps = pb + s2 * (kDh + 2);
                 const float w = __expf(__ldcg(ps) - gm);
@@ -751,7 +658,110 @@ __global__ void __launch_bounds__(kXaWarps * 32) cross_attention_kernel(const XA
             if (lane == 0)
                 p.counters[bh] = 0;
         }
+    };
+
+    for (int c = c_begin; c < c_end; ++c)
+    {
+        const int it_local = c - c_begin;
+        const int s = it_local % kXaStages;
+        const int bh = c / p.nch, ch = c - bh * p.nch;
+        const int nk = min(CK, p.S - ch * CK);
+        if (bh != cur_bh)
+        {
+            if (cur_bh >= 0)
+                flush(cur_bh);
+            cur_bh = bh;
+            m_run = -FLT_MAX;
+            l_run = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                o[i] = 0.f;
+            __half qh[16];
+            load16_half(p.q + (size_t) bh * kDh + chunk * 16, nullptr, qh);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                q2[2 * i] = __halves2half2(qh[4 * i], qh[4 * i + 2]);
+                q2[2 * i + 1] = __halves2half2(qh[4 * i + 1], qh[4 * i + 3]);
+            }
+        }
+        mbar_wait(&bars[s], (it_local / kXaStages) & 1);
+        const uint8_t* kst = ring + s * kStageBytes + (size_t) (kl * kDh + chunk * 16) * ESZ;
+        const uint8_t* vst = kst + kHalfBytes;
+
+        // ---- q.k for the 8 x NIT keys of the chunk (this lane: keys kl, kl+8, ...) ----
+        float sc[NIT];
+        float m_new = m_run;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            __half2 w[8];
+            xa_load16<INT8>(kst + (size_t) it * 8 * kDh * ESZ, w);
+            __half2 h0 = __hmul2(q2[0], w[0]);
+            __half2 h1 = __hmul2(q2[4], w[4]);
+            h0 = __hfma2(q2[1], w[1], h0);
+            h1 = __hfma2(q2[5], w[5], h1);
+            h0 = __hfma2(q2[2], w[2], h0);
+            h1 = __hfma2(q2[6], w[6], h1);
+            h0 = __hfma2(q2[3], w[3], h0);
+            h1 = __hfma2(q2[7], w[7], h1);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            float sv = (f0.x + f0.y) + (f1.x + f1.y);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+            sv = (it * 8 + kl < nk) ? sv * sscale : -FLT_MAX;
+            sc[it] = sv;
+            m_new = fmaxf(m_new, sv);
+        }
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 4));
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 16));
+        // online softmax: rescale the running state to the new maximum
+        const float corr = __expf(m_run - m_new); // 0 on the first chunk (m_run = -FLT_MAX)
+        m_run = m_new;
+        l_run *= corr;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            o[i] *= corr;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            const float e = (it * 8 + kl < nk) ? __expf(sc[it] - m_new) : 0.f;
+            sc[it] = e;
+            l_run += e;
+        }
+        // ---- p.v: up to 8 keys chained in fp16, then flushed to fp32 ----
+        {
+            __half2 o2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                o2[i] = __float2half2_rn(0.f);
+#pragma unroll
+            for (int it = 0; it < NIT; ++it)
+            {
+                if (!INT8 && it * 8 + kl >= nk)
+                    continue; // fp16 cache: stale shared-memory bits beyond the last key could decode to NaN
+                const __half2 p2 = __float2half2_rn(sc[it]);
+                __half2 w[8];
+                xa_load16<INT8>(vst + (size_t) it * 8 * kDh * ESZ, w);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    o2[i] = __hfma2(p2, w[i], o2[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+            {
+                const float2 f = __half22float2(o2[i]);
+                o[2 * i] += f.x;
+                o[2 * i + 1] += f.y;
+            }
+        }
+        // stage s is drained: refill it with chunk c + kXaStages
+        __syncwarp();
+        if (lane == 0 && c + kXaStages < c_end)
+            issue(c + kXaStages, s);
     }
+    flush(cur_bh);
 }
 
 // fp16 K, V [B, S, H*64] -> cache [B, 2, H, S, 64] (int8-quantized or fp16).  grid (S, B), 128 threads... one
@@ -846,22 +856,28 @@ extern "C" int b200_attention_context(const void* qkv, const int32_t* input_leng
 
 namespace b200
 {
-static void xattn_plan(int B, int H, int S, int int8, int& nsplit, int& kps, int& items_per_warp, int& blocks)
+struct XaPlan
 {
-    // warp-private items of <= 128 (int8) / 64 (fp16) keys; every warp gets the same number of items
-    const int max_keys = int8 ? 128 : 64;
-    const int pairs = B * H;
-    const int slots = num_sms() * 2 * kXaWarps; // two 8-warp CTAs per SM are resident (register-limited)
-    nsplit = (S + max_keys - 1) / max_keys;
-    // when there are fewer items than warp slots, split finer (down to 32 keys) so more SMs pull bytes
-    while (pairs * nsplit * 2 <= slots && (S + nsplit * 2 - 1) / (nsplit * 2) >= 32)
-        nsplit *= 2;
-    kps = (S + nsplit - 1) / nsplit;
-    kps = (kps + 7) & ~7; // whole 8-key warp iterations
-    nsplit = (S + kps - 1) / kps;
-    const int items = pairs * nsplit;
-    items_per_warp = (items + slots - 1) / slots;
-    blocks = (items + items_per_warp * kXaWarps - 1) / (items_per_warp * kXaWarps);
+    int nch, chunks_per_warp, max_parts, blocks;
+    size_t smem, ws_bytes;
+};
+
+static XaPlan xattn_plan(int R, int H, int S, int int8)
+{
+    XaPlan pl{};
+    const int ck = int8 ? 64 : 32;
+    pl.nch = (S + ck - 1) / ck;
+    const long long total = (long long) R * H * pl.nch;
+    const long long warps = (long long) num_sms() * kXaWarps; // one persistent 8-warp CTA per SM
+    pl.chunks_per_warp = (int) ((total + warps - 1) / warps);
+    if (pl.chunks_per_warp < 1)
+        pl.chunks_per_warp = 1;
+    const long long used_warps = (total + pl.chunks_per_warp - 1) / pl.chunks_per_warp;
+    pl.blocks = (int) ((used_warps + kXaWarps - 1) / kXaWarps);
+    pl.max_parts = (pl.nch + pl.chunks_per_warp - 1) / pl.chunks_per_warp + 1;
+    pl.smem = (size_t) kXaWarps * kXaStages * 2 * ck * kDh * (int8 ? 1 : 2) + sizeof(uint64_t) * kXaWarps * kXaStages;
+    pl.ws_bytes = (size_t) R * H * pl.max_parts * (kDh + 2) * sizeof(float);
+    return pl;
 }
 
 int* tc_counter_slot(int needed);
@@ -871,13 +887,9 @@ extern "C" size_t b200_cross_attention_workspace_bytes(int batch_size, int num_h
 {
     if (batch_size <= 0 || num_heads <= 0 || kv_len <= 0 || head_size != kDh)
         return 0;
-    int ns, kps, ipw, blocks, best = 0;
-    for (int int8 = 0; int8 < 2; ++int8)
-    {
-        xattn_plan(batch_size, num_heads, kv_len, int8, ns, kps, ipw, blocks);
-        best = ns > best ? ns : best;
-    }
-    return (size_t) batch_size * num_heads * best * (kDh + 2) * sizeof(float);
+    const size_t a = xattn_plan(batch_size, num_heads, kv_len, 1).ws_bytes;
+    const size_t b = xattn_plan(batch_size, num_heads, kv_len, 0).ws_bytes;
+    return a > b ? a : b;
 }
 
 extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const float* kv_scale_quant_orig, void* out,
@@ -903,23 +915,36 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     p.H = num_heads;
     p.S = kv_len;
     p.q_per_seq = q_rows_per_seq;
-    int blocks = 1;
-    xattn_plan(batch_size, num_heads, kv_len, int8_kv_cache, p.nsplit, p.keys_per_split, p.items_per_warp, blocks);
+    const XaPlan pl = xattn_plan(batch_size, num_heads, kv_len, int8_kv_cache);
+    p.nch = pl.nch;
+    p.chunks_per_warp = pl.chunks_per_warp;
+    p.max_parts = pl.max_parts;
     p.inv_sqrt_dh = 1.f / sqrtf((float) kDh);
-    const size_t need = p.nsplit > 1 ? (size_t) batch_size * num_heads * p.nsplit * (kDh + 2) * sizeof(float) : 0;
-    B200_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), B200_ERR_WORKSPACE,
-        "cross attention: workspace of %zu bytes needed, got %zu", need, workspace_bytes);
-    if (p.nsplit > 1)
-    {
-        p.counters = tc_counter_slot(batch_size * num_heads);
-        B200_REQUIRE(p.counters != nullptr, B200_ERR_UNSUPPORTED, "cross attention: %d (row, head) pairs exceed the counter slot",
-            batch_size * num_heads);
-    }
+    B200_REQUIRE(workspace && workspace_bytes >= pl.ws_bytes, B200_ERR_WORKSPACE,
+        "cross attention: workspace of %zu bytes needed, got %zu", pl.ws_bytes, workspace_bytes);
+    p.counters = tc_counter_slot(batch_size * num_heads);
+    B200_REQUIRE(p.counters != nullptr, B200_ERR_UNSUPPORTED, "cross attention: %d (row, head) pairs exceed the counter slot",
+        batch_size * num_heads);
     cudaStream_t st = as_stream(stream);
+    static bool attr_set[2] = {false, false};
     if (int8_kv_cache)
-        B200_LAUNCH(cross_attention_kernel<true>, dim3(blocks), dim3(kXaWarps * 32), 0, st, p);
+    {
+        if (!attr_set[0])
+        {
+            B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
+            attr_set[0] = true;
+        }
+        B200_LAUNCH(cross_attention_kernel<true>, dim3(pl.blocks), dim3(kXaWarps * 32), pl.smem, st, p);
+    }
     else
-        B200_LAUNCH(cross_attention_kernel<false>, dim3(blocks), dim3(kXaWarps * 32), 0, st, p);
+    {
+        if (!attr_set[1])
+        {
+            B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
+            attr_set[1] = true;
+        }
+        B200_LAUNCH(cross_attention_kernel<false>, dim3(pl.blocks), dim3(kXaWarps * 32), pl.smem, st, p);
+    }
     return B200_OK;
 }
 

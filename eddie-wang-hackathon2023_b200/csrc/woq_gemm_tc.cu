@@ -223,8 +223,8 @@ struct TcSmem
     static constexpr int XTileBytes = MT * 128;
     static constexpr size_t ring = (size_t) SS * (kWTileBytes + XTileBytes);
     static constexpr size_t rbuf = (size_t) 128 * MT * sizeof(float); // cluster reduction inbox [S][MT][128/S]
-    static_assert(AS == SS, "one ring: smem stage s and TMEM A stage s are released together");
-    static constexpr size_t bars = sizeof(uint64_t) * (3 * SS + 2) + 16;
+    static_assert(AS <= SS, "the TMEM A ring is never deeper than the shared-memory ring");
+    static constexpr size_t bars = sizeof(uint64_t) * (2 * SS + AS + 2) + 16 + ((AS & 1) ? 8 : 0);
 
     static constexpr size_t ln_bytes(int K)
     {
@@ -258,9 +258,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint8_t* smW = smem;
     uint8_t* smX = smem + SS * kWTileBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smX + SS * XTileBytes);
-    uint64_t* stage_free = full + SS;  // MMA of the block done: smem stage and TMEM A stage reusable
-    uint64_t* a_ready = stage_free + SS; // dequantized A tile is in TMEM (and the X tile has landed)
-    uint64_t* acc_done = a_ready + SS;
+    uint64_t* stage_free = full + SS;  // MMA of block i done (index i % SS): its smem stage and TMEM A stage are reusable
+    uint64_t* a_ready = stage_free + SS; // dequantized A tile of block i is in TMEM stage i % AS (and its X tile has landed)
+    uint64_t* acc_done = a_ready + AS;
     uint64_t* red_bar = acc_done + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 1);
     int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
@@ -303,17 +303,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int t = threadIdx.x;
         if (t < SS)
             mbar_init(&stage_free[t], 1);
-        else if (t < 2 * SS)
+        else if (t < SS + AS)
             mbar_init(&a_ready[t - SS], kTcDequantWarps);
-        else if (t == 2 * SS)
+        else if (t == SS + AS)
             mbar_init(acc_done, 1);
-        else if (t == 2 * SS + 1)
+        else if (t == SS + AS + 1)
         {
             mbar_init(red_bar, 1);
             if (p.cluster)
                 mbar_arrive_expect_tx(red_bar, (uint32_t) (128 * MT * sizeof(float))); // inbox bytes from all ranks
         }
-        if (t <= 2 * SS + 1)
+        if (t <= SS + AS + 1)
             fence_mbar_init();
     }
     if (warp == kMmaWarp)
@@ -368,9 +368,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const uint32_t d_tmem = tmem_base + kDCol;
         for (int i = 0; i < nkb; ++i)
         {
-            const int ss = i % SS;
+            const int ss = i % SS, as = i % AS;
             // a_ready implies full[ss]: the dequant warps arrive on it only after they observed the TMA completion
-            mbar_wait(&a_ready[ss], (i / SS) & 1);
+            mbar_wait(&a_ready[as], (i / AS) & 1);
             tc_fence_after();
             if (lane == 0 && i < 12)
                 TC_STAMP(16 + 4 * i + 2);
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int k4 = 0; k4 < 4; ++k4)
                 {
                     // K advance inside the 128-byte swizzle atom: 16 halves = 32 bytes = 2 descriptor units
-                    tc_mma_ts(d_tmem, tmem_base + ss * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
+                    tc_mma_ts(d_tmem, tmem_base + as * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
                 }
                 tc_commit(&stage_free[ss]);
                 if (i == nkb - 1)
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         for (int i = 0; i < nkb; ++i)
         {
-            const int as = i % SS;
+            const int as = i % AS;
             uint32_t r[16];
 #pragma unroll
             for (int c = 0; c < 2; ++c)
@@ -559,9 +559,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     r[8 * c + 4 + w] = *reinterpret_cast<uint32_t*>(&hi);
                 }
             }
-            if (i >= SS)
+            if (i >= AS)
             {
-                mbar_wait(&stage_free[as], ((i / SS) - 1) & 1);
+                // TMEM stage `as` was last read by the MMAs of block i - AS
+                const int j = i - AS;
+                mbar_wait(&stage_free[j % SS], (j / SS) & 1);
                 tc_fence_after();
             }
             tc_st_x16(tmem_base + lane_field + as * 32 + kh * 16, r);
@@ -984,10 +986,10 @@ TcPlan plan_tc(int M, int N, int K)
     {
         if (g_splitk_mode == 1 && pl.MT <= 64)
         {
-            // cluster split-K: power-of-two cluster (<= 8, portable) along z; up to two CTAs per SM overall, at least
-            // two k-blocks per CTA
+            // cluster split-K: power-of-two cluster (<= 8, portable) along z, at least two k-blocks per CTA
+            // at most one CTA per SM: a second resident CTA starts late and stretches the tail
             int s2 = 8;
-            while (s2 > 1 && (tiles * s2 > 2 * sms || kb_total < 2 * s2))
+            while (s2 > 1 && (tiles * s2 > sms || kb_total < 2 * s2))
                 s2 >>= 1;
             splits = s2;
             cluster = s2 > 1 ? 1 : 0;
@@ -1080,7 +1082,7 @@ bool woq_tc_can_fuse_ln(int M, int K)
 {
     if (M > 32)
         return false;
-    return M <= 16 ? TcSmem<16, 6, 6>::total(true, true, K) <= 200 * 1024 : TcSmem<32, 6, 6>::total(true, true, K) <= 200 * 1024;
+    return M <= 16 ? TcSmem<16, 10, 6>::total(true, true, K) <= 200 * 1024 : TcSmem<32, 8, 6>::total(true, true, K) <= 200 * 1024;
 }
 
 // tcgen05 path entry: any M >= 1.  ln_gamma != nullptr: A is the raw residual stream and LayerNorm(A) is the operand.
@@ -1131,8 +1133,8 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     switch (pl.MT)
     {
-    case 16: return launch_tc<16, 6, 6>(tmW, tmX, p, grid, stream);
-    case 32: return launch_tc<32, 6, 6>(tmW, tmX, p, grid, stream);
+    case 16: return launch_tc<16, 10, 6>(tmW, tmX, p, grid, stream);
+    case 32: return launch_tc<32, 8, 6>(tmW, tmX, p, grid, stream);
     case 64: return launch_tc<64, 6, 6>(tmW, tmX, p, grid, stream);
     case 128: return launch_tc<128, 4, 4>(tmW, tmX, p, grid, stream);
     default: return launch_tc<256, 4, 4>(tmW, tmX, p, grid, stream);
