@@ -36,6 +36,7 @@ _SIGS = {
     "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200_init": (_i, []),
     "b200_set_pdl": (_i, [_i]),
+    "b200_set_static_kv_hint": (_i, [_i]),
     "b200_l2_prefetch": (_i, [_vp, _sz, _vp]),
     "b200_symmetric_quantize_int8": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "b200_preprocess_weights_int8": (_i, [_vp, _i, _i, _vp, _vp]),

@@ -17,6 +17,7 @@
 //
 // Cache layout: [B, 2, H, Smax, Dh] (KVLinearBuffer, T/cpp/tensorrt_llm/kernels/kvCacheUtils.h:114-170). Dh = 64.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -183,31 +184,104 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red, int nwarp
     return v;
 }
 
-// =====================================================================================================
-// Generation step.  grid (H, B), 128 threads.  Lane geometry: 4 lanes per key (16 dims each), 8 keys per warp
-// instruction, so a warp reads 512 contiguous cache bytes (int8) per step.
-// =====================================================================================================
+// 16 cache elements of one key held in registers (int8: one 128-bit load, fp16: two)
 template <bool INT8>
-__global__ void __launch_bounds__(128) mmha_generation_kernel(const b200_mmha_params p)
-{
-    extern __shared__ float s_qk[]; // [Smax + 1]
-    __shared__ float s_red[4];
-    __shared__ float s_out[4][kDh];
+struct KvChunk;
 
-    const int h = blockIdx.x, b = blockIdx.y;
+template <>
+struct KvChunk<true>
+{
+    uint4 v;
+
+    __device__ __forceinline__ void load(const void* base, size_t elem_off)
+    {
+        v = __ldg(reinterpret_cast<const uint4*>(static_cast<const int8_t*>(base) + elem_off));
+    }
+
+    __device__ __forceinline__ void unpack(__half2 (&w)[8]) const
+    {
+        dequant_word(v.x ^ 0x80808080u, w[0], w[1]);
+        dequant_word(v.y ^ 0x80808080u, w[2], w[3]);
+        dequant_word(v.z ^ 0x80808080u, w[4], w[5]);
+        dequant_word(v.w ^ 0x80808080u, w[6], w[7]);
+    }
+};
+
+template <>
+struct KvChunk<false>
+{
+    uint4 v0, v1;
+
+    __device__ __forceinline__ void load(const void* base, size_t elem_off)
+    {
+        const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __half*>(base) + elem_off);
+        v0 = __ldg(p);
+        v1 = __ldg(p + 1);
+    }
+
+    __device__ __forceinline__ void unpack(__half2 (&w)[8]) const
+    {
+        const uint32_t u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w}; // u[j] = (d2j, d2j+1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const uint32_t lo = __byte_perm(u[2 * i], u[2 * i + 1], 0x5410); // (d4i, d4i+2)
+            const uint32_t hi = __byte_perm(u[2 * i], u[2 * i + 1], 0x7632); // (d4i+1, d4i+3)
+            w[2 * i] = *reinterpret_cast<const __half2*>(&lo);
+            w[2 * i + 1] = *reinterpret_cast<const __half2*>(&hi);
+        }
+    }
+};
+
+// =====================================================================================================
+// Generation step.  One WARP per (batch, head): no shared memory, no CTA barrier.  Lane geometry: 4 lanes x 16 dims
+// per key, 8 keys per warp instruction (512 contiguous cache bytes for int8).  Keys are processed in passes of
+// 8 * NIT with an online softmax; the K and V rows of the first pass are requested BEFORE griddepcontrol.wait (cache
+// rows below the current length were written by earlier steps), so under programmatic dependent launch they are in
+// registers when the qkv projection of this step lands.  The first version (CTA per (b, h), three block-wide
+// reductions, loads issued after the dependency) was pure latency: 6 us for 350 KB.
+// =====================================================================================================
+constexpr int kMmhaWarps = 8;
+
+template <bool INT8>
+__global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const b200_mmha_params p, const int early_kv)
+{
+    constexpr int NIT = INT8 ? 8 : 4; // keys per pass = 8 * NIT (same register budget for both cache types)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = lane & 3, kl = lane >> 2;
     const int H = p.num_heads, Smax = p.max_seq_len;
     const int hidden = H * kDh;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chunk = lane & 3, kl = lane >> 2;
+    const int gw = blockIdx.x * kMmhaWarps + warp;
+    if (gw >= p.batch_size * H)
+        return;
+    const int b = gw / H, h = gw - b * H;
+    const size_t esz = INT8 ? 1 : 2;
+    char* kc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 0) * H + h) * Smax * kDh * esz;
+    char* vc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 1) * H + h) * Smax * kDh * esz;
 
-    grid_dep_wait();
+    // ---- speculative first pass: rows [0, 8*NIT) of K and V (clamped to the cache capacity) ----
+    // (only when the caller promised that the cache is not written by the kernel right before this one)
+    KvChunk<INT8> kreg[NIT], vreg[NIT];
     grid_dep_launch_dependents();
+    if (!early_kv)
+        grid_dep_wait();
+#pragma unroll
+    for (int it = 0; it < NIT; ++it)
+    {
+        const int key = min(it * 8 + kl, Smax - 1);
+        kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
+        vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
+    }
+    if (early_kv)
+        grid_dep_wait(); // qkv (and the lengths) come from the previous kernels
 
     int tlen = p.sequence_lengths ? p.sequence_lengths[b] : p.past_kv_length;
     tlen = min(tlen, Smax - 1);
     const float inv_sqrt_dh = 1.f / (sqrtf((float) kDh) * p.q_scaling); // gptAttentionCommon.cpp:163
     const float s_qo = INT8 ? p.kv_scale_quant_orig[0] : 1.f;
     const float s_oq = INT8 ? p.kv_scale_orig_quant[0] : 1.f;
+    const float sscale = s_qo * inv_sqrt_dh;
+    const int* mask = p.masked_tokens ? p.masked_tokens + (size_t) b * Smax : nullptr;
 
     const __half* qkv = static_cast<const __half*>(p.qkv) + (size_t) b * 3 * hidden + h * kDh + chunk * 16;
     const __half* bias = p.qkv_bias ? static_cast<const __half*>(p.qkv_bias) + h * kDh + chunk * 16 : nullptr;
@@ -215,107 +289,112 @@ __global__ void __launch_bounds__(128) mmha_generation_kernel(const b200_mmha_pa
     load16_half(qkv, bias, qh);
     load16_half(qkv + hidden, bias ? bias + hidden : nullptr, kh);
     load16_half(qkv + 2 * hidden, bias ? bias + 2 * hidden : nullptr, vh);
-    float q[16];
+    __half2 q2[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        q2[2 * i] = __halves2half2(qh[4 * i], qh[4 * i + 2]);
+        q2[2 * i + 1] = __halves2half2(qh[4 * i + 1], qh[4 * i + 3]);
+    }
+    // append this step's K and V (lane group 0 writes K, group 1 writes V; 16 dims per lane)
+    if (kl == 0)
+        store16<INT8>(kc, (size_t) tlen * kDh + chunk * 16, s_oq, kh);
+    else if (kl == 1)
+        store16<INT8>(vc, (size_t) tlen * kDh + chunk * 16, s_oq, vh);
+
+    // current token: unquantized k and v (Template.h:1503,1517,1920,1933)
+    float s_cur = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-        q[i] = __half2float(qh[i]);
+        s_cur = fmaf(__half2float(qh[i]), __half2float(kh[i]), s_cur);
+    s_cur += __shfl_xor_sync(0xffffffffu, s_cur, 1);
+    s_cur += __shfl_xor_sync(0xffffffffu, s_cur, 2);
+    s_cur *= inv_sqrt_dh;
 
-    const size_t esz = INT8 ? 1 : 2;
-    char* kc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 0) * H + h) * Smax * kDh * esz;
-    char* vc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 1) * H + h) * Smax * kDh * esz;
-
-    // append this step's K and V (warp 0: lanes 0-3 write K chunks, lanes 4-7 write V chunks)
-    if (warp == 0 && lane < 8)
-    {
-        if (lane < 4)
-            store16<INT8>(kc, (size_t) tlen * kDh + chunk * 16, s_oq, kh);
-        else
-            store16<INT8>(vc, (size_t) tlen * kDh + chunk * 16, s_oq, vh);
-    }
-
-    // ---- q.k over the cache ----
-    float lmax = -FLT_MAX;
-    const int* mask = p.masked_tokens ? p.masked_tokens + (size_t) b * Smax : nullptr;
-    for (int t0 = warp * 8; t0 < tlen; t0 += 32)
-    {
-        const int t = t0 + kl;
-        float s = 0.f;
-        if (t < tlen)
-        {
-            float kf[16];
-            load16<INT8>(kc, (size_t) t * kDh + chunk * 16, s_qo, kf);
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                s = fmaf(q[i], kf[i], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (t < tlen && chunk == 0)
-        {
-            s *= inv_sqrt_dh;
-            s_qk[t] = s;
-            if (!(mask && mask[t]))
-                lmax = fmaxf(lmax, s);
-        }
-    }
-    // current token (unquantized k)
-    if (warp == 0)
-    {
-        float s = 0.f;
-        if (lane < 4)
-        {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                s = fmaf(q[i], __half2float(kh[i]), s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (lane == 0)
-        {
-            s *= inv_sqrt_dh;
-            s_qk[tlen] = s;
-            lmax = fmaxf(lmax, s);
-        }
-    }
-    const float gmax = block_reduce_max(lmax, s_red, 4);
-
-    // ---- softmax numerators ----
-    float lsum = 0.f;
-    for (int t = tid; t <= tlen; t += 128)
-    {
-        const bool masked = (t < tlen) && mask && mask[t];
-        const float e = masked ? 0.f : __expf(s_qk[t] - gmax);
-        s_qk[t] = e;
-        lsum += e;
-    }
-    const float gsum = block_reduce_sum(lsum, s_red, 4); // contains a __syncthreads: s_qk is complete
-    const float inv_sum = __fdividef(1.f, gsum + 1.e-6f);
-
-    // ---- p.v ----
-    float o[16];
+    float m_run = s_cur, l_run = 0.f; // l_run: this lane group's share of the cached keys' denominator
+    float o[16];                      // in units of the dequant scale (integer V values)
 #pragma unroll
     for (int i = 0; i < 16; ++i)
         o[i] = 0.f;
-    for (int t0 = warp * 8; t0 < tlen; t0 += 32)
+
+    for (int k0 = 0; k0 < tlen; k0 += 8 * NIT)
     {
-        const int t = t0 + kl;
-        if (t < tlen)
+        if (k0 > 0)
         {
-            const float pt = s_qk[t];
-            float vf[16];
-            load16<INT8>(vc, (size_t) t * kDh + chunk * 16, s_qo, vf);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                o[i] = fmaf(pt, vf[i], o[i]);
+            for (int it = 0; it < NIT; ++it)
+            {
+                const int key = min(k0 + it * 8 + kl, Smax - 1);
+                kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
+                vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
+            }
         }
-    }
-    if (warp == 0 && lane < 4)
-    {
-        const float pt = s_qk[tlen];
+        float sc[NIT];
+        float m_new = m_run;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            const int key = k0 + it * 8 + kl;
+            __half2 w[8];
+            kreg[it].unpack(w);
+            __half2 h0 = __hmul2(q2[0], w[0]);
+            __half2 h1 = __hmul2(q2[4], w[4]);
+            h0 = __hfma2(q2[1], w[1], h0);
+            h1 = __hfma2(q2[5], w[5], h1);
+            h0 = __hfma2(q2[2], w[2], h0);
+            h1 = __hfma2(q2[6], w[6], h1);
+            h0 = __hfma2(q2[3], w[3], h0);
+            h1 = __hfma2(q2[7], w[7], h1);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            float sv = (f0.x + f0.y) + (f1.x + f1.y);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+            const bool valid = key < tlen && !(mask && mask[key]); // masked keys: probability 0, not in the max
+            sv = valid ? sv * sscale : -FLT_MAX;
+            sc[it] = sv;
+            m_new = fmaxf(m_new, sv);
+        }
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 4));
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 16));
+        const float corr = __expf(m_run - m_new);
+        m_run = m_new;
+        l_run *= corr;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            o[i] = fmaf(pt, __half2float(vh[i]), o[i]);
+            o[i] *= corr;
+        __half2 o2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            o2[i] = __float2half2_rn(0.f);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            if (sc[it] == -FLT_MAX)
+                continue; // invalid / masked key (also keeps stale cache bits out of the fp16 path)
+            const float e = __expf(sc[it] - m_new);
+            l_run += e;
+            const __half2 p2 = __float2half2_rn(e);
+            __half2 w[8];
+            vreg[it].unpack(w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                o2[i] = __hfma2(p2, w[i], o2[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            const float2 f = __half22float2(o2[i]);
+            o[2 * i] += f.x;
+            o[2 * i + 1] += f.y;
+        }
     }
+    // reduce over the 8 key groups
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 4);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 8);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 16);
+    const float e_cur = __expf(s_cur - m_run);
+    const float inv_sum = __fdividef(1.f, l_run + e_cur + 1.e-6f); // Template.h:1756
 #pragma unroll
     for (int i = 0; i < 16; ++i)
     {
@@ -323,19 +402,20 @@ __global__ void __launch_bounds__(128) mmha_generation_kernel(const b200_mmha_pa
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        o[i] = v;
+        o[i] = v * s_qo;
     }
-    if (lane < 4)
+    if (kl == 0)
     {
+        // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
+        __half* dst = static_cast<__half*>(p.out) + (size_t) b * hidden + h * kDh + chunk * 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            s_out[warp][chunk * 16 + i] = o[i];
-    }
-    __syncthreads();
-    if (tid < kDh)
-    {
-        const float v = (s_out[0][tid] + s_out[1][tid]) + (s_out[2][tid] + s_out[3][tid]);
-        static_cast<__half*>(p.out)[(size_t) b * hidden + h * kDh + tid] = __float2half_rn(v * inv_sum);
+        for (int j = 0; j < 4; ++j)
+        {
+            dst[4 * j + 0] = __float2half_rn((o[4 * j + 0] + e_cur * __half2float(vh[4 * j + 0])) * inv_sum);
+            dst[4 * j + 2] = __float2half_rn((o[4 * j + 1] + e_cur * __half2float(vh[4 * j + 2])) * inv_sum);
+            dst[4 * j + 1] = __float2half_rn((o[4 * j + 2] + e_cur * __half2float(vh[4 * j + 1])) * inv_sum);
+            dst[4 * j + 3] = __float2half_rn((o[4 * j + 3] + e_cur * __half2float(vh[4 * j + 3])) * inv_sum);
+        }
     }
 }
 
@@ -465,8 +545,10 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
 //        dequant scale hoisted out of both dot products;
 //      * the ranges of a (row, head) are merged by the last warp to arrive (self-resetting counter).
 // =====================================================================================================
-constexpr int kXaWarps = 8;
-constexpr int kXaStages = 3;
+// (warps per CTA, ring stages per warp, keys per chunk) -- one CTA per SM; WARPS*STAGES*CK*128 B of shared memory (int8)
+struct XaCfgA { static constexpr int W = 8, ST = 3, CK = 64; };
+struct XaCfgB { static constexpr int W = 16, ST = 3, CK = 32; };
+struct XaCfgC { static constexpr int W = 12, ST = 2, CK = 64; };
 
 struct XAttnParams
 {
@@ -481,6 +563,7 @@ struct XAttnParams
     int nch;           // chunks per (row, head) = ceil(S / keys per chunk)
     int chunks_per_warp;
     int max_parts;
+    int early_kv; // the cache is not written by the kernel right before this one: stream it before the PDL wait
     float inv_sqrt_dh;
 };
 
@@ -513,11 +596,12 @@ __device__ __forceinline__ void xa_load16(const uint8_t* p, __half2 (&w)[8])
     }
 }
 
-template <bool INT8>
-__global__ void __launch_bounds__(kXaWarps * 32, 1) cross_attention_kernel(const XAttnParams p)
+template <bool INT8, typename CFG>
+__global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const XAttnParams p)
 {
+    constexpr int kXaWarps = CFG::W, kXaStages = CFG::ST;
     constexpr int ESZ = INT8 ? 1 : 2;
-    constexpr int CK = INT8 ? 64 : 32;      // keys per chunk
+    constexpr int CK = INT8 ? CFG::CK : CFG::CK / 2; // keys per chunk (same bytes per chunk for both cache types)
     constexpr int NIT = CK / 8;             // warp iterations per chunk
     constexpr int kHalfBytes = CK * kDh * ESZ; // bytes of K (or V) per chunk: 4096
     constexpr int kStageBytes = 2 * kHalfBytes;
@@ -557,14 +641,17 @@ __global__ void __launch_bounds__(kXaWarps * 32, 1) cross_attention_kernel(const
         bulk_g2s_hint(ring + s * kStageBytes, kb, bytes, &bars[s], pol);
         bulk_g2s_hint(ring + s * kStageBytes + kHalfBytes, vb, bytes, &bars[s], pol);
     };
+    if (c_begin >= c_end)
+        return;
+    if (!p.early_kv)
+        grid_dep_wait();
     if (lane == 0)
     {
         for (int j = 0; j < kXaStages && c_begin + j < c_end; ++j)
             issue(c_begin + j, j);
     }
-    if (c_begin >= c_end)
-        return;
-    grid_dep_wait(); // q comes from the previous kernel
+    if (p.early_kv)
+        grid_dep_wait(); // q comes from the previous kernel
 
     const float s_qo = INT8 ? p.scale_quant_orig[0] : 1.f;
     const float sscale = s_qo * p.inv_sqrt_dh;
@@ -803,21 +890,11 @@ extern "C" int b200_mmha_generation(const b200_mmha_params* p, b200_stream_t str
     if (p->batch_size == 0)
         return B200_OK;
     B200_REQUIRE_DEVICE();
-    const dim3 grid(p->num_heads, p->batch_size);
-    const size_t smem = sizeof(float) * (p->max_seq_len + 1);
-    B200_REQUIRE(smem <= 200 * 1024, B200_ERR_UNSUPPORTED, "max_seq_len %d too large", p->max_seq_len);
+    const dim3 grid((p->num_heads * p->batch_size + kMmhaWarps - 1) / kMmhaWarps);
     if (p->int8_kv_cache)
-    {
-        if (smem > 48 * 1024)
-            B200_CUDA(cudaFuncSetAttribute(mmha_generation_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        B200_LAUNCH(mmha_generation_kernel<true>, grid, dim3(128), smem, as_stream(stream), *p);
-    }
+        B200_LAUNCH(mmha_generation_kernel<true>, grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, static_kv_hint() ? 1 : 0);
     else
-    {
-        if (smem > 48 * 1024)
-            B200_CUDA(cudaFuncSetAttribute(mmha_generation_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        B200_LAUNCH(mmha_generation_kernel<false>, grid, dim3(128), smem, as_stream(stream), *p);
-    }
+        B200_LAUNCH(mmha_generation_kernel<false>, grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, static_kv_hint() ? 1 : 0);
     return B200_OK;
 }
 
@@ -858,26 +935,50 @@ namespace b200
 {
 struct XaPlan
 {
-    int nch, chunks_per_warp, max_parts, blocks;
+    int nch, chunks_per_warp, max_parts, blocks, cfg;
     size_t smem, ws_bytes;
 };
 
+static int g_xa_cfg = -1; // env B200_XA_CFG = A | B | C
+
 static XaPlan xattn_plan(int R, int H, int S, int int8)
 {
+    if (g_xa_cfg < 0)
+    {
+        const char* e = getenv("B200_XA_CFG");
+        g_xa_cfg = (e != nullptr && (e[0] == 'A' || e[0] == 'B' || e[0] == 'C')) ? e[0] - 'A' : 1;
+    }
+    const int W = g_xa_cfg == 0 ? XaCfgA::W : g_xa_cfg == 1 ? XaCfgB::W : XaCfgC::W;
+    const int ST = g_xa_cfg == 0 ? XaCfgA::ST : g_xa_cfg == 1 ? XaCfgB::ST : XaCfgC::ST;
+    const int CKi = g_xa_cfg == 0 ? XaCfgA::CK : g_xa_cfg == 1 ? XaCfgB::CK : XaCfgC::CK;
     XaPlan pl{};
-    const int ck = int8 ? 64 : 32;
+    pl.cfg = g_xa_cfg;
+    const int ck = int8 ? CKi : CKi / 2;
     pl.nch = (S + ck - 1) / ck;
     const long long total = (long long) R * H * pl.nch;
-    const long long warps = (long long) num_sms() * kXaWarps; // one persistent 8-warp CTA per SM
+    const long long warps = (long long) num_sms() * W; // one persistent CTA per SM
     pl.chunks_per_warp = (int) ((total + warps - 1) / warps);
     if (pl.chunks_per_warp < 1)
         pl.chunks_per_warp = 1;
     const long long used_warps = (total + pl.chunks_per_warp - 1) / pl.chunks_per_warp;
-    pl.blocks = (int) ((used_warps + kXaWarps - 1) / kXaWarps);
+    pl.blocks = (int) ((used_warps + W - 1) / W);
     pl.max_parts = (pl.nch + pl.chunks_per_warp - 1) / pl.chunks_per_warp + 1;
-    pl.smem = (size_t) kXaWarps * kXaStages * 2 * ck * kDh * (int8 ? 1 : 2) + sizeof(uint64_t) * kXaWarps * kXaStages;
+    pl.smem = (size_t) W * ST * 2 * ck * kDh * (int8 ? 1 : 2) + sizeof(uint64_t) * W * ST;
     pl.ws_bytes = (size_t) R * H * pl.max_parts * (kDh + 2) * sizeof(float);
     return pl;
+}
+
+template <bool INT8, typename CFG>
+static int xattn_launch(const XAttnParams& p, const XaPlan& pl, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<INT8, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
+        attr_set = true;
+    }
+    B200_LAUNCH((cross_attention_kernel<INT8, CFG>), dim3(pl.blocks), dim3(CFG::W * 32), pl.smem, st, p);
+    return B200_OK;
 }
 
 int* tc_counter_slot(int needed);
@@ -919,6 +1020,7 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     p.nch = pl.nch;
     p.chunks_per_warp = pl.chunks_per_warp;
     p.max_parts = pl.max_parts;
+    p.early_kv = static_kv_hint() ? 1 : 0;
     p.inv_sqrt_dh = 1.f / sqrtf((float) kDh);
     B200_REQUIRE(workspace && workspace_bytes >= pl.ws_bytes, B200_ERR_WORKSPACE,
         "cross attention: workspace of %zu bytes needed, got %zu", pl.ws_bytes, workspace_bytes);
@@ -926,26 +1028,15 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     B200_REQUIRE(p.counters != nullptr, B200_ERR_UNSUPPORTED, "cross attention: %d (row, head) pairs exceed the counter slot",
         batch_size * num_heads);
     cudaStream_t st = as_stream(stream);
-    static bool attr_set[2] = {false, false};
-    if (int8_kv_cache)
+    switch (pl.cfg * 2 + (int8_kv_cache ? 1 : 0))
     {
-        if (!attr_set[0])
-        {
-            B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
-            attr_set[0] = true;
-        }
-        B200_LAUNCH(cross_attention_kernel<true>, dim3(pl.blocks), dim3(kXaWarps * 32), pl.smem, st, p);
+    case 0: return xattn_launch<false, XaCfgA>(p, pl, st);
+    case 1: return xattn_launch<true, XaCfgA>(p, pl, st);
+    case 2: return xattn_launch<false, XaCfgB>(p, pl, st);
+    case 3: return xattn_launch<true, XaCfgB>(p, pl, st);
+    case 4: return xattn_launch<false, XaCfgC>(p, pl, st);
+    default: return xattn_launch<true, XaCfgC>(p, pl, st);
     }
-    else
-    {
-        if (!attr_set[1])
-        {
-            B200_CUDA(cudaFuncSetAttribute(cross_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
-            attr_set[1] = true;
-        }
-        B200_LAUNCH(cross_attention_kernel<false>, dim3(pl.blocks), dim3(kXaWarps * 32), pl.smem, st, p);
-    }
-    return B200_OK;
 }
 
 extern "C" int b200_cross_kv_pack(const void* k, const void* v, void* cross_kv, const float* kv_scale_orig_quant,

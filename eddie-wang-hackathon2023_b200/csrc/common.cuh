@@ -54,6 +54,7 @@ static inline cudaStream_t as_stream(b200_stream_t s)
     return reinterpret_cast<cudaStream_t>(s);
 }
 
+bool static_kv_hint(); // attention kernels may read KV caches before griddepcontrol.wait (b200_set_static_kv_hint)
 bool pdl_enabled(); // programmatic dependent launch for the hot-path kernels (b200_set_pdl / env B200_PDL)
 
 #ifdef __CUDACC__

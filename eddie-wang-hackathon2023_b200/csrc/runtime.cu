@@ -67,6 +67,18 @@ bool pdl_enabled()
     return g_pdl == 1;
 }
 
+static int g_static_kv = 0;
+
+bool static_kv_hint()
+{
+    return g_static_kv == 1;
+}
+
+void set_static_kv(int on)
+{
+    g_static_kv = on ? 1 : 0;
+}
+
 void set_pdl(int on)
 {
     g_pdl = on ? 1 : 0;
@@ -102,6 +114,12 @@ unsigned long long b200_launch_count(void)
 int b200_set_pdl(int enabled)
 {
     b200::set_pdl(enabled);
+    return B200_OK;
+}
+
+int b200_set_static_kv_hint(int enabled)
+{
+    b200::set_static_kv(enabled);
     return B200_OK;
 }
 }

@@ -51,6 +51,8 @@ class WhisperDecoding:
             raise ValueError("WhisperDecoding implements the int8 weight-only + int8 KV cache configuration")
         self.lib = _lib.load()
         _lib.check(self.lib.b200_init(), "b200_init")
+        # inside a decoder step the caches are never written by the kernel right before the one that reads them
+        self.static_kv = os.environ.get("B200_STATIC_KV", "1") != "0"
         self.dims = dims
         self.B = batch_size
         self.device = torch.device(device)
@@ -264,12 +266,14 @@ class WhisperDecoding:
 
     def _step_body(self):
         B = self.B
+        self.lib.b200_set_static_kv_hint(1 if self.static_kv else 0)
         x = self._buf("x", B, self.d)
         _lib.check(self.lib.b200_embed_tokens_fp16(self.tokens.data_ptr(), self.seq_len.data_ptr(),
                                                    self.tok_emb.data_ptr(), self.pos_emb.data_ptr(), x.data_ptr(), B,
                                                    self.d, self.V, self.Smax, self._st()), "embed")
         self._stack(x, B, 1, context=False)
         self._head(x, B, self.logits, self.next_tokens)
+        self.lib.b200_set_static_kv_hint(0)
         self.seq_len.add_(1)
         self.tokens.copy_(self.next_tokens)
 
