@@ -18,6 +18,7 @@
 // Cache layout: [B, 2, H, Smax, Dh] (KVLinearBuffer, T/cpp/tensorrt_llm/kernels/kvCacheUtils.h:114-170). Dh = 64.
 #include <float.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -110,7 +111,8 @@ __device__ __forceinline__ void load16_raw_perm(const void* base, size_t elem_of
     }
 }
 
-template <bool INT8>
+// XORV flips the sign bit of every stored byte (offset-binary form of the cross cache)
+template <bool INT8, uint32_t XORV = 0u>
 __device__ __forceinline__ void store16(void* base, size_t elem_off, float scale_orig_quant, const __half (&x)[16])
 {
     if constexpr (INT8)
@@ -124,7 +126,7 @@ __device__ __forceinline__ void store16(void* base, size_t elem_off, float scale
             for (int b = 0; b < 4; ++b)
                 v |= (static_cast<uint32_t>(static_cast<uint8_t>(quant_s8(scale_orig_quant * __half2float(x[4 * i + b]))))
                     << (8 * b));
-            w[i] = v;
+            w[i] = v ^ XORV;
         }
         *reinterpret_cast<uint4*>(static_cast<int8_t*>(base) + elem_off) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -550,6 +552,27 @@ struct XaCfgA { static constexpr int W = 8, ST = 3, CK = 64; };
 struct XaCfgB { static constexpr int W = 16, ST = 3, CK = 32; };
 struct XaCfgC { static constexpr int W = 12, ST = 2, CK = 64; };
 
+__device__ __forceinline__ float fast_exp2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ uint32_t h2u(__half2 h)
+{
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col)
+__device__ __forceinline__ void mma_m16n8k16(float& c0, float& c1, float& c2, float& c3, uint32_t a0, uint32_t a1,
+    uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 struct XAttnParams
 {
     const __half* q;   // [R, H*64]
@@ -575,10 +598,11 @@ __device__ __forceinline__ void xa_load16(const uint8_t* p, __half2 (&w)[8])
     if constexpr (INT8)
     {
         const uint4 v = *reinterpret_cast<const uint4*>(p);
-        dequant_word(v.x ^ 0x80808080u, w[0], w[1]);
-        dequant_word(v.y ^ 0x80808080u, w[2], w[3]);
-        dequant_word(v.z ^ 0x80808080u, w[4], w[5]);
-        dequant_word(v.w ^ 0x80808080u, w[6], w[7]);
+        // the cross cache stores offset-binary bytes (q + 128), so the magic-number conversion needs no sign fix-up
+        dequant_word(v.x, w[0], w[1]);
+        dequant_word(v.y, w[2], w[3]);
+        dequant_word(v.z, w[4], w[5]);
+        dequant_word(v.w, w[6], w[7]);
     }
     else
     {
@@ -654,11 +678,11 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
         grid_dep_wait(); // q comes from the previous kernel
 
     const float s_qo = INT8 ? p.scale_quant_orig[0] : 1.f;
-    const float sscale = s_qo * p.inv_sqrt_dh;
+    const float sscale = s_qo * p.inv_sqrt_dh * 1.4426950408889634f;
 
     int cur_bh = -1;
-    __half2 q2[8];
-    float m_run = -FLT_MAX, l_run = 0.f; // l_run: this lane group's share of the denominator
+    uint32_t bq[8];
+    float m_run = -FLT_MAX, l_run = 0.f; // l_run: this lane group's share of the denominator; m_run in log2 units
     float o[16];
 
     auto flush = [&](int bh)
@@ -734,7 +758,7 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
             for (int s2 = 0; s2 < nparts; ++s2)
             {
                 const float* ps = pb + s2 * (kDh + 2);
-                const float w = __expf(__ldcg(ps) - gm);
+                const float w = fast_exp2(__ldcg(ps) - gm);
                 gl += w * __ldcg(ps + 1);
                 a0 += w * __ldcg(ps + 2 + lane);
                 a1 += w * __ldcg(ps + 2 + 32 + lane);
@@ -744,6 +768,80 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
             p.out[(size_t) bh * kDh + 32 + lane] = __float2half_rn(a1 * inv);
             if (lane == 0)
                 p.counters[bh] = 0;
+        }
+    };
+
+
+    // one chunk of keys: scores on the tensor cores (mma.sync m16n8k16, the 16 keys of two warp iterations are the
+    // rows of A, q is column 0 of B), online softmax, then p.v on the fp16 pipe.  FULL: no key of the chunk is masked.
+    auto chunk_body = [&](auto full_tag, const uint8_t* kst, const uint8_t* vst, int nk)
+    {
+        constexpr bool FULL = decltype(full_tag)::value;
+        float sc[NIT];
+        float m_new = m_run;
+#pragma unroll
+        for (int it = 0; it < NIT; it += 2)
+        {
+            __half2 w0[8], w1[8];
+            xa_load16<INT8>(kst + (size_t) it * 8 * kDh * ESZ, w0);
+            xa_load16<INT8>(kst + (size_t) (it + 1) * 8 * kDh * ESZ, w1);
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                mma_m16n8k16(c0, c1, c2, c3, h2u(w0[2 * j]), h2u(w1[2 * j]), h2u(w0[2 * j + 1]), h2u(w1[2 * j + 1]),
+                    bq[2 * j], bq[2 * j + 1]);
+            // column 0 of D lives in the lanes with chunk == 0: c0 = key it*8+kl, c2 = key (it+1)*8+kl
+            float s0 = __shfl_sync(0xffffffffu, c0, lane & ~3) * sscale;
+            float s1 = __shfl_sync(0xffffffffu, c2, lane & ~3) * sscale;
+            if (!FULL)
+            {
+                s0 = (it * 8 + kl < nk) ? s0 : -FLT_MAX;
+                s1 = ((it + 1) * 8 + kl < nk) ? s1 : -FLT_MAX;
+            }
+            sc[it] = s0;
+            sc[it + 1] = s1;
+            m_new = fmaxf(m_new, fmaxf(s0, s1));
+        }
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 4));
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
+        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 16));
+        // online softmax in the log2 domain: rescale the running state to the new maximum
+        const float corr = fast_exp2(m_run - m_new); // 0 on the first chunk (m_run = -FLT_MAX)
+        m_run = m_new;
+        l_run *= corr;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            o[i] *= corr;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            const float e = (FULL || it * 8 + kl < nk) ? fast_exp2(sc[it] - m_new) : 0.f;
+            sc[it] = e;
+            l_run += e;
+        }
+        // ---- p.v: up to 8 keys chained in fp16, then flushed to fp32 ----
+        __half2 o2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            o2[i] = __float2half2_rn(0.f);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            if (!INT8 && !FULL && it * 8 + kl >= nk)
+                continue; // fp16 cache: stale shared-memory bits beyond the last key could decode to NaN
+            const __half2 p2 = __float2half2_rn(sc[it]);
+            __half2 w[8];
+            xa_load16<INT8>(vst + (size_t) it * 8 * kDh * ESZ, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                o2[i] = __hfma2(p2, w[i], o2[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            const float2 f = __half22float2(o2[i]);
+            o[2 * i] += f.x;
+            o[2 * i + 1] += f.y;
         }
     };
 
@@ -768,81 +866,19 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
 #pragma unroll
             for (int i = 0; i < 4; ++i)
             {
-                q2[2 * i] = __halves2half2(qh[4 * i], qh[4 * i + 2]);
-                q2[2 * i + 1] = __halves2half2(qh[4 * i + 1], qh[4 * i + 3]);
+                // B fragment of the score MMA: q is column 0, i.e. only the lanes of key group 0 carry it
+                bq[2 * i] = kl == 0 ? h2u(__halves2half2(qh[4 * i], qh[4 * i + 2])) : 0u;
+                bq[2 * i + 1] = kl == 0 ? h2u(__halves2half2(qh[4 * i + 1], qh[4 * i + 3])) : 0u;
             }
         }
         mbar_wait(&bars[s], (it_local / kXaStages) & 1);
         const uint8_t* kst = ring + s * kStageBytes + (size_t) (kl * kDh + chunk * 16) * ESZ;
         const uint8_t* vst = kst + kHalfBytes;
 
-        // ---- q.k for the 8 x NIT keys of the chunk (this lane: keys kl, kl+8, ...) ----
-        float sc[NIT];
-        float m_new = m_run;
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            __half2 w[8];
-            xa_load16<INT8>(kst + (size_t) it * 8 * kDh * ESZ, w);
-            __half2 h0 = __hmul2(q2[0], w[0]);
-            __half2 h1 = __hmul2(q2[4], w[4]);
-            h0 = __hfma2(q2[1], w[1], h0);
-            h1 = __hfma2(q2[5], w[5], h1);
-            h0 = __hfma2(q2[2], w[2], h0);
-            h1 = __hfma2(q2[6], w[6], h1);
-            h0 = __hfma2(q2[3], w[3], h0);
-            h1 = __hfma2(q2[7], w[7], h1);
-            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-            float sv = (f0.x + f0.y) + (f1.x + f1.y);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-            sv = (it * 8 + kl < nk) ? sv * sscale : -FLT_MAX;
-            sc[it] = sv;
-            m_new = fmaxf(m_new, sv);
-        }
-        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 4));
-        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
-        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 16));
-        // online softmax: rescale the running state to the new maximum
-        const float corr = __expf(m_run - m_new); // 0 on the first chunk (m_run = -FLT_MAX)
-        m_run = m_new;
-        l_run *= corr;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            o[i] *= corr;
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            const float e = (it * 8 + kl < nk) ? __expf(sc[it] - m_new) : 0.f;
-            sc[it] = e;
-            l_run += e;
-        }
-        // ---- p.v: up to 8 keys chained in fp16, then flushed to fp32 ----
-        {
-            __half2 o2[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                o2[i] = __float2half2_rn(0.f);
-#pragma unroll
-            for (int it = 0; it < NIT; ++it)
-            {
-                if (!INT8 && it * 8 + kl >= nk)
-                    continue; // fp16 cache: stale shared-memory bits beyond the last key could decode to NaN
-                const __half2 p2 = __float2half2_rn(sc[it]);
-                __half2 w[8];
-                xa_load16<INT8>(vst + (size_t) it * 8 * kDh * ESZ, w);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    o2[i] = __hfma2(p2, w[i], o2[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-            {
-                const float2 f = __half22float2(o2[i]);
-                o[2 * i] += f.x;
-                o[2 * i + 1] += f.y;
-            }
-        }
+        if (nk == CK)
+            chunk_body(std::true_type{}, kst, vst, nk);
+        else
+            chunk_body(std::false_type{}, kst, vst, nk);
         // stage s is drained: refill it with chunk c + kXaStages
         __syncwarp();
         if (lane == 0 && c + kXaStages < c_end)
@@ -868,7 +904,7 @@ __global__ void cross_kv_pack_kernel(const __half* __restrict__ k, const __half*
         __half x[16];
         load16_half(src, nullptr, x);
         const size_t off = (((size_t) (b * 2 + kv) * H + h) * S + t) * kDh + c * 16;
-        store16<INT8>(cache, off, s_oq, x);
+        store16<INT8, 0x80808080u>(cache, off, s_oq, x);
     }
 }
 

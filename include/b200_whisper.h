@@ -183,7 +183,12 @@ int b200_cross_attention(const void* q, const void* cross_kv, const float* kv_sc
     int num_q_rows, int q_rows_per_seq, int num_heads, int head_size, int kv_len, int int8_kv_cache, void* workspace,
     size_t workspace_bytes, b200_stream_t stream);
 /* Packs fp16 K and V projections [B, S, H*Dh] into the cross-KV cache layout, quantizing with
- * cvt.rni.sat.s8.f32(scale * x) when int8_kv_cache (same rule as the self-attention cache). */
+ * cvt.rni.sat.s8.f32(scale * x) when int8_kv_cache (same rule as the self-attention cache).
+ * The int8 CROSS cache is stored in offset-binary form: byte = (uint8)(q + 128), i.e. the two's-complement byte with
+ * its sign bit flipped (the same +128 bias the reference applies to int8 weights, cutlass_preprocessors.cpp:470-506).
+ * The values are identical; the form lets the attention kernel turn bytes into fp16 without a sign fix-up.  The
+ * reference has no int8 cross cache (its cross K/V are fp16 engine tensors), so this layout is private to the
+ * b200_cross_kv_pack -> b200_cross_attention pair; the self-attention cache keeps plain int8. */
 int b200_cross_kv_pack(const void* k, const void* v, void* cross_kv, const float* kv_scale_orig_quant, int batch_size,
     int kv_len, int num_heads, int head_size, int int8_kv_cache, b200_stream_t stream);
 

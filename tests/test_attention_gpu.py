@@ -130,9 +130,11 @@ def test_cross_attention(B, H, S, int8):
     cache = cross_kv_pack(k, v, oq, H, D, int8)
     if int8:
         ek = woq.kv_quantize_int8(k.view(B, S, H, D).permute(0, 2, 1, 3).contiguous().cpu().numpy(), float(oq))
-        assert np.array_equal(cache[:, 0].cpu().numpy(), ek)
-        kd = (cache[:, 0].float() * qo).half().float()
-        vd = (cache[:, 1].float() * qo).half().float()
+        # the int8 cross cache is kept in offset-binary form (stored byte = q + 128)
+        vals = (cache.view(torch.uint8) ^ 0x80).view(torch.int8)
+        assert np.array_equal(vals[:, 0].cpu().numpy(), ek)
+        kd = (vals[:, 0].float() * qo).half().float()
+        vd = (vals[:, 1].float() * qo).half().float()
     else:
         kd, vd = cache[:, 0].float(), cache[:, 1].float()
     out = cross_attention(q, cache, qo, H, D, int8)
