@@ -551,6 +551,8 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
 struct XaCfgA { static constexpr int W = 8, ST = 3, CK = 64; };
 struct XaCfgB { static constexpr int W = 16, ST = 3, CK = 32; };
 struct XaCfgC { static constexpr int W = 12, ST = 2, CK = 64; };
+struct XaCfgD { static constexpr int W = 13, ST = 2, CK = 64; };
+struct XaCfgE { static constexpr int W = 9, ST = 3, CK = 64; };
 
 __device__ __forceinline__ float fast_exp2(float x)
 {
@@ -620,6 +622,82 @@ __device__ __forceinline__ void xa_load16(const uint8_t* p, __half2 (&w)[8])
     }
 }
 
+// one chunk of keys: scores on the tensor cores (mma.sync m16n8k16, the 16 keys of two warp iterations are the
+// rows of A, q is column 0 of B), online softmax, then p.v on the fp16 pipe.  FULL: no key of the chunk is masked.
+template <bool INT8, int NIT, bool FULL>
+__device__ __forceinline__ void xa_chunk(const uint8_t* kst, const uint8_t* vst, int nk, int kl, int lane, float sscale,
+    const uint32_t (&bq)[8], float& m_run, float& l_run, float (&o)[16])
+{
+    constexpr int ESZ = INT8 ? 1 : 2;
+    float sc[NIT];
+    float m_new = m_run;
+#pragma unroll
+    for (int it = 0; it < NIT; it += 2)
+    {
+        __half2 w0[8], w1[8];
+        xa_load16<INT8>(kst + (size_t) it * 8 * kDh * ESZ, w0);
+        xa_load16<INT8>(kst + (size_t) (it + 1) * 8 * kDh * ESZ, w1);
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            mma_m16n8k16(c0, c1, c2, c3, h2u(w0[2 * j]), h2u(w1[2 * j]), h2u(w0[2 * j + 1]), h2u(w1[2 * j + 1]),
+                bq[2 * j], bq[2 * j + 1]);
+        // column 0 of D lives in the lanes with chunk == 0: c0 = key it*8+kl, c2 = key (it+1)*8+kl
+        float s0 = __shfl_sync(0xffffffffu, c0, lane & ~3) * sscale;
+        float s1 = __shfl_sync(0xffffffffu, c2, lane & ~3) * sscale;
+        if (!FULL)
+        {
+            s0 = (it * 8 + kl < nk) ? s0 : -FLT_MAX;
+            s1 = ((it + 1) * 8 + kl < nk) ? s1 : -FLT_MAX;
+        }
+        sc[it] = s0;
+        sc[it + 1] = s1;
+        m_new = fmaxf(m_new, fmaxf(s0, s1));
+    }
+    m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 4));
+    m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
+    m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 16));
+    // online softmax in the log2 domain: rescale the running state to the new maximum
+    const float corr = fast_exp2(m_run - m_new); // 0 on the first chunk (m_run = -FLT_MAX)
+    m_run = m_new;
+    l_run *= corr;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        o[i] *= corr;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it)
+    {
+        const float e = (FULL || it * 8 + kl < nk) ? fast_exp2(sc[it] - m_new) : 0.f;
+        sc[it] = e;
+        l_run += e;
+    }
+    // ---- p.v: up to 8 keys chained in fp16, then flushed to fp32 ----
+    __half2 o2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        o2[i] = __float2half2_rn(0.f);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it)
+    {
+        if (!INT8 && !FULL && it * 8 + kl >= nk)
+            continue; // fp16 cache: stale shared-memory bits beyond the last key could decode to NaN
+        const __half2 p2 = __float2half2_rn(sc[it]);
+        __half2 w[8];
+        xa_load16<INT8>(vst + (size_t) it * 8 * kDh * ESZ, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            o2[i] = __hfma2(p2, w[i], o2[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        const float2 f = __half22float2(o2[i]);
+        o[2 * i] += f.x;
+        o[2 * i + 1] += f.y;
+    }
+}
+
+
 template <bool INT8, typename CFG>
 __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const XAttnParams p)
 {
@@ -637,7 +715,7 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
 
     const int total = p.B * p.H * p.nch;
     const int gw = blockIdx.x * kXaWarps + warp;
-    const int c_begin = min(gw * p.chunks_per_warp, total);
+    const int c_begin = (int) min((long long) gw * p.chunks_per_warp, (long long) total);
     const int c_end = min(c_begin + p.chunks_per_warp, total);
 
     if (lane == 0)
@@ -772,79 +850,6 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
     };
 
 
-    // one chunk of keys: scores on the tensor cores (mma.sync m16n8k16, the 16 keys of two warp iterations are the
-    // rows of A, q is column 0 of B), online softmax, then p.v on the fp16 pipe.  FULL: no key of the chunk is masked.
-    auto chunk_body = [&](auto full_tag, const uint8_t* kst, const uint8_t* vst, int nk)
-    {
-        constexpr bool FULL = decltype(full_tag)::value;
-        float sc[NIT];
-        float m_new = m_run;
-#pragma unroll
-        for (int it = 0; it < NIT; it += 2)
-        {
-            __half2 w0[8], w1[8];
-            xa_load16<INT8>(kst + (size_t) it * 8 * kDh * ESZ, w0);
-            xa_load16<INT8>(kst + (size_t) (it + 1) * 8 * kDh * ESZ, w1);
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                mma_m16n8k16(c0, c1, c2, c3, h2u(w0[2 * j]), h2u(w1[2 * j]), h2u(w0[2 * j + 1]), h2u(w1[2 * j + 1]),
-                    bq[2 * j], bq[2 * j + 1]);
-            // column 0 of D lives in the lanes with chunk == 0: c0 = key it*8+kl, c2 = key (it+1)*8+kl
-            float s0 = __shfl_sync(0xffffffffu, c0, lane & ~3) * sscale;
-            float s1 = __shfl_sync(0xffffffffu, c2, lane & ~3) * sscale;
-            if (!FULL)
-            {
-                s0 = (it * 8 + kl < nk) ? s0 : -FLT_MAX;
-                s1 = ((it + 1) * 8 + kl < nk) ? s1 : -FLT_MAX;
-            }
-            sc[it] = s0;
-            sc[it + 1] = s1;
-            m_new = fmaxf(m_new, fmaxf(s0, s1));
-        }
-        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 4));
-        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
-        m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 16));
-        // online softmax in the log2 domain: rescale the running state to the new maximum
-        const float corr = fast_exp2(m_run - m_new); // 0 on the first chunk (m_run = -FLT_MAX)
-        m_run = m_new;
-        l_run *= corr;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            o[i] *= corr;
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            const float e = (FULL || it * 8 + kl < nk) ? fast_exp2(sc[it] - m_new) : 0.f;
-            sc[it] = e;
-            l_run += e;
-        }
-        // ---- p.v: up to 8 keys chained in fp16, then flushed to fp32 ----
-        __half2 o2[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            o2[i] = __float2half2_rn(0.f);
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            if (!INT8 && !FULL && it * 8 + kl >= nk)
-                continue; // fp16 cache: stale shared-memory bits beyond the last key could decode to NaN
-            const __half2 p2 = __float2half2_rn(sc[it]);
-            __half2 w[8];
-            xa_load16<INT8>(vst + (size_t) it * 8 * kDh * ESZ, w);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                o2[i] = __hfma2(p2, w[i], o2[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-        {
-            const float2 f = __half22float2(o2[i]);
-            o[2 * i] += f.x;
-            o[2 * i + 1] += f.y;
-        }
-    };
-
     for (int c = c_begin; c < c_end; ++c)
     {
         const int it_local = c - c_begin;
@@ -876,15 +881,178 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
         const uint8_t* vst = kst + kHalfBytes;
 
         if (nk == CK)
-            chunk_body(std::true_type{}, kst, vst, nk);
+            xa_chunk<INT8, NIT, true>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o);
         else
-            chunk_body(std::false_type{}, kst, vst, nk);
+            xa_chunk<INT8, NIT, false>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o);
         // stage s is drained: refill it with chunk c + kXaStages
         __syncwarp();
         if (lane == 0 && c + kXaStages < c_end)
             issue(c + kXaStages, s);
     }
     flush(cur_bh);
+}
+
+// ---- cross attention, one CTA per (row, head) at a time ("row-head" kernel) --------------------------------------
+// Used when there are enough (row, head) pairs to fill the GPU.  CTA i walks the pairs i, i + grid, ...; the W warps
+// of the CTA split the pair's chunks into contiguous runs, stream them through their private TMA rings exactly like
+// the split kernel above, and merge their partial softmax states through shared memory -- no global partials, no
+// fences, no counters.  q of the next pair is fetched while the current one is being processed.
+template <bool INT8, typename CFG>
+__global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_rowhead_kernel(const XAttnParams p)
+{
+    constexpr int W = CFG::W, ST = CFG::ST;
+    constexpr int ESZ = INT8 ? 1 : 2;
+    constexpr int CK = INT8 ? CFG::CK : CFG::CK / 2;
+    constexpr int NIT = CK / 8;
+    constexpr int kHalfBytes = CK * kDh * ESZ;
+    constexpr int kStageBytes = 2 * kHalfBytes;
+    constexpr int kPart = kDh + 4; // m, l, 2 pad floats (keeps the o rows 16-byte aligned), o[64]
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = lane & 3, kl = lane >> 2;
+    uint8_t* ring = smem + (size_t) warp * ST * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) W * ST * kStageBytes) + warp * ST;
+    float* parts = reinterpret_cast<float*>(smem + (size_t) W * ST * kStageBytes + sizeof(uint64_t) * W * ST); // [2][W][68]
+
+    const int RH = p.B * p.H;
+    const int nbh = (RH - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x; // pairs of this CTA (>= 1)
+    const int wc0 = warp * p.nch / W, wc1 = (warp + 1) * p.nch / W;                   // this warp's chunks of every pair
+    const int n_w = wc1 - wc0;
+    const int tot = nbh * n_w;
+
+    if (lane == 0)
+    {
+        for (int s = 0; s < ST; ++s)
+            mbar_init(&bars[s], 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+    }
+    __syncwarp();
+    grid_dep_launch_dependents();
+
+    const uint64_t pol = policy_evict_first();
+    auto issue = [&](int i, int s)
+    {
+        const int r = i / n_w, ch = wc0 + (i - r * n_w);
+        const int bh = blockIdx.x + r * gridDim.x;
+        const int b = (bh / p.H) / p.q_per_seq, h = bh % p.H;
+        const int key0 = ch * CK;
+        const int nk = min(CK, p.S - key0);
+        const uint32_t bytes = (uint32_t) nk * kDh * ESZ;
+        const uint8_t* kb = static_cast<const uint8_t*>(p.kv) + (((size_t) (b * 2 + 0) * p.H + h) * p.S + key0) * (size_t) (kDh * ESZ);
+        const uint8_t* vb = static_cast<const uint8_t*>(p.kv) + (((size_t) (b * 2 + 1) * p.H + h) * p.S + key0) * (size_t) (kDh * ESZ);
+        mbar_arrive_expect_tx(&bars[s], 2 * bytes);
+        bulk_g2s_hint(ring + s * kStageBytes, kb, bytes, &bars[s], pol);
+        bulk_g2s_hint(ring + s * kStageBytes + kHalfBytes, vb, bytes, &bars[s], pol);
+    };
+    if (!p.early_kv)
+        grid_dep_wait();
+    if (lane == 0)
+    {
+        for (int j = 0; j < ST && j < tot; ++j)
+            issue(j, j);
+    }
+    if (p.early_kv)
+        grid_dep_wait(); // q comes from the previous kernel
+
+    // q of the first pair and the dequant scale: both loads in flight together
+    const uint4* qsrc = reinterpret_cast<const uint4*>(p.q + (size_t) blockIdx.x * kDh + chunk * 16);
+    uint4 qn0 = __ldg(qsrc), qn1 = __ldg(qsrc + 1);
+    const float s_qo = INT8 ? __ldg(p.scale_quant_orig) : 1.f;
+    const float sscale = s_qo * p.inv_sqrt_dh * 1.4426950408889634f;
+
+    int i = 0;
+    for (int r = 0; r < nbh; ++r)
+    {
+        const int bh = blockIdx.x + r * gridDim.x;
+        uint32_t bq[8];
+        {
+            const uint32_t u[8] = {qn0.x, qn0.y, qn0.z, qn0.w, qn1.x, qn1.y, qn1.z, qn1.w}; // u[j] = (d2j, d2j+1)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                // B fragment of the score MMA: q is column 0, i.e. only the lanes of key group 0 carry it
+                bq[2 * j] = kl == 0 ? __byte_perm(u[2 * j], u[2 * j + 1], 0x5410) : 0u;     // (d4j, d4j+2)
+                bq[2 * j + 1] = kl == 0 ? __byte_perm(u[2 * j], u[2 * j + 1], 0x7632) : 0u; // (d4j+1, d4j+3)
+            }
+        }
+        if (r + 1 < nbh)
+        {
+            const uint4* qs = reinterpret_cast<const uint4*>(p.q + (size_t) (bh + gridDim.x) * kDh + chunk * 16);
+            qn0 = __ldg(qs);
+            qn1 = __ldg(qs + 1);
+        }
+        float m_run = -FLT_MAX, l_run = 0.f;
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            o[j] = 0.f;
+        for (int j = 0; j < n_w; ++j, ++i)
+        {
+            const int s = i % ST;
+            const int nk = min(CK, p.S - (wc0 + j) * CK);
+            mbar_wait(&bars[s], (i / ST) & 1);
+            const uint8_t* kst = ring + s * kStageBytes + (size_t) (kl * kDh + chunk * 16) * ESZ;
+            const uint8_t* vst = kst + kHalfBytes;
+            if (nk == CK)
+                xa_chunk<INT8, NIT, true>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o);
+            else
+                xa_chunk<INT8, NIT, false>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o);
+            __syncwarp();
+            if (lane == 0 && i + ST < tot)
+                issue(i + ST, s);
+        }
+        // this warp's state, reduced over its 8 key groups -> shared memory
+        float l = l_run;
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+        {
+            float v = o[j];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            o[j] = v;
+        }
+        float* pr = parts + ((r & 1) * W + warp) * kPart;
+        if (kl == 0)
+        {
+            // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
+            float* dst = pr + 4 + chunk * 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(o[4 * j + 0], o[4 * j + 2], o[4 * j + 1], o[4 * j + 3]);
+            if (chunk == 0)
+            {
+                pr[0] = m_run;
+                pr[1] = l;
+            }
+        }
+        __syncthreads();
+        if (warp == r % W)
+        {
+            const float* pb = parts + (r & 1) * W * kPart;
+            float gm = -FLT_MAX;
+#pragma unroll
+            for (int w2 = 0; w2 < W; ++w2)
+                gm = fmaxf(gm, pb[w2 * kPart]);
+            float gl = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < W; ++w2)
+            {
+                const float* ps = pb + w2 * kPart;
+                const float wt = fast_exp2(ps[0] - gm);
+                gl += wt * ps[1];
+                a0 += wt * ps[4 + lane];
+                a1 += wt * ps[4 + 32 + lane];
+            }
+            const float inv = s_qo / gl; // hoisted V dequant scale
+            p.out[(size_t) bh * kDh + lane] = __float2half_rn(a0 * inv);
+            p.out[(size_t) bh * kDh + 32 + lane] = __float2half_rn(a1 * inv);
+        }
+    }
 }
 
 // fp16 K, V [B, S, H*64] -> cache [B, 2, H, S, 64] (int8-quantized or fp16).  grid (S, B), 128 threads... one
@@ -971,28 +1139,48 @@ namespace b200
 {
 struct XaPlan
 {
-    int nch, chunks_per_warp, max_parts, blocks, cfg;
+    int nch, chunks_per_warp, max_parts, blocks, cfg, rowhead;
     size_t smem, ws_bytes;
 };
 
-static int g_xa_cfg = -1; // env B200_XA_CFG = A | B | C
+static int g_xa_cfg = -1;  // env B200_XA_CFG = A .. E
+static int g_xa_mode = -1; // env B200_XA_MODE = split | rowhead | auto (default)
 
 static XaPlan xattn_plan(int R, int H, int S, int int8)
 {
     if (g_xa_cfg < 0)
     {
         const char* e = getenv("B200_XA_CFG");
-        g_xa_cfg = (e != nullptr && (e[0] == 'A' || e[0] == 'B' || e[0] == 'C')) ? e[0] - 'A' : 1;
+        g_xa_cfg = (e != nullptr && e[0] >= 'A' && e[0] <= 'E') ? e[0] - 'A' : 2;
     }
-    const int W = g_xa_cfg == 0 ? XaCfgA::W : g_xa_cfg == 1 ? XaCfgB::W : XaCfgC::W;
-    const int ST = g_xa_cfg == 0 ? XaCfgA::ST : g_xa_cfg == 1 ? XaCfgB::ST : XaCfgC::ST;
-    const int CKi = g_xa_cfg == 0 ? XaCfgA::CK : g_xa_cfg == 1 ? XaCfgB::CK : XaCfgC::CK;
+    static const int kW[5] = {XaCfgA::W, XaCfgB::W, XaCfgC::W, XaCfgD::W, XaCfgE::W};
+    static const int kST[5] = {XaCfgA::ST, XaCfgB::ST, XaCfgC::ST, XaCfgD::ST, XaCfgE::ST};
+    static const int kCK[5] = {XaCfgA::CK, XaCfgB::CK, XaCfgC::CK, XaCfgD::CK, XaCfgE::CK};
+    const int W = kW[g_xa_cfg], ST = kST[g_xa_cfg], CKi = kCK[g_xa_cfg];
+    if (g_xa_mode < 0)
+    {
+        const char* e = getenv("B200_XA_MODE");
+        g_xa_mode = (e != nullptr && e[0] == 's') ? 0 : (e != nullptr && e[0] == 'r') ? 1 : 2;
+    }
     XaPlan pl{};
     pl.cfg = g_xa_cfg;
     const int ck = int8 ? CKi : CKi / 2;
     pl.nch = (S + ck - 1) / ck;
+    // enough (row, head) pairs to give every SM whole pairs: merge inside the CTA, no workspace
+    pl.rowhead = g_xa_mode == 2 ? ((long long) R * H * 2 >= num_sms() ? 1 : 0) : g_xa_mode;
+    if (pl.rowhead)
+    {
+        pl.blocks = R * H < num_sms() ? R * H : num_sms();
+        pl.smem = (size_t) W * ST * 2 * ck * kDh * (int8 ? 1 : 2) + sizeof(uint64_t) * W * ST
+            + sizeof(float) * 2 * W * (kDh + 4);
+        pl.ws_bytes = 0;
+        return pl;
+    }
     const long long total = (long long) R * H * pl.nch;
-    const long long warps = (long long) num_sms() * W; // one persistent CTA per SM
+    // one persistent CTA per SM, every warp a contiguous run of chunks_per_warp chunks.  (Dealing the chunks evenly
+    // to all 148 x W warps measured slower than this rounding, which leaves a few SMs free for the next kernel's
+    // programmatic early launch.)
+    const long long warps = (long long) num_sms() * W;
     pl.chunks_per_warp = (int) ((total + warps - 1) / warps);
     if (pl.chunks_per_warp < 1)
         pl.chunks_per_warp = 1;
@@ -1014,6 +1202,19 @@ static int xattn_launch(const XAttnParams& p, const XaPlan& pl, cudaStream_t st)
         attr_set = true;
     }
     B200_LAUNCH((cross_attention_kernel<INT8, CFG>), dim3(pl.blocks), dim3(CFG::W * 32), pl.smem, st, p);
+    return B200_OK;
+}
+
+template <bool INT8, typename CFG>
+static int xattn_launch_rowhead(const XAttnParams& p, const XaPlan& pl, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        B200_CUDA(cudaFuncSetAttribute(cross_attention_rowhead_kernel<INT8, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
+        attr_set = true;
+    }
+    B200_LAUNCH((cross_attention_rowhead_kernel<INT8, CFG>), dim3(pl.blocks), dim3(CFG::W * 32), pl.smem, st, p);
     return B200_OK;
 }
 
@@ -1058,12 +1259,28 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     p.max_parts = pl.max_parts;
     p.early_kv = static_kv_hint() ? 1 : 0;
     p.inv_sqrt_dh = 1.f / sqrtf((float) kDh);
+    cudaStream_t st = as_stream(stream);
+    if (pl.rowhead)
+    {
+        switch (pl.cfg * 2 + (int8_kv_cache ? 1 : 0))
+        {
+        case 0: return xattn_launch_rowhead<false, XaCfgA>(p, pl, st);
+        case 1: return xattn_launch_rowhead<true, XaCfgA>(p, pl, st);
+        case 2: return xattn_launch_rowhead<false, XaCfgB>(p, pl, st);
+        case 3: return xattn_launch_rowhead<true, XaCfgB>(p, pl, st);
+        case 4: return xattn_launch_rowhead<false, XaCfgC>(p, pl, st);
+        case 5: return xattn_launch_rowhead<true, XaCfgC>(p, pl, st);
+        case 6: return xattn_launch_rowhead<false, XaCfgD>(p, pl, st);
+        case 7: return xattn_launch_rowhead<true, XaCfgD>(p, pl, st);
+        case 8: return xattn_launch_rowhead<false, XaCfgE>(p, pl, st);
+        default: return xattn_launch_rowhead<true, XaCfgE>(p, pl, st);
+        }
+    }
     B200_REQUIRE(workspace && workspace_bytes >= pl.ws_bytes, B200_ERR_WORKSPACE,
         "cross attention: workspace of %zu bytes needed, got %zu", pl.ws_bytes, workspace_bytes);
     p.counters = tc_counter_slot(batch_size * num_heads);
     B200_REQUIRE(p.counters != nullptr, B200_ERR_UNSUPPORTED, "cross attention: %d (row, head) pairs exceed the counter slot",
         batch_size * num_heads);
-    cudaStream_t st = as_stream(stream);
     switch (pl.cfg * 2 + (int8_kv_cache ? 1 : 0))
     {
     case 0: return xattn_launch<false, XaCfgA>(p, pl, st);
@@ -1071,7 +1288,11 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     case 2: return xattn_launch<false, XaCfgB>(p, pl, st);
     case 3: return xattn_launch<true, XaCfgB>(p, pl, st);
     case 4: return xattn_launch<false, XaCfgC>(p, pl, st);
-    default: return xattn_launch<true, XaCfgC>(p, pl, st);
+    case 5: return xattn_launch<true, XaCfgC>(p, pl, st);
+    case 6: return xattn_launch<false, XaCfgD>(p, pl, st);
+    case 7: return xattn_launch<true, XaCfgD>(p, pl, st);
+    case 8: return xattn_launch<false, XaCfgE>(p, pl, st);
+    default: return xattn_launch<true, XaCfgE>(p, pl, st);
     }
 }
 

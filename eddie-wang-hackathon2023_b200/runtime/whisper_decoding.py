@@ -109,7 +109,7 @@ class WhisperDecoding:
         self.graph = None
         # side stream that pulls the next layer's cross-KV cache into L2 while the current layer's small kernels run
         self.prefetch_cross_kv = os.environ.get("B200_XKV_PREFETCH", "0") != "0"
-        self.fuse_ln = os.environ.get("B200_FUSE_LN", "1") != "0"
+        self.fuse_ln = os.environ.get("B200_FUSE_LN", "0") != "0"
         self._side = torch.cuda.Stream(device=dev) if torch.cuda.is_available() else None
         self._pinned_in = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
         self._pinned_out = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None

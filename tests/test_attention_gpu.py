@@ -114,7 +114,9 @@ def test_context_then_generation(int8, in_len):
             past_k, past_v = k_all, v_all
 
 
-@pytest.mark.parametrize("B,H,S", [(1, 20, 1500), (16, 20, 1500), (3, 6, 1500), (2, 2, 96), (5, 4, 333)])
+# the last three shapes have enough (row, head) pairs for the one-CTA-per-pair kernel, with fewer chunks than warps
+@pytest.mark.parametrize("B,H,S", [(1, 20, 1500), (16, 20, 1500), (3, 6, 1500), (2, 2, 96), (5, 4, 333),
+                                   (10, 16, 700), (40, 4, 100), (9, 20, 1)])
 @pytest.mark.parametrize("int8", [True, False])
 def test_cross_attention(B, H, S, int8):
     from b200_whisper.functional import cross_attention, cross_kv_pack
@@ -148,7 +150,13 @@ def test_cross_attention_multi_query_rows():
     """Context phase: S_q prompt rows per sequence attend to their sequence's cache."""
     from b200_whisper.functional import cross_attention, cross_kv_pack
     torch.manual_seed(5)
-    B, H, D, S, Sq = 3, 4, 64, 200, 4
+    _multi_query_rows(3, 4, 200, 4)
+    _multi_query_rows(6, 8, 130, 5)  # 240 (row, head) pairs: one-CTA-per-pair kernel
+
+
+def _multi_query_rows(B, H, S, Sq):
+    from b200_whisper.functional import cross_attention, cross_kv_pack
+    D = 64
     dev = "cuda"
     k = torch.randn((B, S, H * D), device=dev).half()
     v = torch.randn((B, S, H * D), device=dev).half()
