@@ -224,7 +224,7 @@ struct TcSmem
     static constexpr size_t ring = (size_t) SS * (kWTileBytes + XTileBytes);
     static constexpr size_t rbuf = (size_t) 128 * MT * sizeof(float); // cluster reduction inbox [S][MT][128/S]
     static_assert(AS <= SS, "the TMEM A ring is never deeper than the shared-memory ring");
-    static constexpr size_t bars = sizeof(uint64_t) * (2 * SS + AS + 2) + 16 + ((AS & 1) ? 8 : 0);
+    static constexpr size_t bars = sizeof(uint64_t) * (3 * SS + AS + 2) + 16 + ((AS & 1) ? 8 : 0);
 
     static constexpr size_t ln_bytes(int K)
     {
@@ -257,9 +257,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smW = smem;
     uint8_t* smX = smem + SS * kWTileBytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smX + SS * XTileBytes);
-    uint64_t* stage_free = full + SS;  // MMA of block i done (index i % SS): its smem stage and TMEM A stage are reusable
-    uint64_t* a_ready = stage_free + SS; // dequantized A tile of block i is in TMEM stage i % AS (and its X tile has landed)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smX + SS * XTileBytes); // weight tile of block i has landed
+    uint64_t* xfull = full + SS;       // activation tile of block i has landed (separate: the weights never wait for x)
+    uint64_t* stage_free = xfull + SS; // MMA of block i done (index i % SS): its smem stage and TMEM A stage are reusable
+    uint64_t* a_ready = stage_free + SS; // dequantized A tile of block i is in TMEM stage i % AS
     uint64_t* acc_done = a_ready + AS;
     uint64_t* red_bar = acc_done + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 1);
@@ -285,16 +286,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // ---- prologue.  The producer thread owns the `full` barriers: it initialises them and immediately starts the
     // weight stream (weights never depend on the previous kernel), while the other warps set up the rest. ----
     const int pre = nkb < SS ? nkb : SS;
-    const uint32_t tx = kWTileBytes + (fused_ln ? 0 : XTileBytes);
     if (warp == kProducerWarp && elect_one_sync())
     {
         for (int s = 0; s < SS; ++s)
-            mbar_init(&full[s], fused_ln ? 1 + kTcDequantWarps : 1);
+        {
+            mbar_init(&full[s], 1);
+            mbar_init(&xfull[s], fused_ln ? kTcDequantWarps : 1);
+        }
         fence_mbar_init();
         fence_proxy_async_smem();
         for (int i = 0; i < pre; ++i)
         {
-            mbar_arrive_expect_tx(&full[i], tx);
+            mbar_arrive_expect_tx(&full[i], kWTileBytes);
             tma_load_2d(smW + i * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[i]);
         }
         TC_STAMP(2);
@@ -349,16 +352,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             {
                 grid_dep_wait();
                 for (int i = 0; i < pre; ++i)
-                    tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &full[i]);
+                {
+                    mbar_arrive_expect_tx(&xfull[i], XTileBytes);
+                    tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[i]);
+                }
             }
             for (int i = pre; i < nkb; ++i)
             {
                 const int ss = i % SS;
                 mbar_wait(&stage_free[ss], ((i / SS) - 1) & 1);
-                mbar_arrive_expect_tx(&full[ss], tx);
+                mbar_arrive_expect_tx(&full[ss], kWTileBytes);
                 tma_load_2d(smW + ss * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[ss]);
                 if (!fused_ln)
-                    tma_load_2d(smX + ss * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &full[ss]);
+                {
+                    mbar_arrive_expect_tx(&xfull[ss], XTileBytes);
+                    tma_load_2d(smX + ss * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[ss]);
+                }
             }
         }
     }
@@ -369,8 +378,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int i = 0; i < nkb; ++i)
         {
             const int ss = i % SS, as = i % AS;
-            // a_ready implies full[ss]: the dequant warps arrive on it only after they observed the TMA completion
             mbar_wait(&a_ready[as], (i / AS) & 1);
+            mbar_wait(&xfull[ss], (i / SS) & 1);
             tc_fence_after();
             if (lane == 0 && i < 12)
                 TC_STAMP(16 + 4 * i + 2);
@@ -516,7 +525,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0)
-                mbar_arrive(&full[ss]);
+                mbar_arrive(&xfull[ss]);
         };
 
         // this thread's 32 bytes of k-block i: chunks 2*kh and 2*kh+1 of its 64-byte column slice
@@ -1082,7 +1091,7 @@ bool woq_tc_can_fuse_ln(int M, int K)
 {
     if (M > 32)
         return false;
-    return M <= 16 ? TcSmem<16, 10, 6>::total(true, true, K) <= 200 * 1024 : TcSmem<32, 8, 6>::total(true, true, K) <= 200 * 1024;
+    return M <= 16 ? TcSmem<16, 10, 10>::total(true, true, K) <= 200 * 1024 : TcSmem<32, 8, 8>::total(true, true, K) <= 200 * 1024;
 }
 
 // tcgen05 path entry: any M >= 1.  ln_gamma != nullptr: A is the raw residual stream and LayerNorm(A) is the operand.
@@ -1133,8 +1142,8 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     switch (pl.MT)
     {
-    case 16: return launch_tc<16, 10, 6>(tmW, tmX, p, grid, stream);
-    case 32: return launch_tc<32, 8, 6>(tmW, tmX, p, grid, stream);
+    case 16: return launch_tc<16, 10, 10>(tmW, tmX, p, grid, stream);
+    case 32: return launch_tc<32, 8, 8>(tmW, tmX, p, grid, stream);
     case 64: return launch_tc<64, 6, 6>(tmW, tmX, p, grid, stream);
     case 128: return launch_tc<128, 4, 4>(tmW, tmX, p, grid, stream);
     default: return launch_tc<256, 4, 4>(tmW, tmX, p, grid, stream);

@@ -36,7 +36,7 @@ for fam in "$@"; do
          echo "fuse_ln=$1 xa_cfg=$2 static_kv=$3 xa_mode=${4:-auto}: $(grep -o '"value": [0-9.]*' gpurun_out/bench_var.log | head -1) $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench_var.log | head -1) $(grep -o '"frac": [0-9.]*' gpurun_out/bench_var.log | head -1) $(tail -n 2 gpurun_out/bench_var.log | grep -v '^{' | cut -c1-200)" | tee -a gpurun_out/summary.txt
        done;;
     ncufull) echo "=== ncu full" | tee -a gpurun_out/summary.txt
-       timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:cross_attention_kernel -c 2 \
+       timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:cross_attention -c 2 \
           -f -o gpurun_out/prof_xattn python bench.py --profile > gpurun_out/ncu_xattn.log 2>&1; echo "exit $?" | tee -a gpurun_out/summary.txt
        timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:woq_gemm_tc_kernel -c 6 \
           -f -o gpurun_out/prof_gemm python bench.py --profile > gpurun_out/ncu_gemm.log 2>&1; echo "exit $?" | tee -a gpurun_out/summary.txt;;
