@@ -46,6 +46,9 @@ _SIGS = {
     "b200_woq_int8_gemm": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "b200_woq_int8_gemm_fused": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "b200_woq_int8_gemm_ln_fused": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "b200_woq_ln_fold_prepare": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "b200_woq_int8_gemm_ln_folded": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz,
+                                          _vp]),
     "b200_woq_set_kernel_policy": (_i, [_i]),
     "b200_debug_tc_timing": (_i, [_vp]),
     "b200_mmha_generation": (_i, [ctypes.POINTER(MmhaParams), _vp]),

@@ -11,13 +11,54 @@ int woq_gemv_simt(const __half* A, int M, int K, const uint8_t* W, const __half*
     int activation, const __half* residual, __half* C, cudaStream_t stream);
 int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
     int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-    const __half* ln_gamma, const __half* ln_beta, float ln_eps);
+    const __half* fold_gamma, const float* fold_c1s, const float* fold_c2, float ln_eps);
 size_t woq_tc_workspace_bytes(int max_m, int N, int K);
 int tc_init();
 void tc_set_debug_buffer(long long* p);
-bool woq_tc_can_fuse_ln(int M, int K);
+bool woq_tc_can_fold_ln(int M, int K);
 
 static int g_policy = 0; // 0 auto, 1 simt, 2 tcgen05
+
+// One thread per weight column n: walks the column through the preprocessed layout exactly like the GEMM's dequant
+// warps do (same 16-byte chunks, same PRMT/HSUB2 conversion, same HMUL2 by the gamma pair) and sums
+//   c1[n] = sum_k fp16(Wint[k][n] * gamma[k])      c2[n] = sum_k beta[k] * Wint[k][n]
+// both scaled by the column's dequant scale at the end.
+__global__ void ln_fold_prepare_kernel(const uint8_t* __restrict__ W, const __half* __restrict__ scales,
+    const __half* __restrict__ gamma, const __half* __restrict__ beta, int K, int N, float* __restrict__ c1s,
+    float* __restrict__ c2)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N)
+        return;
+    const uint8_t* row = W + (size_t) (n >> 1) * 2 * K + (n & 1) * 64;
+    const __half2* g2 = reinterpret_cast<const __half2*>(gamma);
+    const __half2* b2 = reinterpret_cast<const __half2*>(beta);
+    float a1 = 0.f, a2 = 0.f;
+    for (int kb = 0; kb < K / 64; ++kb)
+    {
+        for (int ch = 0; ch < 4; ++ch)
+        {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + (size_t) kb * 128 + ch * 16));
+            const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+            {
+                __half2 lo, hi;
+                dequant_word(words[w], lo, hi);
+                const int plo = kb * 32 + ch * 8 + w, phi = plo + 4; // k pairs (2p, 2p+1)
+                const float2 flo = __half22float2(__hmul2(lo, g2[plo]));
+                const float2 fhi = __half22float2(__hmul2(hi, g2[phi]));
+                a1 += (flo.x + flo.y) + (fhi.x + fhi.y);
+                const float2 wl = __half22float2(lo), wh = __half22float2(hi);
+                const float2 bl = __half22float2(b2[plo]), bh = __half22float2(b2[phi]);
+                a2 += wl.x * bl.x + wl.y * bl.y + wh.x * bh.x + wh.y * bh.y;
+            }
+        }
+    }
+    const float sc = __half2float(scales[n]);
+    c1s[n] = sc * a1;
+    c2[n] = sc * a2;
+}
 } // namespace b200
 
 using namespace b200;
@@ -38,7 +79,7 @@ extern "C" size_t b200_woq_workspace_bytes(int max_m, int n, int k)
 
 static int woq_dispatch(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N, const void* bias,
     int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes, b200_stream_t stream,
-    const void* ln_gamma, const void* ln_beta, float ln_eps)
+    const void* ln_gamma, const void* ln_beta, float ln_eps, const float* fold_c1s = nullptr, const float* fold_c2 = nullptr)
 {
     B200_REQUIRE(A && Wproc && scales && C, B200_ERR_INVALID_ARG, "null pointer (A/W/scales/C)");
     B200_REQUIRE(M >= 0, B200_ERR_INVALID_ARG, "M=%d must be >= 0", M);
@@ -50,7 +91,8 @@ static int woq_dispatch(const void* A, int M, int K, const int8_t* Wproc, const 
         return B200_OK; // empty batch: nothing to do (the reference would launch an empty grid)
     B200_REQUIRE_DEVICE();
     const bool simt = (g_policy == 1) || (g_policy == 0 && M <= 4);
-    if (simt || (ln_gamma != nullptr && !woq_tc_can_fuse_ln(M, K)))
+    const bool fold = ln_gamma != nullptr && fold_c1s != nullptr && fold_c2 != nullptr && !simt && woq_tc_can_fold_ln(M, K);
+    if (!fold)
     {
         const __half* a = static_cast<const __half*>(A);
         if (ln_gamma != nullptr)
@@ -73,12 +115,37 @@ static int woq_dispatch(const void* A, int M, int K, const int8_t* Wproc, const 
                 static_cast<__half*>(C), as_stream(stream));
         return woq_gemm_tc(a, M, K, reinterpret_cast<const uint8_t*>(Wproc), static_cast<const __half*>(scales), N,
             static_cast<const __half*>(bias), activation, static_cast<const __half*>(residual), static_cast<__half*>(C),
-            workspace, workspace_bytes, as_stream(stream), nullptr, nullptr, 0.f);
+            workspace, workspace_bytes, as_stream(stream), nullptr, nullptr, nullptr, 0.f);
     }
     return woq_gemm_tc(static_cast<const __half*>(A), M, K, reinterpret_cast<const uint8_t*>(Wproc),
         static_cast<const __half*>(scales), N, static_cast<const __half*>(bias), activation,
         static_cast<const __half*>(residual), static_cast<__half*>(C), workspace, workspace_bytes, as_stream(stream),
-        static_cast<const __half*>(ln_gamma), static_cast<const __half*>(ln_beta), ln_eps);
+        static_cast<const __half*>(ln_gamma), fold_c1s, fold_c2, ln_eps);
+}
+
+extern "C" int b200_woq_ln_fold_prepare(const int8_t* Wproc, const void* scales, const void* ln_gamma, const void* ln_beta,
+    int K, int N, float* c1s, float* c2, b200_stream_t stream)
+{
+    B200_REQUIRE(Wproc && scales && ln_gamma && ln_beta && c1s && c2, B200_ERR_INVALID_ARG, "null pointer");
+    B200_REQUIRE(K > 0 && K % 64 == 0 && N > 0 && N % 64 == 0, B200_ERR_INVALID_ARG,
+        "K=%d and N=%d must be positive multiples of 64", K, N);
+    B200_REQUIRE_DEVICE();
+    // plain (fully serialised) launch: a one-off preparation step, no programmatic overlap with its producers
+    ln_fold_prepare_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(Wproc),
+        static_cast<const __half*>(scales), static_cast<const __half*>(ln_gamma), static_cast<const __half*>(ln_beta), K,
+        N, c1s, c2);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_woq_int8_gemm_ln_folded(const void* X, const void* ln_gamma, const void* ln_beta, const float* c1s,
+    const float* c2, float ln_eps, int M, int K, const int8_t* Wproc, const void* scales, int N, const void* bias,
+    int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes, b200_stream_t stream)
+{
+    B200_REQUIRE(ln_gamma && ln_beta && c1s && c2, B200_ERR_INVALID_ARG, "null pointer (ln_gamma/ln_beta/c1s/c2)");
+    B200_REQUIRE(workspace == nullptr || workspace != C, B200_ERR_INVALID_ARG, "workspace must not alias C");
+    return woq_dispatch(X, M, K, Wproc, scales, N, bias, activation, residual, C, workspace, workspace_bytes, stream,
+        ln_gamma, ln_beta, ln_eps, c1s, c2);
 }
 
 extern "C" int b200_woq_int8_gemm_fused(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N,

@@ -42,10 +42,13 @@ struct TcParams
     __half* C;
     float* slabs;  // split-K partial tiles (workspace), global-memory reduction mode
     int* counters; // per-tile arrival counters (library owned, self-resetting)
-    // fused LayerNorm on the activation operand: x_raw != nullptr => B tiles are LN(x_raw) computed in-kernel
-    const __half* x_raw; // [M, K]
-    const __half* ln_gamma;
-    const __half* ln_beta;
+    // folded LayerNorm (fold_gamma != nullptr): the activation operand is the RAW residual stream x; gamma is
+    // multiplied into the dequantized weights, the row statistics are computed next to the main loop and applied to
+    // the accumulator:  y = rstd * (acc - mean * c1s[n]) + c2[n]   (see b200_woq_ln_fold_prepare)
+    const __half* fold_x; // [M, K] raw rows (same memory the activation tensor map points at)
+    const __half* fold_gamma;
+    const float* fold_c1s;
+    const float* fold_c2;
     float ln_eps;
     int M, N, K;
     int ldc;
@@ -86,11 +89,11 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t
 
 // bias / activation / residual with the reference's per-layer fp16 rounding (see epilogue_apply in common.cuh);
 // the residual value is passed in so callers can issue all residual loads before the dependent stores.
-__device__ __forceinline__ __half finish_output(float acc, const __half* bias, int activation, bool has_res, float res, int n)
+__device__ __forceinline__ __half finish_output(float acc, bool has_bias, float biasv, int activation, bool has_res, float res)
 {
     __half o = __float2half_rn(acc);
-    if (bias != nullptr)
-        o = __float2half_rn(__half2float(o) + __half2float(bias[n]));
+    if (has_bias)
+        o = __float2half_rn(__half2float(o) + biasv);
     if (activation == B200_ACT_GELU_ERF)
         o = __float2half_rn(gelu_erf(__half2float(o)));
     else if (activation == B200_ACT_GELU_TANH)
@@ -224,11 +227,11 @@ struct TcSmem
     static constexpr size_t ring = (size_t) SS * (kWTileBytes + XTileBytes);
     static constexpr size_t rbuf = (size_t) 128 * MT * sizeof(float); // cluster reduction inbox [S][MT][128/S]
     static_assert(AS <= SS, "the TMEM A ring is never deeper than the shared-memory ring");
-    static constexpr size_t bars = sizeof(uint64_t) * (3 * SS + AS + 2) + 16 + ((AS & 1) ? 8 : 0);
+    static constexpr size_t bars = (sizeof(uint64_t) * (3 * SS + AS + 2) + 16 + 15) & ~size_t(15); // keeps what follows 16-byte aligned
 
-    static constexpr size_t ln_bytes(int K)
+    static constexpr size_t ln_bytes(int K) // folded LayerNorm: gamma [K] fp16 + (mean, rstd) per row
     {
-        return (size_t) MT * K * 2 + (size_t) 2 * K * 2 + (size_t) MT * 2 * sizeof(float);
+        return (size_t) K * 2 + (size_t) MT * 2 * sizeof(float);
     }
 
     static constexpr size_t total(bool cluster, bool ln, int K)
@@ -238,7 +241,7 @@ struct TcSmem
 };
 
 template <int MT, int SS, int AS>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     woq_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const TcParams p)
 {
     using L = TcSmem<MT, SS, AS>;
@@ -268,10 +271,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint8_t* extra = reinterpret_cast<uint8_t*>(full) + L::bars;
     float* rbuf = reinterpret_cast<float*>(extra);                       // cluster mode: [S][MT][128/S]
     uint8_t* ln_base = extra + (p.cluster ? L::rbuf : 0);
-    __half* ln_x = reinterpret_cast<__half*>(ln_base);                   // fused LN: [MT][K] raw rows
-    __half* ln_g = ln_x + (size_t) MT * p.K;                             // [K]
-    __half* ln_b = ln_g + p.K;                                           // [K]
-    float* ln_stat = reinterpret_cast<float*>(ln_b + p.K);               // [MT][2] mean, rstd
+    __half* ln_g = reinterpret_cast<__half*>(ln_base);                   // folded LN: gamma of this split's k range
+    float* ln_stat = reinterpret_cast<float*>(ln_g + p.K);               // [MT][2] mean, rstd
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int kb_begin = (int) (((long long) split * p.kb_total) / p.splits);
     const int kb_end = (int) (((long long) (split + 1) * p.kb_total) / p.splits);
     const int nkb = kb_end - kb_begin;
-    const bool fused_ln = p.x_raw != nullptr;
+    const bool fold = p.fold_gamma != nullptr;
     if (threadIdx.x == 0)
         TC_STAMP(0);
 
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int s = 0; s < SS; ++s)
         {
             mbar_init(&full[s], 1);
-            mbar_init(&xfull[s], fused_ln ? kTcDequantWarps : 1);
+            mbar_init(&xfull[s], 1);
         }
         fence_mbar_init();
         fence_proxy_async_smem();
@@ -333,6 +334,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     __half sc = __float2half(0.f);
     if (warp < kTcDequantWarps && n < p.N)
         sc = __ldg(p.scales + n);
+    if (fold && warp < kTcDequantWarps)
+    {
+        // gamma never depends on the previous kernel: stage this split's slice before the dependency wait
+        const uint4* g4 = reinterpret_cast<const uint4*>(p.fold_gamma) + (size_t) kb_begin * 8;
+        for (int idx = threadIdx.x; idx < nkb * 8; idx += kDq)
+            reinterpret_cast<uint4*>(ln_g)[idx] = __ldg(g4 + idx);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -348,14 +356,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // ===== TMA producer (continued) =====
         if (elect_one_sync())
         {
-            if (!fused_ln)
+            grid_dep_wait();
+            for (int i = 0; i < pre; ++i)
             {
-                grid_dep_wait();
-                for (int i = 0; i < pre; ++i)
-                {
-                    mbar_arrive_expect_tx(&xfull[i], XTileBytes);
-                    tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[i]);
-                }
+                mbar_arrive_expect_tx(&xfull[i], XTileBytes);
+                tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[i]);
             }
             for (int i = pre; i < nkb; ++i)
             {
@@ -363,11 +368,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 mbar_wait(&stage_free[ss], ((i / SS) - 1) & 1);
                 mbar_arrive_expect_tx(&full[ss], kWTileBytes);
                 tma_load_2d(smW + ss * kWTileBytes, &tmW, (kb_begin + i) * 128, n_tile * 64, &full[ss]);
-                if (!fused_ln)
-                {
-                    mbar_arrive_expect_tx(&xfull[ss], XTileBytes);
-                    tma_load_2d(smX + ss * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[ss]);
-                }
+                mbar_arrive_expect_tx(&xfull[ss], XTileBytes);
+                tma_load_2d(smX + ss * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[ss]);
             }
         }
     }
@@ -411,123 +413,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const float scf = __half2float(sc); // per-column dequant scale, applied in the epilogue
         const uint32_t lane_field = (uint32_t) ((warp & 3) * 32) << 16;
 
-        if (fused_ln)
-        {
-            // stage the raw rows of this m-tile, gamma and beta in shared memory (coalesced, all loads in flight),
-            // then two-pass statistics per row (one warp per row) -- this runs while the weight tiles are in flight
-            grid_dep_wait(); // x_raw is the previous kernel's output
-            const int cpr = p.K >> 3; // 16-byte chunks per row
-            // the rows of an m-tile are contiguous in x_raw: chunk idx of the tile is chunk (m_tile*MT*cpr + idx) of x_raw;
-            // loads are issued in independent batches of 10 so one L2 round trip covers a whole batch
-            {
-                const uint4* src = reinterpret_cast<const uint4*>(p.x_raw) + (size_t) m_tile * MT * cpr;
-                const int valid = max(0, min(MT, p.M - m_tile * MT)) * cpr;
-                constexpr int LB = 10;
-                for (int base = 0; base < MT * cpr; base += LB * kDq)
-                {
-                    uint4 u[LB];
-#pragma unroll
-                    for (int j = 0; j < LB; ++j)
-                    {
-                        const int idx = base + j * kDq + tq;
-                        u[j] = (idx < valid) ? __ldg(src + idx) : make_uint4(0, 0, 0, 0);
-                    }
-#pragma unroll
-                    for (int j = 0; j < LB; ++j)
-                    {
-                        const int idx = base + j * kDq + tq;
-                        if (idx < MT * cpr)
-                            reinterpret_cast<uint4*>(ln_x)[idx] = u[j];
-                    }
-                }
-            }
-            for (int idx = tq; idx < 2 * cpr; idx += kDq)
-            {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(idx < cpr ? p.ln_gamma : p.ln_beta) + (idx < cpr ? idx : idx - cpr));
-                reinterpret_cast<uint4*>(ln_g)[idx] = u; // gamma then beta, contiguous
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
-            for (int rl = warp; rl < MT; rl += kTcDequantWarps)
-            {
-                const uint4* xr = reinterpret_cast<const uint4*>(ln_x + (size_t) rl * p.K);
-                float sum = 0.f;
-                for (int c = lane; c < cpr; c += 32)
-                {
-                    const uint4 u = xr[c];
-                    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                    {
-                        const float2 f = __half22float2(h[j]);
-                        sum += f.x + f.y;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1)
-                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                const float mean = sum / (float) p.K;
-                float sq = 0.f;
-                for (int c = lane; c < cpr; c += 32)
-                {
-                    const uint4 u = xr[c];
-                    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                    {
-                        const float2 f = __half22float2(h[j]);
-                        sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1)
-                    sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                if (lane == 0)
-                {
-                    ln_stat[2 * rl] = mean;
-                    ln_stat[2 * rl + 1] = rsqrtf(sq / (float) p.K + p.ln_eps);
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
-        }
-
-        // writes LN(x)[rows of this m-tile][64 k of block i] into the SW128 K-major B tile of stage i % SS
-        auto write_ln_tile = [&](int i)
-        {
-            const int ss = i % SS;
-            if (i >= SS)
-                mbar_wait(&stage_free[ss], ((i / SS) - 1) & 1);
-            for (int idx = tq; idx < MT * 8; idx += kDq)
-            {
-                const int rl = idx >> 3, c = idx & 7;
-                const int kcol = (kb_begin + i) * 64 + c * 8;
-                const uint4 u = *reinterpret_cast<const uint4*>(ln_x + (size_t) rl * p.K + kcol);
-                const uint4 g4 = *reinterpret_cast<const uint4*>(ln_g + kcol);
-                const uint4 b4 = *reinterpret_cast<const uint4*>(ln_b + kcol);
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
-                const __half2* gh = reinterpret_cast<const __half2*>(&g4);
-                const __half2* bh = reinterpret_cast<const __half2*>(&b4);
-                const float mean = ln_stat[2 * rl], rstd = ln_stat[2 * rl + 1];
-                uint4 o = make_uint4(0, 0, 0, 0);
-                if (m_tile * MT + rl < p.M)
-                {
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                    {
-                        const float2 f = __half22float2(h[j]);
-                        const float2 gf = __half22float2(gh[j]);
-                        const float2 bf = __half22float2(bh[j]);
-                        oh[j] = __floats2half2_rn((f.x - mean) * rstd * gf.x + bf.x, (f.y - mean) * rstd * gf.y + bf.y);
-                    }
-                }
-                *reinterpret_cast<uint4*>(smX + ss * XTileBytes + rl * 128 + ((c ^ (rl & 7)) << 4)) = o;
-            }
-            fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(&xfull[ss]);
-        };
-
         // this thread's 32 bytes of k-block i: chunks 2*kh and 2*kh+1 of its 64-byte column slice
         uint4 v[2];
         auto load_w = [&](int i)
@@ -542,10 +427,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
         if (nkb > 0)
         {
-            if (fused_ln)
-                write_ln_tile(0);
-            if (tq == 0)
-                TC_STAMP(13);
             load_w(0);
             if (tq == 0)
                 TC_STAMP(3);
@@ -568,6 +449,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     r[8 * c + 4 + w] = *reinterpret_cast<uint32_t*>(&hi);
                 }
             }
+            if (fold)
+            {
+                // r[idx] is the k pair kh*16 + idx of the block: scale it by the matching gamma pair (rounded to fp16
+                // exactly like b200_woq_ln_fold_prepare does when it sums the column)
+                const uint4* g4 = reinterpret_cast<const uint4*>(ln_g + i * 64 + kh * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    const uint4 g = g4[q];
+                    const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                    {
+                        const __half2 pr = __hmul2(*reinterpret_cast<const __half2*>(&r[4 * q + w]),
+                            *reinterpret_cast<const __half2*>(&gw[w]));
+                        r[4 * q + w] = *reinterpret_cast<const uint32_t*>(&pr);
+                    }
+                }
+            }
             if (i >= AS)
             {
                 // TMEM stage `as` was last read by the MMAs of block i - AS
@@ -578,11 +478,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             tc_st_x16(tmem_base + lane_field + as * 32 + kh * 16, r);
             // overlap the TMEM store with fetching the next block
             if (i + 1 < nkb)
-            {
-                if (fused_ln)
-                    write_ln_tile(i + 1);
                 load_w(i + 1);
-            }
             if (tq == 0 && i < 12)
                 TC_STAMP(16 + 4 * i + 0);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -596,16 +492,86 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 TC_STAMP(4);
         }
 
+        const int m_valid = min(MT, p.M - m_tile * MT);
+        if (fold)
+        {
+            // ---- LayerNorm statistics of the m-tile's rows, two-pass in registers, off the tensor-core critical path:
+            // the whole split is already dequantized into TMEM, this overlaps the activation TMA and the MMAs ----
+            grid_dep_wait(); // x is the previous kernel's output
+            const int cpr = p.K >> 3; // 16-byte chunks per row (<= 192: at most 6 per lane)
+            const float inv_k = 1.f / (float) p.K;
+            for (int rl0 = warp; rl0 < MT; rl0 += 2 * kTcDequantWarps)
+            {
+                uint4 u[2][6];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                {
+                    const int rl = rl0 + rr * kTcDequantWarps;
+                    const uint4* xr = reinterpret_cast<const uint4*>(p.fold_x + (size_t) (m_tile * MT + rl) * p.K);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+                    {
+                        const int c = lane + 32 * j;
+                        u[rr][j] = (rl < m_valid && c < cpr) ? __ldcg(xr + c) : make_uint4(0, 0, 0, 0);
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                {
+                    const int rl = rl0 + rr * kTcDequantWarps;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+                    {
+                        const __half2* h = reinterpret_cast<const __half2*>(&u[rr][j]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                        {
+                            const float2 f = __half22float2(h[q]);
+                            sum += f.x + f.y;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1)
+                        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    const float mean = sum * inv_k;
+                    float sq = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+                    {
+                        if (lane + 32 * j < cpr)
+                        {
+                            const __half2* h = reinterpret_cast<const __half2*>(&u[rr][j]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                            {
+                                const float2 f = __half22float2(h[q]);
+                                sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1)
+                        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (lane == 0 && rl < MT)
+                    {
+                        ln_stat[2 * rl] = mean;
+                        ln_stat[2 * rl + 1] = rsqrtf(sq * inv_k + p.ln_eps);
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
+        }
+        // y = rstd * (acc - mean * c1s) + c2 when the LayerNorm is folded, acc otherwise
+        auto ln_apply = [&](float acc, int ml, float c1v, float c2v) -> float
+        { return fold ? ln_stat[2 * ml + 1] * (acc - ln_stat[2 * ml] * c1v) + c2v : acc; };
+
         // ---- epilogue: thread (T, kh) owns accumulator row T, columns [kh*MT/2, (kh+1)*MT/2) ----
-        mbar_wait(acc_done, 0);
-        tc_fence_after();
-        if (tq == 0)
-            TC_STAMP(7);
         const int n_tiles = gridDim.x, m_tiles = gridDim.y;
         const int tile_id = m_tile * n_tiles + n_tile;
         const bool direct = (p.splits == 1);
         const bool has_res = p.residual != nullptr;
-        const int m_valid = min(MT, p.M - m_tile * MT);
+        const bool has_bias = p.bias != nullptr;
         const size_t slab_elems = (size_t) 128 * MT;
         float* slab = (direct || p.cluster)
             ? nullptr
@@ -614,6 +580,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const uint32_t S = (uint32_t) p.splits;
         const int nslice = 128 / (int) S;
         uint32_t push_addr = 0, push_bar = 0;
+        // operands of the final outputs this thread will write, requested before the accumulator is waited for
+        float own_bias = 0.f, own_c1 = 0.f, own_c2 = 0.f, own_res = 0.f;
+        int own_ml = 0, own_nn = 0;
+        bool own_valid = false;
         if (p.cluster)
         {
             const uint32_t owner = (uint32_t) (T / nslice);
@@ -621,7 +591,32 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // inbox layout [sender rank][ml][nl]
             push_addr = mapa_u32(smem_u32(rbuf + ((size_t) rank * MT) * nslice + (T % nslice)), owner);
             push_bar = mapa_u32(smem_u32(red_bar), owner);
+            // first (usually only) element of this rank's column slice reduced by this thread
+            own_ml = tq / nslice;
+            own_nn = n_tile * 128 + (int) rank * nslice + (tq - own_ml * nslice);
+            own_valid = tq < nslice * m_valid && own_nn < p.N;
         }
+        else
+        {
+            own_nn = n;
+            own_valid = n < p.N;
+        }
+        if (own_valid)
+        {
+            if (has_bias)
+                own_bias = __half2float(__ldg(p.bias + own_nn));
+            if (fold)
+            {
+                own_c1 = __ldg(p.fold_c1s + own_nn);
+                own_c2 = __ldg(p.fold_c2 + own_nn);
+            }
+            if (p.cluster && has_res)
+                own_res = __half2float(p.residual[(size_t) (m_tile * MT + own_ml) * p.ldc + own_nn]);
+        }
+        mbar_wait(acc_done, 0);
+        tc_fence_after();
+        if (tq == 0)
+            TC_STAMP(7);
 #pragma unroll 1
         for (int c8 = 0; c8 < kHalfCols / 8; ++c8)
         {
@@ -641,7 +636,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int i = 0; i < 8; ++i)
                     if (ml0 + i < m_valid && n < p.N)
                         p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
-                            = finish_output(__uint_as_float(acc[i]) * scf, p.bias, p.activation, has_res, res[i], n);
+                            = finish_output(ln_apply(__uint_as_float(acc[i]) * scf, ml0 + i, own_c1, own_c2), has_bias,
+                                own_bias, p.activation, has_res, res[i]);
             }
             else if (p.cluster)
             {
@@ -673,16 +669,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int ml = e / nslice;
                 const int nl = e - ml * nslice;
                 const int nn = n_tile * 128 + n_lo + nl;
+                if (nn >= p.N)
+                    continue;
                 const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + nn;
-                const float res = (has_res && nn < p.N) ? __half2float(p.residual[idx]) : 0.f;
+                float res = own_res, bv = own_bias, c1v = own_c1, c2v = own_c2;
+                if (e != tq)
+                {
+                    res = has_res ? __half2float(p.residual[idx]) : 0.f;
+                    bv = has_bias ? __half2float(__ldg(p.bias + nn)) : 0.f;
+                    c1v = fold ? __ldg(p.fold_c1s + nn) : 0.f;
+                    c2v = fold ? __ldg(p.fold_c2 + nn) : 0.f;
+                }
                 const float* src = rbuf + (size_t) ml * nslice + nl;
                 float sum = 0.f;
 #pragma unroll
                 for (uint32_t q = 0; q < 8; ++q)
                     if (q < S)
                         sum += src[(size_t) q * MT * nslice];
-                if (nn < p.N)
-                    p.C[idx] = finish_output(sum, p.bias, p.activation, has_res, res, nn);
+                p.C[idx] = finish_output(ln_apply(sum, ml, c1v, c2v), has_bias, bv, p.activation, has_res, res);
             }
             if (tq == 0)
                 TC_STAMP(10);
@@ -753,7 +757,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         for (int i = 0; i < 8; ++i)
                             if (ml0 + i < m_valid)
                                 p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
-                                    = finish_output(sum[i], p.bias, p.activation, has_res, res[i], n);
+                                    = finish_output(ln_apply(sum[i], ml0 + i, own_c1, own_c2), has_bias, own_bias,
+                                        p.activation, has_res, res[i]);
                     }
                 }
                 if (tq == 0)
@@ -1050,12 +1055,14 @@ template <int MT, int SS, int AS>
 static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcParams& p, dim3 grid, cudaStream_t stream)
 {
     auto kern = woq_gemm_tc_kernel<MT, SS, AS>;
-    const size_t smem = TcSmem<MT, SS, AS>::total(p.cluster != 0, p.x_raw != nullptr, p.K);
+    const size_t smem = TcSmem<MT, SS, AS>::total(p.cluster != 0, p.fold_gamma != nullptr, p.K);
     B200_REQUIRE(smem <= 227 * 1024, B200_ERR_UNSUPPORTED, "woq gemm: %zu bytes of shared memory needed", smem);
     static size_t attr_smem = 0;
     if (smem > attr_smem)
     {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        // decode tiles are sized so that two CTAs (this GEMM's and the next one's, launched early) share an SM
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_smem = smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -1086,18 +1093,18 @@ static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcPar
     return B200_OK;
 }
 
-// Can LayerNorm be folded into the GEMM for this shape?  (the raw rows of one m-tile are staged in shared memory)
-bool woq_tc_can_fuse_ln(int M, int K)
+// Can LayerNorm be folded into the GEMM for this shape?  (decode-sized m-tiles whose rows fit the statistics warps'
+// registers: 6 x 16-byte chunks per lane)
+bool woq_tc_can_fold_ln(int M, int K)
 {
-    if (M > 32)
-        return false;
-    return M <= 16 ? TcSmem<16, 10, 10>::total(true, true, K) <= 200 * 1024 : TcSmem<32, 8, 8>::total(true, true, K) <= 200 * 1024;
+    return M <= 32 && K <= 1536;
 }
 
-// tcgen05 path entry: any M >= 1.  ln_gamma != nullptr: A is the raw residual stream and LayerNorm(A) is the operand.
+// tcgen05 path entry: any M >= 1.  fold_gamma != nullptr: A is the raw residual stream and the LayerNorm is folded
+// into the kernel (see TcParams).
 int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
     int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-    const __half* ln_gamma, const __half* ln_beta, float ln_eps)
+    const __half* fold_gamma, const float* fold_c1s, const float* fold_c2, float ln_eps)
 {
     const TcPlan pl = plan_tc(M, N, K);
     B200_REQUIRE(pl.slab_bytes == 0 || (workspace != nullptr && workspace_bytes >= pl.slab_bytes), B200_ERR_WORKSPACE,
@@ -1123,11 +1130,12 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     p.C = C;
     p.slabs = static_cast<float*>(workspace);
     p.counters = tc_counter_slot(pl.m_tiles * pl.n_tiles <= kCounterSlotInts ? pl.m_tiles * pl.n_tiles : 1);
-    if (ln_gamma != nullptr)
+    if (fold_gamma != nullptr)
     {
-        p.x_raw = A;
-        p.ln_gamma = ln_gamma;
-        p.ln_beta = ln_beta;
+        p.fold_x = A;
+        p.fold_gamma = fold_gamma;
+        p.fold_c1s = fold_c1s;
+        p.fold_c2 = fold_c2;
         p.ln_eps = ln_eps;
     }
     p.M = M;
@@ -1142,8 +1150,8 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     switch (pl.MT)
     {
-    case 16: return launch_tc<16, 10, 10>(tmW, tmX, p, grid, stream);
-    case 32: return launch_tc<32, 8, 8>(tmW, tmX, p, grid, stream);
+    case 16: return launch_tc<16, 10, 6>(tmW, tmX, p, grid, stream);
+    case 32: return launch_tc<32, 7, 6>(tmW, tmX, p, grid, stream);
     case 64: return launch_tc<64, 6, 6>(tmW, tmX, p, grid, stream);
     case 128: return launch_tc<128, 4, 4>(tmW, tmX, p, grid, stream);
     default: return launch_tc<256, 4, 4>(tmW, tmX, p, grid, stream);

@@ -31,6 +31,16 @@ class _QLinear:
         self.k, self.n = w_kn.shape
         self.weight, self.scales = ops.symmetric_quantize_last_axis_of_batched_matrix(w_kn, torch.int8)
         self.bias = None if bias is None else bias.detach().to(device=device, dtype=torch.float16).contiguous()
+        self.c1s = self.c2 = None
+
+    def fold_layernorm(self, lib, gamma, beta, stream):
+        """Per-column vectors that let the LayerNorm in front of this Linear be folded into the GEMM kernel
+        (b200_woq_ln_fold_prepare)."""
+        self.c1s = torch.empty((self.n,), dtype=torch.float32, device=self.weight.device)
+        self.c2 = torch.empty_like(self.c1s)
+        _lib.check(lib.b200_woq_ln_fold_prepare(self.weight.data_ptr(), self.scales.data_ptr(), gamma.data_ptr(),
+                                                beta.data_ptr(), self.k, self.n, self.c1s.data_ptr(), self.c2.data_ptr(),
+                                                stream), "ln_fold_prepare")
 
 
 def _cat_qkv(sd, p, device):
@@ -92,6 +102,13 @@ class WhisperDecoding:
                 "ckv_qo": torch.tensor([cross_kv_scales[i]], dtype=torch.float32, device=dev),
             }
             self.layers.append(lay)
+        # LayerNorm -> Linear pairs run as ONE kernel (B200_FUSE_LN=0: separate LayerNorm launch, for A/B timing)
+        self.fuse_ln = os.environ.get("B200_FUSE_LN", "1") != "0"
+        if self.fuse_ln:
+            st0 = torch.cuda.current_stream(dev).cuda_stream
+            for lay in self.layers:
+                for ln, lin in (("attn_ln", "qkv"), ("cross_ln", "cross_q"), ("mlp_ln", "fc1")):
+                    lay[lin].fold_layernorm(self.lib, lay[ln][0], lay[ln][1], st0)
 
         B, d = self.B, self.d
         self.self_kv = [torch.zeros((B, 2, self.H, self.Smax, self.Dh), dtype=torch.int8, device=dev)
@@ -109,7 +126,6 @@ class WhisperDecoding:
         self.graph = None
         # side stream that pulls the next layer's cross-KV cache into L2 while the current layer's small kernels run
         self.prefetch_cross_kv = os.environ.get("B200_XKV_PREFETCH", "0") != "0"
-        self.fuse_ln = os.environ.get("B200_FUSE_LN", "0") != "0"
         self._side = torch.cuda.Stream(device=dev) if torch.cuda.is_available() else None
         self._pinned_in = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
         self._pinned_out = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
@@ -127,12 +143,13 @@ class WhisperDecoding:
         _lib.check(rc, "woq gemm")
 
     def _gemm_ln(self, x, wb, rows, lin, out, act=_lib.ACT_NONE):
-        """out = act(LayerNorm(x; wb) @ W + bias): the LayerNorm is folded into the GEMM kernel's operand path."""
-        rc = self.lib.b200_woq_int8_gemm_ln_fused(
-            x.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), 1e-5, rows, lin.k, lin.weight.data_ptr(),
-            lin.scales.data_ptr(), lin.n, lin.bias.data_ptr() if lin.bias is not None else None, act, None,
-            out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self._st())
-        _lib.check(rc, "woq gemm (fused LayerNorm)")
+        """out = act(LayerNorm(x; wb) @ W + bias) with the LayerNorm folded into the GEMM kernel (decode-sized row
+        counts; larger ones take the two-launch route inside the same entry point)."""
+        rc = self.lib.b200_woq_int8_gemm_ln_folded(
+            x.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), lin.c1s.data_ptr(), lin.c2.data_ptr(), 1e-5, rows, lin.k,
+            lin.weight.data_ptr(), lin.scales.data_ptr(), lin.n, lin.bias.data_ptr() if lin.bias is not None else None,
+            act, None, out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self._st())
+        _lib.check(rc, "woq gemm (folded LayerNorm)")
 
     def _ln(self, x, wb, out, rows):
         _lib.check(self.lib.b200_layernorm_fp16(x.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), out.data_ptr(), rows,

@@ -109,13 +109,27 @@ int b200_woq_int8_gemm(const void* A, int M, int K, const int8_t* Wproc, const v
 int b200_woq_int8_gemm_fused(const void* A, int M, int K, const int8_t* Wproc, const void* scales, int N,
     const void* bias, int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes,
     b200_stream_t stream);
-/* LayerNorm folded into the matmul: C = epilogue( LN(X; gamma, beta, eps) x W ).  X [M, K] fp16 is the raw residual
- * stream; the normalised activations (rounded to fp16 exactly like b200_layernorm_fp16) are produced inside the GEMM
- * kernel while the first weight tiles are in flight, saving the separate LayerNorm launch of the reference graph
- * (T/tensorrt_llm/models/whisper/model.py:86-118).  With M <= 4 (SIMT path) the workspace must hold M*K fp16. */
+/* LayerNorm + matmul in one call: C = epilogue( LN(X; gamma, beta, eps) x W ), X [M, K] fp16 the raw residual stream
+ * (the LayerNorm -> Linear pairs of T/tensorrt_llm/models/whisper/model.py:86-118).  This entry normalises into the
+ * workspace (which must hold M*K fp16 on top of the split-K needs) and then runs the matmul: two launches. */
 int b200_woq_int8_gemm_ln_fused(const void* X, const void* ln_gamma, const void* ln_beta, float ln_eps, int M, int K,
     const int8_t* Wproc, const void* scales, int N, const void* bias, int activation, const void* residual, void* C,
     void* workspace, size_t workspace_bytes, b200_stream_t stream);
+/* The same operation with the LayerNorm FOLDED into the tcgen05 kernel (decode-sized M <= 32, K <= 1536; other shapes
+ * take the two-launch route above).  Algebra:
+ *     LN(x)[k] = (x[k] - mean) * rstd * gamma[k] + beta[k]
+ *     y[n]     = rstd * ( sum_k x[k] * W'[k][n]  -  mean * c1[n] ) * scale[n]  +  c2[n]
+ * with W'[k][n] = fp16(Wint[k][n] * gamma[k]) formed by the dequant warps (one extra HMUL2 per k pair),
+ * c1[n] = sum_k W'[k][n] and c2[n] = scale[n] * sum_k beta[k] * Wint[k][n].  The tensor cores therefore consume the
+ * RAW rows of x straight from TMA, and (mean, rstd) are only needed in the epilogue: they are computed by the idle
+ * dequant warps while the activation tiles and MMAs are in flight, so no LayerNorm work sits on the critical path.
+ * b200_woq_ln_fold_prepare fills c1s[n] = scale[n] * c1[n] and c2[n] (fp32 [N] each) once per (layer norm, weight)
+ * pair, walking the preprocessed layout with the same arithmetic as the kernel so the mean term cancels exactly. */
+int b200_woq_ln_fold_prepare(const int8_t* Wproc, const void* scales, const void* ln_gamma, const void* ln_beta, int K,
+    int N, float* c1s, float* c2, b200_stream_t stream);
+int b200_woq_int8_gemm_ln_folded(const void* X, const void* ln_gamma, const void* ln_beta, const float* c1s,
+    const float* c2, float ln_eps, int M, int K, const int8_t* Wproc, const void* scales, int N, const void* bias,
+    int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes, b200_stream_t stream);
 /* Forces a kernel family for tests/benchmarks: 0 = auto, 1 = SIMT GEMV, 2 = tcgen05 GEMM. */
 int b200_woq_set_kernel_policy(int policy);
 /* Debug aid: device buffer of >= 16 int64 receiving clock64() stamps of CTA (0,0,0) of each following tcgen05 GEMM

@@ -200,6 +200,52 @@ def test_layernorm_fused_gemm(policy, m, k, n):
     assert (out.cpu().float() - ref.float()).abs().max().item() <= 2e-3 * ref.float().abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize("m,k,n,res", [(16, 1280, 3840, False), (16, 1280, 5120, False), (16, 1280, 1280, True),
+                                       (5, 384, 1152, False), (32, 1280, 1280, False), (9, 1536, 256, True), (9, 2048, 256, True),
+                                       (48, 1280, 1280, False), (3, 1280, 1280, False)])
+def test_layernorm_folded_gemm(m, k, n, res):
+    """b200_woq_int8_gemm_ln_folded (LayerNorm folded into the tcgen05 kernel: gamma in the dequant, statistics in the
+    epilogue) against LayerNorm -> reference-order GEMM.  x has a large per-row offset so a mean term that does not
+    cancel would show.  M = 48 and M = 3 take the two-launch fallback of the same entry point."""
+    import b200_whisper as bw
+    from b200_whisper import _lib
+    from b200_whisper.functional import layer_norm
+    lib = _lib.load()
+    torch.manual_seed(m + n + k)
+    x = (torch.randn((m, k)) * 2 + 3.0 * torch.randn((m, 1))).half().cuda()
+    gamma = (1 + 0.2 * torch.randn(k)).half().cuda()
+    beta = (0.2 * torch.randn(k)).half().cuda()
+    weight = gen((k, n), seed=21) * 0.05
+    bias = gen((n,), seed=22).cuda()
+    residual = gen((m, n), seed=23).cuda() if res else None
+    raw, proc, scales = bw.ops._symmetric_quantize_last_axis_of_batched_matrix(weight.cuda(), torch.int8)
+    c1s = torch.empty((n,), dtype=torch.float32, device="cuda")
+    c2 = torch.empty((n,), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.b200_woq_ln_fold_prepare(proc.data_ptr(), scales.data_ptr(), gamma.data_ptr(), beta.data_ptr(), k, n,
+                                            c1s.data_ptr(), c2.data_ptr(), st), "ln fold prepare")
+    # the prepared vectors against their definition, from the raw (unprocessed) int8 weights
+    wg = (raw.float() * gamma.float()[:, None]).half().float()
+    exp_c1 = wg.sum(0) * scales.float()
+    exp_c2 = (raw.float() * beta.float()[:, None]).sum(0) * scales.float()
+    assert (c1s - exp_c1).abs().max().item() <= 1e-4 * exp_c1.abs().max().item() + 1e-5
+    assert (c2 - exp_c2).abs().max().item() <= 1e-4 * exp_c2.abs().max().item() + 1e-5
+    h = layer_norm(x, (k,), gamma, beta, 1e-5)
+    ref = run_plugin(h.cpu(), proc.cpu(), scales.cpu(), "tc", bias=bias)
+    if res:
+        ref = (ref.float() + residual.cpu().float()).half()
+    out = torch.empty((m, n), dtype=torch.float16, device="cuda")
+    ws = torch.empty((lib.b200_woq_workspace_bytes(m, n, k) + m * k * 2,), dtype=torch.uint8, device="cuda")
+    rc = lib.b200_woq_int8_gemm_ln_folded(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), c1s.data_ptr(), c2.data_ptr(),
+                                          1e-5, m, k, proc.data_ptr(), scales.data_ptr(), n, bias.data_ptr(),
+                                          _lib.ACT_NONE, residual.data_ptr() if res else None, out.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), st)
+    _lib.check(rc, "ln folded gemm")
+    torch.cuda.synchronize()
+    # tolerance: fp16 rounding of LN(x) (reference order) vs fp16 rounding of Wint*gamma (folded order)
+    assert (out.cpu().float() - ref.float()).abs().max().item() <= 3e-3 * ref.float().abs().max().item() + 2e-3
+
+
 @pytest.mark.parametrize("mode", ["cluster", "global"])
 def test_splitk_modes_agree(mode, monkeypatch):
     """Cluster (DSMEM) and global-slab split-K reductions are both deterministic and agree to fp32 rounding."""
