@@ -1000,10 +1000,12 @@ TcPlan plan_tc(int M, int N, int K)
     {
         if (g_splitk_mode == 1 && pl.MT <= 64)
         {
-            // cluster split-K: power-of-two cluster (<= 8, portable) along z, at least two k-blocks per CTA
-            // at most one CTA per SM: a second resident CTA starts late and stretches the tail
+            // cluster split-K: power-of-two cluster (<= 8, portable) along z, at least two k-blocks per CTA.
+            // Decode tiles (MT <= 32) fit two CTAs per SM, so a grid may exceed the SM count a little; it must still
+            // leave most second slots free for the NEXT kernel's early (programmatic) launch.
+            const int cap = pl.MT <= 32 ? sms + sms / 8 : sms;
             int s2 = 8;
-            while (s2 > 1 && (tiles * s2 > sms || kb_total < 2 * s2))
+            while (s2 > 1 && (tiles * s2 > cap || kb_total < 2 * s2))
                 s2 >>= 1;
             splits = s2;
             cluster = s2 > 1 ? 1 : 0;
