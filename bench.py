@@ -290,62 +290,119 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.item())
 
-    # ---- roofline of the dominant kernel (cross-attention: 68 % of the step's bytes at batch 16) -------
-    from b200_whisper import _lib as L_
-    q = torch.randn((B, dims.n_text_state), device=dev).half()
-    out = torch.empty_like(q)
-    reps = 3
-    def xattn(i):
-        lay = dec.layers[i % L]
-        L_.check(lib.b200_cross_attention(q.data_ptr(), dec.cross_kv[i % L].data_ptr(), lay["ckv_qo"].data_ptr(),
-                                          out.data_ptr(), B, 1, dims.n_text_head, 64, dims.n_audio_ctx, 1,
-                                          dec.ws.data_ptr(), dec.ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
-    for i in range(L):
-        xattn(i)
-    torch.cuda.synchronize(dev)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for r in range(reps):
-        for i in range(L):  # 32 different caches (1.97 GB) per sweep: every launch misses L2
-            xattn(i)
-    k1.record()
-    torch.cuda.synchronize(dev)
-    xa_ms = k0.elapsed_time(k1) / (reps * L)
-    xa_bytes = 2 * dims.n_text_head * 64 * dims.n_audio_ctx * B  # SURVEY 8d: 3.84 MB per sequence per call
+    # ---- rooflines, measured live with CUDA events around CUDA-graph replays (no host launch cost inside) ---------
+    # The dominant kernel BY TIME is the tcgen05 weight-only GEMM (192 launches per step, ~60 % of the step in
+    # profiles/r01_launches_*.txt); the dominant kernel BY BYTES is the cross-attention (68 % of the step's bytes).
+    # Both get a roofline entry; `roofline` is the GEMM family, `roofline_cross_attention` the attention kernel.
     peak, peak_src = measured_peak()
-    achieved = xa_bytes / (xa_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "cross_attention_kernel<int8> (+merge)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": xa_bytes, "avg_launch_ms": xa_ms}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f)
+    cur = torch.cuda.current_stream(dev)
 
-    # ---- per-GEMM numbers for the "GEMV HBM GB/s" half of the metric ------------------------------------
+    def graph_ms(body, reps=5):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            body()  # warm-up outside capture
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            body()
+        gr.replay()
+        torch.cuda.synchronize(dev)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            gr.replay()
+        k1.record()
+        torch.cuda.synchronize(dev)
+        return k0.elapsed_time(k1) / reps
+
+    d = dims.n_text_state
+    xs = torch.randn((B, d), device=dev).half()
+    x2 = xs.clone()
+    qkv_o = torch.empty((B, 3 * d), device=dev).half()
+    q_o = torch.empty((B, d), device=dev).half()
+    u_o = torch.empty((B, 4 * d), device=dev).half()
+    ctx_i = torch.randn((B, d), device=dev).half()
+    lib.b200_set_static_kv_hint(1)
+
+    def gemm_family():
+        # the six GEMM launches of every layer exactly as the decoder step issues them (folded LayerNorm, bias,
+        # GELU, residual); 32 layers of distinct weights = 629 MB per sweep, far beyond L2
+        for lay in dec.layers:
+            if dec.fuse_ln:
+                dec._gemm_ln(xs, lay["attn_ln"], B, lay["qkv"], qkv_o)
+            else:
+                dec._gemm(xs, B, lay["qkv"], qkv_o)
+            dec._gemm(ctx_i, B, lay["attn_out"], x2, residual=x2)
+            if dec.fuse_ln:
+                dec._gemm_ln(x2, lay["cross_ln"], B, lay["cross_q"], q_o)
+            else:
+                dec._gemm(x2, B, lay["cross_q"], q_o)
+            dec._gemm(ctx_i, B, lay["cross_out"], x2, residual=x2)
+            if dec.fuse_ln:
+                dec._gemm_ln(x2, lay["mlp_ln"], B, lay["fc1"], u_o, act=L_.ACT_GELU_ERF)
+            else:
+                dec._gemm(x2, B, lay["fc1"], u_o, act=L_.ACT_GELU_ERF)
+            dec._gemm(u_o, B, lay["fc2"], x2, residual=x2)
+
+    from b200_whisper import _lib as L_
+    n_gemm = 6 * L
+    gemm_ms = graph_ms(gemm_family) / n_gemm
+
+    def gemm_bytes(lin):  # int8 weights + fp16 scales, activations in and out
+        return lin.k * lin.n + 2 * lin.n + 2 * B * lin.k + 2 * B * lin.n
+    lay0 = dec.layers[0]
+    gemm_b = sum(gemm_bytes(lay0[nm]) for nm in ("qkv", "attn_out", "cross_q", "cross_out", "fc1", "fc2")) / 6.0
+    gemm_ach = gemm_b / (gemm_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "woq_gemm_tc_kernel<16,10,6> (6 launches per layer: qkv, attn_out, cross_q, "
+                "cross_out, fc1, fc2; LayerNorm folded in 3 of them)", "achieved": gemm_ach, "peak": peak,
+                "unit": "GB/s", "frac": gemm_ach / peak, "traffic": traffic.get("woq_gemm_tc_kernel"),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": gemm_b, "avg_launch_ms": gemm_ms,
+                "launches_timed": n_gemm, "timing": "CUDA events around graph replays of the 192 launches, PDL on"}
+
+    q = torch.randn((B, d), device=dev).half()
+    out = torch.empty_like(q)
+
+    def xattn_family():
+        for i in range(L):  # 32 different caches (1.97 GB) per sweep: every launch misses L2
+            lay = dec.layers[i]
+            L_.check(lib.b200_cross_attention(q.data_ptr(), dec.cross_kv[i].data_ptr(), lay["ckv_qo"].data_ptr(),
+                                              out.data_ptr(), B, 1, dims.n_text_head, 64, dims.n_audio_ctx, 1,
+                                              dec.ws.data_ptr(), dec.ws.numel(),
+                                              torch.cuda.current_stream(dev).cuda_stream))
+    xa_ms = graph_ms(xattn_family) / L
+    xa_bytes = 2 * dims.n_text_head * 64 * dims.n_audio_ctx * B  # SURVEY 8d: 3.84 MB per sequence per call
+    xa_ach = xa_bytes / (xa_ms / 1e3) / 1e9
+    roofline_xa = {"bound": "hbm", "kernel": "cross_attention_rowhead_kernel<int8>", "achieved": xa_ach, "peak": peak,
+                   "unit": "GB/s", "frac": xa_ach / peak, "traffic": traffic.get("cross_attention_rowhead_kernel"),
+                   "algorithmic_bytes_per_launch": xa_bytes, "avg_launch_ms": xa_ms}
+
+    # ---- per-shape GEMM numbers for the "GEMV HBM GB/s" half of the metric ------------------------------------
     gemm_stats = {}
     x16 = torch.randn((B, 5120), device=dev).half()
     o16 = torch.empty((B, 5120), device=dev).half()
     for name in ("qkv", "attn_out", "fc1", "fc2"):
         lins = [lay[name] for lay in dec.layers]
-        def run(i):
-            lin = lins[i % L]
-            L_.check(lib.b200_woq_int8_gemm(x16.data_ptr(), B, lin.k, lin.weight.data_ptr(), lin.scales.data_ptr(), lin.n,
-                                            o16.data_ptr(), dec.ws.data_ptr(), dec.ws.numel(),
-                                            torch.cuda.current_stream(dev).cuda_stream))
-        for i in range(L):
-            run(i)
-        torch.cuda.synchronize(dev)
-        k0.record()
-        for r in range(reps):
-            for i in range(L):
-                run(i)
-        k1.record()
-        torch.cuda.synchronize(dev)
-        gms = k0.elapsed_time(k1) / (reps * L)
+
+        def sweep():
+            for lin in lins:
+                L_.check(lib.b200_woq_int8_gemm(x16.data_ptr(), B, lin.k, lin.weight.data_ptr(), lin.scales.data_ptr(),
+                                                lin.n, o16.data_ptr(), dec.ws.data_ptr(), dec.ws.numel(),
+                                                torch.cuda.current_stream(dev).cuda_stream))
+        gms = graph_ms(sweep) / L
         lin = lins[0]
-        gbytes = lin.k * lin.n + 2 * lin.n + 2 * B * lin.k + 2 * B * lin.n
+        gbytes = gemm_bytes(lin)
         gemm_stats[f"{name}_{lin.k}x{lin.n}_m{B}"] = {"avg_launch_us": 1e3 * gms, "GB/s": gbytes / (gms / 1e3) / 1e9,
                                                      "frac_of_peak": gbytes / (gms / 1e3) / 1e9 / peak}
+    lib.b200_set_static_kv_hint(0)
 
     # algorithmic bytes of one whole step, for the step-level roofline fraction
-    d = dims.n_text_state
     t_mid = len(PROMPT) + args.warmup + args.steps // 2
     step_bytes = L * (12 * d * d) + L * 2 * (3 * d + 3 * d + 4 * d + 2 * d) + dims.n_vocab * d * 2 \
         + B * L * 2 * d * dims.n_audio_ctx + B * L * 2 * d * t_mid
@@ -373,6 +430,7 @@ def main():
             "gpu_launches": int((launches_per_step or 0) * args.steps if launches_per_step else eager_launches),
             "launches_per_step": launches_per_step,
             "roofline": roofline,
+            "roofline_cross_attention": roofline_xa,
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_peak": step_frac},
             "kernels": gemm_stats,
         }

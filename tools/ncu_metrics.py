@@ -22,12 +22,19 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio']
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr, units = rows[0], rows[1]
-for r in rows[2:]:
-    print("==", r[hdr.index('Kernel Name')][:80], r[hdr.index('Grid Size')] if 'Grid Size' in hdr else "")
-    for k in KEYS:
-        if k in hdr:
-            print(f"   {k:85s} {r[hdr.index(k)]:>14s} {units[hdr.index(k)]}")
-    break
+def main():
+    out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    every = "--all" in sys.argv
+    for r in rows[2:]:
+        print("==", r[hdr.index('Kernel Name')][:80], r[hdr.index('Grid Size')] if 'Grid Size' in hdr else "")
+        for k in KEYS:
+            if k in hdr:
+                print(f"   {k:85s} {r[hdr.index(k)]:>14s} {units[hdr.index(k)]}")
+        if not every:
+            break
+
+
+if __name__ == "__main__":
+    main()
