@@ -15,7 +15,8 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
 size_t woq_tc_workspace_bytes(int max_m, int N, int K);
 int tc_init();
 void tc_set_debug_buffer(long long* p);
-bool woq_tc_can_fold_ln(int M, int K);
+void tc_set_debug_filter(int n, int fold);
+bool woq_tc_can_fold_ln(int M, int N, int K);
 
 static int g_policy = 0; // 0 auto, 1 simt, 2 tcgen05
 
@@ -91,7 +92,7 @@ static int woq_dispatch(const void* A, int M, int K, const int8_t* Wproc, const 
         return B200_OK; // empty batch: nothing to do (the reference would launch an empty grid)
     B200_REQUIRE_DEVICE();
     const bool simt = (g_policy == 1) || (g_policy == 0 && M <= 4);
-    const bool fold = ln_gamma != nullptr && fold_c1s != nullptr && fold_c2 != nullptr && !simt && woq_tc_can_fold_ln(M, K);
+    const bool fold = ln_gamma != nullptr && fold_c1s != nullptr && fold_c2 != nullptr && !simt && woq_tc_can_fold_ln(M, N, K);
     if (!fold)
     {
         const __half* a = static_cast<const __half*>(A);
@@ -181,6 +182,12 @@ extern "C" int b200_init(void)
 
 // Debug aid: device buffer of >= 16 int64 that receives clock64() stamps of CTA (0,0,0) of every following tcgen05
 // GEMM launch (phase boundaries, see TC_STAMP in woq_gemm_tc.cu); NULL switches it off.
+extern "C" int b200_debug_tc_timing_filter(int n, int folded_ln)
+{
+    tc_set_debug_filter(n, folded_ln);
+    return B200_OK;
+}
+
 extern "C" int b200_debug_tc_timing(void* device_buffer)
 {
     tc_set_debug_buffer(static_cast<long long*>(device_buffer));

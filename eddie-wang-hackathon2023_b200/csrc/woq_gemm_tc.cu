@@ -229,9 +229,9 @@ struct TcSmem
     static_assert(AS <= SS, "the TMEM A ring is never deeper than the shared-memory ring");
     static constexpr size_t bars = (sizeof(uint64_t) * (3 * SS + AS + 2) + 16 + 15) & ~size_t(15); // keeps what follows 16-byte aligned
 
-    static constexpr size_t ln_bytes(int K) // folded LayerNorm: gamma [K] fp16 + (mean, rstd) per row
+    static constexpr size_t ln_bytes(int K) // folded LayerNorm: gamma [K] fp16 + (mean, M2) per sender rank and row
     {
-        return (size_t) K * 2 + (size_t) MT * 2 * sizeof(float);
+        return (size_t) K * 2 + (size_t) 9 * MT * 2 * sizeof(float);
     }
 
     static constexpr size_t total(bool cluster, bool ln, int K)
@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     float* rbuf = reinterpret_cast<float*>(extra);                       // cluster mode: [S][MT][128/S]
     uint8_t* ln_base = extra + (p.cluster ? L::rbuf : 0);
     __half* ln_g = reinterpret_cast<__half*>(ln_base);                   // folded LN: gamma of this split's k range
-    float* ln_stat = reinterpret_cast<float*>(ln_g + p.K);               // [MT][2] mean, rstd
+    float* ln_part = reinterpret_cast<float*>(ln_g + p.K);               // [sender rank <= 8][MT][2] partial mean, M2
+    float* ln_fin = ln_part + 8 * MT * 2;                                // [MT][2] merged mean, rstd
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -287,8 +288,13 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     // ---- prologue.  The producer thread owns the `full` barriers: it initialises them and immediately starts the
     // weight stream (weights never depend on the previous kernel), while the other warps set up the rest. ----
     const int pre = nkb < SS ? nkb : SS;
+    // the whole k range of this CTA fits the ring (always true for decode shapes): all activation tiles complete on
+    // ONE barrier, so the MMA loop and the statistics wait once instead of once per k-block
+    const bool x_single = nkb <= SS;
     if (warp == kProducerWarp && elect_one_sync())
     {
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmX); // first used right after the dependency wait: keep its fetch off the critical path
         for (int s = 0; s < SS; ++s)
         {
             mbar_init(&full[s], 1);
@@ -315,7 +321,8 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         {
             mbar_init(red_bar, 1);
             if (p.cluster)
-                mbar_arrive_expect_tx(red_bar, (uint32_t) (128 * MT * sizeof(float))); // inbox bytes from all ranks
+                mbar_arrive_expect_tx(red_bar, (uint32_t) (128 * MT * sizeof(float)) // inbox bytes from all ranks
+                        + (fold ? (uint32_t) (p.splits * MT * 2 * sizeof(float)) : 0u)); // + their LayerNorm partials
         }
         if (t <= SS + AS + 1)
             fence_mbar_init();
@@ -357,10 +364,20 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         if (elect_one_sync())
         {
             grid_dep_wait();
-            for (int i = 0; i < pre; ++i)
+            TC_STAMP(15);
+            if (x_single)
             {
-                mbar_arrive_expect_tx(&xfull[i], XTileBytes);
-                tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[i]);
+                mbar_arrive_expect_tx(&xfull[0], (uint32_t) (nkb * XTileBytes));
+                for (int i = 0; i < nkb; ++i)
+                    tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[0]);
+            }
+            else
+            {
+                for (int i = 0; i < pre; ++i)
+                {
+                    mbar_arrive_expect_tx(&xfull[i], XTileBytes);
+                    tma_load_2d(smX + i * XTileBytes, &tmX, (kb_begin + i) * 64, m_tile * MT, &xfull[i]);
+                }
             }
             for (int i = pre; i < nkb; ++i)
             {
@@ -381,7 +398,10 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         {
             const int ss = i % SS, as = i % AS;
             mbar_wait(&a_ready[as], (i / AS) & 1);
-            mbar_wait(&xfull[ss], (i / SS) & 1);
+            if (!x_single)
+                mbar_wait(&xfull[ss], (i / SS) & 1);
+            else if (i == 0)
+                mbar_wait(&xfull[0], 0);
             tc_fence_after();
             if (lane == 0 && i < 12)
                 TC_STAMP(16 + 4 * i + 2);
@@ -394,7 +414,9 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                     // K advance inside the 128-byte swizzle atom: 16 halves = 32 bytes = 2 descriptor units
                     tc_mma_ts(d_tmem, tmem_base + as * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
                 }
-                tc_commit(&stage_free[ss]);
+                // stage_free is only consumed when a later block recycles this shared-memory or TMEM stage
+                if (i + AS < nkb)
+                    tc_commit(&stage_free[ss]);
                 if (i == nkb - 1)
                     tc_commit(acc_done);
             }
@@ -493,101 +515,22 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         }
 
         const int m_valid = min(MT, p.M - m_tile * MT);
-        if (fold)
-        {
-            // ---- LayerNorm statistics of the m-tile's rows, two-pass in registers, off the tensor-core critical path:
-            // the whole split is already dequantized into TMEM, this overlaps the activation TMA and the MMAs ----
-            grid_dep_wait(); // x is the previous kernel's output
-            const int cpr = p.K >> 3; // 16-byte chunks per row (<= 192: at most 6 per lane)
-            const float inv_k = 1.f / (float) p.K;
-            for (int rl0 = warp; rl0 < MT; rl0 += 2 * kTcDequantWarps)
-            {
-                uint4 u[2][6];
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-                {
-                    const int rl = rl0 + rr * kTcDequantWarps;
-                    const uint4* xr = reinterpret_cast<const uint4*>(p.fold_x + (size_t) (m_tile * MT + rl) * p.K);
-#pragma unroll
-                    for (int j = 0; j < 6; ++j)
-                    {
-                        const int c = lane + 32 * j;
-                        u[rr][j] = (rl < m_valid && c < cpr) ? __ldcg(xr + c) : make_uint4(0, 0, 0, 0);
-                    }
-                }
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-                {
-                    const int rl = rl0 + rr * kTcDequantWarps;
-                    float sum = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j)
-                    {
-                        const __half2* h = reinterpret_cast<const __half2*>(&u[rr][j]);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                        {
-                            const float2 f = __half22float2(h[q]);
-                            sum += f.x + f.y;
-                        }
-                    }
-#pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1)
-                        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    const float mean = sum * inv_k;
-                    float sq = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j)
-                    {
-                        if (lane + 32 * j < cpr)
-                        {
-                            const __half2* h = reinterpret_cast<const __half2*>(&u[rr][j]);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                            {
-                                const float2 f = __half22float2(h[q]);
-                                sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1)
-                        sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                    if (lane == 0 && rl < MT)
-                    {
-                        ln_stat[2 * rl] = mean;
-                        ln_stat[2 * rl + 1] = rsqrtf(sq * inv_k + p.ln_eps);
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
-        }
-        // y = rstd * (acc - mean * c1s) + c2 when the LayerNorm is folded, acc otherwise
-        auto ln_apply = [&](float acc, int ml, float c1v, float c2v) -> float
-        { return fold ? ln_stat[2 * ml + 1] * (acc - ln_stat[2 * ml] * c1v) + c2v : acc; };
-
-        // ---- epilogue: thread (T, kh) owns accumulator row T, columns [kh*MT/2, (kh+1)*MT/2) ----
-        const int n_tiles = gridDim.x, m_tiles = gridDim.y;
-        const int tile_id = m_tile * n_tiles + n_tile;
-        const bool direct = (p.splits == 1);
-        const bool has_res = p.residual != nullptr;
-        const bool has_bias = p.bias != nullptr;
-        const size_t slab_elems = (size_t) 128 * MT;
-        float* slab = (direct || p.cluster)
-            ? nullptr
-            : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * slab_elems + (size_t) T * MT + kh * kHalfCols;
-        // cluster mode: element (ml, n) goes to the rank that owns column slice n / nslice
+        // cluster geometry of the split-K reduction (also used by the LayerNorm statistics exchange)
         const uint32_t S = (uint32_t) p.splits;
+        const uint32_t my_rank = p.cluster ? cluster_ctarank() : 0u;
+        // cluster mode: element (ml, n) goes to the rank that owns column slice n / nslice
         const int nslice = 128 / (int) S;
         uint32_t push_addr = 0, push_bar = 0;
-        // operands of the final outputs this thread will write, requested before the accumulator is waited for
+        const bool has_bias = p.bias != nullptr;
+        // static operands (weights-side vectors) of the final outputs this thread will write, requested before the
+        // accumulator is waited for
         float own_bias = 0.f, own_c1 = 0.f, own_c2 = 0.f, own_res = 0.f;
         int own_ml = 0, own_nn = 0;
         bool own_valid = false;
         if (p.cluster)
         {
             const uint32_t owner = (uint32_t) (T / nslice);
-            const uint32_t rank = cluster_ctarank();
+            const uint32_t rank = my_rank;
             // inbox layout [sender rank][ml][nl]
             push_addr = mapa_u32(smem_u32(rbuf + ((size_t) rank * MT) * nslice + (T % nslice)), owner);
             push_bar = mapa_u32(smem_u32(red_bar), owner);
@@ -610,13 +553,161 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                 own_c1 = __ldg(p.fold_c1s + own_nn);
                 own_c2 = __ldg(p.fold_c2 + own_nn);
             }
-            if (p.cluster && has_res)
-                own_res = __half2float(p.residual[(size_t) (m_tile * MT + own_ml) * p.ldc + own_nn]);
         }
+        float fin_cn = 0.f; // element count of the partial this thread will merge (rank tq & 7 of row tq >> 3)
+        if (fold && (tq >> 3) < MT && (tq & 7) < (int) S)
+        {
+            const int r = tq & 7;
+            fin_cn = 64.f * (float) (((r + 1) * p.kb_total) / p.splits - (r * p.kb_total) / p.splits);
+        }
+        if constexpr (MT <= 32)
+        {
+            if (fold)
+            {
+                // ---- LayerNorm statistics without touching global memory: every CTA of the split-K cluster reduces
+                // the rows of ITS k range straight from the activation tiles the MMAs consume (shared memory, TMA
+                // already brought them), as (count, mean, M2); the partials travel to all ranks next to the partial
+                // accumulators (same inbox barrier) and are merged with Chan's formula -- two-pass accuracy, no
+                // extra round trip.  TPR threads share a row: 8 chunks of 8 halves x G k-block phases. ----
+                constexpr int TPR = kDq / MT, G = TPR / 8;
+                const int row = tq / TPR, c = tq & 7, g = (tq & (TPR - 1)) >> 3;
+                if (tq == 0)
+                    TC_STAMP(13);
+                // per thread: sums of (v - sh) and (v - sh)^2 with sh = the first value it sees (a sample of the row, so
+                // the cancellation in M2 = b - a^2/n is benign); no divisions in the loop
+                float sh = 0.f, sa = 0.f, sb = 0.f;
+                int cnt = 0;
+                for (int i = g; i < nkb; i += G)
+                {
+                    const int ss = i % SS;
+                    if (!x_single)
+                        mbar_wait(&xfull[ss], (i / SS) & 1);
+                    else if (i == g)
+                        mbar_wait(&xfull[0], 0);
+                    const uint4 u = *reinterpret_cast<const uint4*>(smX + ss * XTileBytes + row * 128 + ((c ^ (row & 7)) << 4));
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
+                    if (i == g)
+                        sh = __low2float(h[0]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                    {
+                        const float2 f = __half22float2(h[q]);
+                        const float d0 = f.x - sh, d1 = f.y - sh;
+                        sa += d0 + d1;
+                        sb = fmaf(d0, d0, fmaf(d1, d1, sb));
+                    }
+                    cnt += 8;
+                }
+                float cn = (float) cnt;
+                const float rn = cnt > 0 ? __fdividef(1.f, cn) : 0.f;
+                float cm = sh + sa * rn, cM2 = sb - sa * sa * rn;
+                // the 8 chunk threads of one k-block phase hold equal counts: exact halving merges
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1)
+                {
+                    const float om = __shfl_xor_sync(0xffffffffu, cm, o);
+                    const float oM = __shfl_xor_sync(0xffffffffu, cM2, o);
+                    const float dl = om - cm;
+                    cm += 0.5f * dl;
+                    cM2 += oM + dl * dl * (0.5f * cn);
+                    cn *= 2.f;
+                }
+                if constexpr (G == 2)
+                {
+                    // the two phases may differ by one k-block: general Chan merge
+                    const float on = __shfl_xor_sync(0xffffffffu, cn, 8);
+                    const float om = __shfl_xor_sync(0xffffffffu, cm, 8);
+                    const float oM = __shfl_xor_sync(0xffffffffu, cM2, 8);
+                    const float nn = cn + on, dl = om - cm;
+                    const float inv = nn > 0.f ? __fdividef(1.f, nn) : 0.f;
+                    cm += dl * on * inv;
+                    cM2 += oM + dl * dl * cn * on * inv;
+                    cn = nn;
+                }
+                // every thread of the row now holds the CTA's partial: thread r of the row pushes it to rank r
+                {
+                    const uint32_t r = (uint32_t) (tq & (TPR - 1));
+                    float* mine = ln_part + ((size_t) my_rank * MT + row) * 2; // [sender rank][row][mean, M2]
+                    if (p.cluster)
+                    {
+                        if (r < S)
+                        {
+                            const uint32_t dst = mapa_u32(smem_u32(mine), r), bar = mapa_u32(smem_u32(red_bar), r);
+                            st_async_f32(dst, cm, bar);
+                            st_async_f32(dst + 4u, cM2, bar);
+                        }
+                    }
+                    else if (r == 0)
+                    {
+                        mine[0] = cm;
+                        mine[1] = cM2;
+                    }
+                }
+                if (tq == 0)
+                    TC_STAMP(14);
+            }
+        }
+        // merges the per-rank partials into (mean, rstd) per row: thread (row, r) takes rank r's partial (it covers
+        // k-blocks [r*kb_total/S, (r+1)*kb_total/S), 64 elements each), 3 shuffle rounds of Chan merges
+        auto ln_finish = [&]()
+        {
+            const int row = tq >> 3, r = tq & 7;
+            float cn = fin_cn, cm = 0.f, cM2 = 0.f;
+            if (row < MT && r < (int) S)
+            {
+                cm = ln_part[(r * MT + row) * 2];
+                cM2 = ln_part[(r * MT + row) * 2 + 1];
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1)
+            {
+                const float on = __shfl_xor_sync(0xffffffffu, cn, o);
+                const float om = __shfl_xor_sync(0xffffffffu, cm, o);
+                const float oM = __shfl_xor_sync(0xffffffffu, cM2, o);
+                const float nn = cn + on, dl = om - cm;
+                const float inv = nn > 0.f ? __fdividef(1.f, nn) : 0.f;
+                cm += dl * on * inv;
+                cM2 += oM + dl * dl * cn * on * inv;
+                cn = nn;
+            }
+            if (row < MT && r == 0)
+            {
+                ln_fin[2 * row] = cm;
+                ln_fin[2 * row + 1] = rsqrtf(__fdividef(cM2, cn) + p.ln_eps);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
+        };
+        auto ln_row_stats = [&](int ml, float& mean, float& rstd)
+        {
+            mean = ln_fin[2 * ml];
+            rstd = ln_fin[2 * ml + 1];
+        };
+        // y = rstd * (acc - mean * c1s) + c2 when the LayerNorm is folded, acc otherwise
+        auto ln_apply = [&](float acc, float mean, float rstd, float c1v, float c2v) -> float
+        { return fold ? rstd * (acc - mean * c1v) + c2v : acc; };
+
+        // ---- epilogue: thread (T, kh) owns accumulator row T, columns [kh*MT/2, (kh+1)*MT/2) ----
+        const int n_tiles = gridDim.x, m_tiles = gridDim.y;
+        const int tile_id = m_tile * n_tiles + n_tile;
+        const bool direct = (p.splits == 1);
+        const bool has_res = p.residual != nullptr;
+        const size_t slab_elems = (size_t) 128 * MT;
+        float* slab = (direct || p.cluster)
+            ? nullptr
+            : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * slab_elems + (size_t) T * MT + kh * kHalfCols;
         mbar_wait(acc_done, 0);
         tc_fence_after();
+        // the residual is an earlier kernel's output: it may only be read after the dependency wait, which acc_done
+        // implies (activation TMA -> MMA -> commit); its latency hides behind the cluster exchange below
+        if (own_valid && p.cluster && has_res)
+            own_res = __half2float(p.residual[(size_t) (m_tile * MT + own_ml) * p.ldc + own_nn]);
         if (tq == 0)
             TC_STAMP(7);
+        if (fold && !p.cluster)
+        {
+            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory"); // this CTA's own partial is complete
+            ln_finish();
+        }
 #pragma unroll 1
         for (int c8 = 0; c8 < kHalfCols / 8; ++c8)
         {
@@ -635,9 +726,14 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     if (ml0 + i < m_valid && n < p.N)
+                    {
+                        float mean = 0.f, rstd = 1.f;
+                        if (fold)
+                            ln_row_stats(ml0 + i, mean, rstd);
                         p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
-                            = finish_output(ln_apply(__uint_as_float(acc[i]) * scf, ml0 + i, own_c1, own_c2), has_bias,
+                            = finish_output(ln_apply(__uint_as_float(acc[i]) * scf, mean, rstd, own_c1, own_c2), has_bias,
                                 own_bias, p.activation, has_res, res[i]);
+                    }
             }
             else if (p.cluster)
             {
@@ -663,6 +759,10 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
             mbar_wait(red_bar, 0);
             if (tq == 0)
                 TC_STAMP(9);
+            if (fold)
+                ln_finish();
+            if (tq == 0)
+                TC_STAMP(11);
             const int n_lo = (int) cluster_ctarank() * nslice;
             for (int e = tq; e < nslice * m_valid; e += kDq)
             {
@@ -686,7 +786,10 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                 for (uint32_t q = 0; q < 8; ++q)
                     if (q < S)
                         sum += src[(size_t) q * MT * nslice];
-                p.C[idx] = finish_output(ln_apply(sum, ml, c1v, c2v), has_bias, bv, p.activation, has_res, res);
+                float mean = 0.f, rstd = 1.f;
+                if (fold)
+                    ln_row_stats(ml, mean, rstd);
+                p.C[idx] = finish_output(ln_apply(sum, mean, rstd, c1v, c2v), has_bias, bv, p.activation, has_res, res);
             }
             if (tq == 0)
                 TC_STAMP(10);
@@ -757,8 +860,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                         for (int i = 0; i < 8; ++i)
                             if (ml0 + i < m_valid)
                                 p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
-                                    = finish_output(ln_apply(sum[i], ml0 + i, own_c1, own_c2), has_bias, own_bias,
-                                        p.activation, has_res, res[i]);
+                                    = finish_output(sum[i], has_bias, own_bias, p.activation, has_res, res[i]); // (no fold here)
                     }
                 }
                 if (tq == 0)
@@ -973,6 +1075,12 @@ struct TcPlan
 };
 
 static long long* g_tc_dbg = nullptr;
+static int g_tc_dbg_n = 0, g_tc_dbg_fold = 0; // optional filter: only launches with this N (and folded-LN flag) stamp
+void tc_set_debug_filter(int n, int fold)
+{
+    g_tc_dbg_n = n;
+    g_tc_dbg_fold = fold;
+}
 void tc_set_debug_buffer(long long* p)
 {
     g_tc_dbg = p;
@@ -1095,11 +1203,17 @@ static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcPar
     return B200_OK;
 }
 
-// Can LayerNorm be folded into the GEMM for this shape?  (decode-sized m-tiles whose rows fit the statistics warps'
-// registers: 6 x 16-byte chunks per lane)
-bool woq_tc_can_fold_ln(int M, int K)
+// Can LayerNorm be folded into the GEMM for this shape?  (decode-sized m-tiles, cluster or unsplit reduction, the
+// whole k range of a CTA resident in the activation ring)
+bool woq_tc_can_fold_ln(int M, int N, int K)
 {
-    return M <= 32 && K <= 1536;
+    if (M > 32)
+        return false;
+    const TcPlan pl = plan_tc(M, N, K);
+    if (!(pl.cluster || pl.splits == 1))
+        return false; // the statistics travel through the cluster inbox
+    const int nkb = (K / 64 + pl.splits - 1) / pl.splits;
+    return nkb <= (pl.MT == 16 ? 10 : 7); // the activation stages must not be recycled before they are summed
 }
 
 // tcgen05 path entry: any M >= 1.  fold_gamma != nullptr: A is the raw residual stream and the LayerNorm is folded
@@ -1148,7 +1262,7 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     p.kb_total = K / 64;
     p.splits = pl.splits;
     p.cluster = pl.cluster;
-    p.dbg = g_tc_dbg;
+    p.dbg = (g_tc_dbg_n == 0 || (g_tc_dbg_n == N && g_tc_dbg_fold == (fold_gamma != nullptr ? 1 : 0))) ? g_tc_dbg : nullptr;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     switch (pl.MT)
     {

@@ -134,6 +134,7 @@ int b200_woq_int8_gemm_ln_folded(const void* X, const void* ln_gamma, const void
 int b200_woq_set_kernel_policy(int policy);
 /* Debug aid: device buffer of >= 16 int64 receiving clock64() stamps of CTA (0,0,0) of each following tcgen05 GEMM
  * launch at its phase boundaries; NULL switches it off. */
+int b200_debug_tc_timing_filter(int n, int folded_ln); /* only launches with this N and folded-LN flag stamp (0: all) */
 int b200_debug_tc_timing(void* device_buffer);
 /* One-time allocation of library-owned device state (split-K tile counters).  Call before CUDA-graph capture. */
 int b200_init(void);
