@@ -227,7 +227,7 @@ struct TcSmem
     static constexpr size_t ring = (size_t) SS * (kWTileBytes + XTileBytes);
     static constexpr size_t rbuf = (size_t) 128 * MT * sizeof(float); // cluster reduction inbox [S][MT][128/S]
     static_assert(AS <= SS, "the TMEM A ring is never deeper than the shared-memory ring");
-    static constexpr size_t bars = (sizeof(uint64_t) * (3 * SS + AS + 2) + 16 + 15) & ~size_t(15); // keeps what follows 16-byte aligned
+    static constexpr size_t bars = (sizeof(uint64_t) * (3 * SS + AS + 3) + 16 + 15) & ~size_t(15); // keeps what follows 16-byte aligned
 
     static constexpr size_t ln_bytes(int K) // folded LayerNorm: gamma [K] fp16 + (mean, M2) per sender rank and row
     {
@@ -265,8 +265,9 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     uint64_t* stage_free = xfull + SS; // MMA of block i done (index i % SS): its smem stage and TMEM A stage are reusable
     uint64_t* a_ready = stage_free + SS; // dequantized A tile of block i is in TMEM stage i % AS
     uint64_t* acc_done = a_ready + AS;
-    uint64_t* red_bar = acc_done + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(red_bar + 1);
+    uint64_t* red_bar = acc_done + 1;  // cluster inbox: partial accumulators of all ranks have landed
+    uint64_t* stat_bar = red_bar + 1;  // cluster inbox: LayerNorm partials of all ranks have landed (they arrive earlier)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_bar + 1);
     int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
     uint8_t* extra = reinterpret_cast<uint8_t*>(full) + L::bars;
     float* rbuf = reinterpret_cast<float*>(extra);                       // cluster mode: [S][MT][128/S]
@@ -320,9 +321,13 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         else if (t == SS + AS + 1)
         {
             mbar_init(red_bar, 1);
+            mbar_init(stat_bar, 1);
             if (p.cluster)
-                mbar_arrive_expect_tx(red_bar, (uint32_t) (128 * MT * sizeof(float)) // inbox bytes from all ranks
-                        + (fold ? (uint32_t) (p.splits * MT * 2 * sizeof(float)) : 0u)); // + their LayerNorm partials
+            {
+                mbar_arrive_expect_tx(red_bar, (uint32_t) (128 * MT * sizeof(float))); // inbox bytes from all ranks
+                if (fold)
+                    mbar_arrive_expect_tx(stat_bar, (uint32_t) (p.splits * MT * 2 * sizeof(float)));
+            }
         }
         if (t <= SS + AS + 1)
             fence_mbar_init();
@@ -524,20 +529,22 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         const bool has_bias = p.bias != nullptr;
         // static operands (weights-side vectors) of the final outputs this thread will write, requested before the
         // accumulator is waited for
-        float own_bias = 0.f, own_c1 = 0.f, own_c2 = 0.f, own_res = 0.f;
-        int own_ml = 0, own_nn = 0;
+        float own_bias = 0.f, own_c1 = 0.f, own_c2 = 0.f;
+        float own_res[4] = {0.f, 0.f, 0.f, 0.f};
+        // cluster mode: this thread reduces elements (ml_first + j*ml_step, own_nn), j = 0, 1, ... -- one fixed column
+        // (256 threads are a multiple of the slice width), so bias and the fold vectors are per-thread constants
+        const int ns_shift = __ffs(nslice) - 1; // nslice is a power of two
+        const int ml_first = tq >> ns_shift, ml_step = kDq >> ns_shift;
+        int own_nn = 0;
         bool own_valid = false;
         if (p.cluster)
         {
-            const uint32_t owner = (uint32_t) (T / nslice);
-            const uint32_t rank = my_rank;
+            const uint32_t owner = (uint32_t) (T >> ns_shift);
             // inbox layout [sender rank][ml][nl]
-            push_addr = mapa_u32(smem_u32(rbuf + ((size_t) rank * MT) * nslice + (T % nslice)), owner);
+            push_addr = mapa_u32(smem_u32(rbuf + ((size_t) my_rank * MT) * nslice + (T & (nslice - 1))), owner);
             push_bar = mapa_u32(smem_u32(red_bar), owner);
-            // first (usually only) element of this rank's column slice reduced by this thread
-            own_ml = tq / nslice;
-            own_nn = n_tile * 128 + (int) rank * nslice + (tq - own_ml * nslice);
-            own_valid = tq < nslice * m_valid && own_nn < p.N;
+            own_nn = n_tile * 128 + (int) my_rank * nslice + (tq & (nslice - 1));
+            own_valid = ml_first < m_valid && own_nn < p.N;
         }
         else
         {
@@ -632,7 +639,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                     {
                         if (r < S)
                         {
-                            const uint32_t dst = mapa_u32(smem_u32(mine), r), bar = mapa_u32(smem_u32(red_bar), r);
+                            const uint32_t dst = mapa_u32(smem_u32(mine), r), bar = mapa_u32(smem_u32(stat_bar), r);
                             st_async_f32(dst, cm, bar);
                             st_async_f32(dst + 4u, cM2, bar);
                         }
@@ -700,7 +707,12 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         // the residual is an earlier kernel's output: it may only be read after the dependency wait, which acc_done
         // implies (activation TMA -> MMA -> commit); its latency hides behind the cluster exchange below
         if (own_valid && p.cluster && has_res)
-            own_res = __half2float(p.residual[(size_t) (m_tile * MT + own_ml) * p.ldc + own_nn]);
+        {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (ml_first + j * ml_step < m_valid)
+                    own_res[j] = __half2float(p.residual[(size_t) (m_tile * MT + ml_first + j * ml_step) * p.ldc + own_nn]);
+        }
         if (tq == 0)
             TC_STAMP(7);
         if (fold && !p.cluster)
@@ -752,44 +764,48 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         }
         if (tq == 0)
             TC_STAMP(8);
+        // the accumulator has been read: let the MMA warp free the TMEM columns while the reduction runs
+        tc_fence_before();
+        asm volatile("bar.arrive 2, %0;" ::"n"(kDq + 32) : "memory");
         if (p.cluster)
         {
             // ---- split-K reduction through distributed shared memory: every rank received the partial values of its
             // column slice from all ranks (st.async + complete_tx on its inbox barrier) and sums them in rank order ----
+            if (fold)
+            {
+                // the LayerNorm partials were pushed before the accumulators: merge them while those are in flight
+                mbar_wait(stat_bar, 0);
+                ln_finish();
+            }
+            if (tq == 0)
+                TC_STAMP(11);
             mbar_wait(red_bar, 0);
             if (tq == 0)
                 TC_STAMP(9);
-            if (fold)
-                ln_finish();
-            if (tq == 0)
-                TC_STAMP(11);
-            const int n_lo = (int) cluster_ctarank() * nslice;
-            for (int e = tq; e < nslice * m_valid; e += kDq)
+            if (own_valid)
             {
-                const int ml = e / nslice;
-                const int nl = e - ml * nslice;
-                const int nn = n_tile * 128 + n_lo + nl;
-                if (nn >= p.N)
-                    continue;
-                const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + nn;
-                float res = own_res, bv = own_bias, c1v = own_c1, c2v = own_c2;
-                if (e != tq)
+                const int nl = tq & (nslice - 1);
+                auto reduce_one = [&](int ml, float res)
                 {
-                    res = has_res ? __half2float(p.residual[idx]) : 0.f;
-                    bv = has_bias ? __half2float(__ldg(p.bias + nn)) : 0.f;
-                    c1v = fold ? __ldg(p.fold_c1s + nn) : 0.f;
-                    c2v = fold ? __ldg(p.fold_c2 + nn) : 0.f;
-                }
-                const float* src = rbuf + (size_t) ml * nslice + nl;
-                float sum = 0.f;
+                    const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + own_nn;
+                    const float* src = rbuf + (size_t) ml * nslice + nl;
+                    float sum = 0.f;
 #pragma unroll
-                for (uint32_t q = 0; q < 8; ++q)
-                    if (q < S)
-                        sum += src[(size_t) q * MT * nslice];
-                float mean = 0.f, rstd = 1.f;
-                if (fold)
-                    ln_row_stats(ml, mean, rstd);
-                p.C[idx] = finish_output(ln_apply(sum, mean, rstd, c1v, c2v), has_bias, bv, p.activation, has_res, res);
+                    for (uint32_t q = 0; q < 8; ++q)
+                        if (q < S)
+                            sum += src[(size_t) q * MT * nslice];
+                    float mean = 0.f, rstd = 1.f;
+                    if (fold)
+                        ln_row_stats(ml, mean, rstd);
+                    p.C[idx] = finish_output(ln_apply(sum, mean, rstd, own_c1, own_c2), has_bias, own_bias, p.activation,
+                        has_res, res);
+                };
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ml_first + j * ml_step < m_valid)
+                        reduce_one(ml_first + j * ml_step, own_res[j]);
+                for (int ml = ml_first + 4 * ml_step; ml < m_valid; ml += ml_step) // only MT = 32 with 2 splits
+                    reduce_one(ml, has_res ? __half2float(p.residual[(size_t) (m_tile * MT + ml) * p.ldc + own_nn]) : 0.f);
             }
             if (tq == 0)
                 TC_STAMP(10);
@@ -869,11 +885,10 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         }
     }
 
-    // ---- teardown ----
-    tc_fence_before();
-    __syncthreads();
+    // ---- teardown: no CTA-wide barrier; the MMA warp waits for the epilogue warps' last TMEM read only ----
     if (warp == kMmaWarp)
     {
+        asm volatile("bar.sync 2, %0;" ::"n"(kDq + 32) : "memory");
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
         if (lane == 0)
