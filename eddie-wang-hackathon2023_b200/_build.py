@@ -23,6 +23,11 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
           "-I" + PLUG]
+# B200_TC_DEBUG=1: compile the clock64 / %globaltimer stamps into the tcgen05 GEMM (tools/tc_timing*.py,
+# tools/gemm_timeline.py).  Off by default: the stamps cost about 1 % of the decoder step even when unused.
+DEBUG_STAMPS = os.environ.get("B200_TC_DEBUG", "0") == "1"
+if DEBUG_STAMPS:
+    COMMON = COMMON + ["-DB200_TC_DEBUG=1"]
 
 
 def _sources():
@@ -52,7 +57,7 @@ def _headers_stamp():
 
 def _compile(src, stamp, verbose):
     rel = os.path.relpath(src, PKG).replace(os.sep, "_")
-    obj = os.path.join(OBJDIR, f"{rel}.{stamp}.o")
+    obj = os.path.join(OBJDIR, f"{rel}.{stamp}{'.dbg' if DEBUG_STAMPS else ''}.o")
     if os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(src):
         return obj
     cmd = [NVCC] + ARCH + COMMON + (["-x", "cu"] if src.endswith(".cpp") else []) + ["-c", src, "-o", obj]
@@ -75,13 +80,18 @@ def build(verbose=False, force=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, stamp, verbose), srcs))
     out = os.path.join(LIBDIR, LIBNAME)
-    if (not os.path.exists(out)) or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs):
+    flavour = os.path.join(LIBDIR, ".flavour")
+    want = "debug-stamps" if DEBUG_STAMPS else "release"
+    have = open(flavour).read().strip() if os.path.exists(flavour) else ""
+    if (not os.path.exists(out)) or have != want or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-Xlinker", "--version-script=" + os.path.join(PKG, "exports.map")]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        with open(flavour, "w") as f:
+            f.write(want)
     # drop stale objects
     keep = set(objs)
     for f in os.listdir(OBJDIR):

@@ -52,6 +52,7 @@ _SIGS = {
     "b200_woq_set_kernel_policy": (_i, [_i]),
     "b200_debug_tc_timing": (_i, [_vp]),
     "b200_debug_tc_timing_filter": (_i, [_i, _i]),
+    "b200_debug_tc_timeline": (_i, [_vp, _i]),
     "b200_mmha_generation": (_i, [ctypes.POINTER(MmhaParams), _vp]),
     "b200_attention_context": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "b200_cross_attention_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -548,11 +548,13 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
 //      * the ranges of a (row, head) are merged by the last warp to arrive (self-resetting counter).
 // =====================================================================================================
 // (warps per CTA, ring stages per warp, keys per chunk) -- one CTA per SM; WARPS*STAGES*CK*128 B of shared memory (int8)
-struct XaCfgA { static constexpr int W = 8, ST = 3, CK = 64; };
-struct XaCfgB { static constexpr int W = 16, ST = 3, CK = 32; };
-struct XaCfgC { static constexpr int W = 12, ST = 2, CK = 64; };
-struct XaCfgD { static constexpr int W = 13, ST = 2, CK = 64; };
-struct XaCfgE { static constexpr int W = 9, ST = 3, CK = 64; };
+// OCC = CTAs per SM the row-head kernel is sized for (F: half-size CTAs, so a GEMM CTA of another stream can share the SM)
+struct XaCfgA { static constexpr int W = 8, ST = 3, CK = 64, OCC = 1; };
+struct XaCfgB { static constexpr int W = 16, ST = 3, CK = 32, OCC = 1; };
+struct XaCfgC { static constexpr int W = 12, ST = 2, CK = 64, OCC = 1; };
+struct XaCfgD { static constexpr int W = 13, ST = 2, CK = 64, OCC = 1; };
+struct XaCfgE { static constexpr int W = 9, ST = 3, CK = 64, OCC = 1; };
+struct XaCfgF { static constexpr int W = 6, ST = 2, CK = 64, OCC = 2; };
 
 __device__ __forceinline__ float fast_exp2(float x)
 {
@@ -898,7 +900,7 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
 // the split kernel above, and merge their partial softmax states through shared memory -- no global partials, no
 // fences, no counters.  q of the next pair is fetched while the current one is being processed.
 template <bool INT8, typename CFG>
-__global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_rowhead_kernel(const XAttnParams p)
+__global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead_kernel(const XAttnParams p)
 {
     constexpr int W = CFG::W, ST = CFG::ST;
     constexpr int ESZ = INT8 ? 1 : 2;
@@ -1143,7 +1145,7 @@ struct XaPlan
     size_t smem, ws_bytes;
 };
 
-static int g_xa_cfg = -1;  // env B200_XA_CFG = A .. E
+static int g_xa_cfg = -1;  // env B200_XA_CFG = A .. F
 static int g_xa_mode = -1; // env B200_XA_MODE = split | rowhead | auto (default)
 
 static XaPlan xattn_plan(int R, int H, int S, int int8)
@@ -1151,11 +1153,12 @@ static XaPlan xattn_plan(int R, int H, int S, int int8)
     if (g_xa_cfg < 0)
     {
         const char* e = getenv("B200_XA_CFG");
-        g_xa_cfg = (e != nullptr && e[0] >= 'A' && e[0] <= 'E') ? e[0] - 'A' : 2;
+        g_xa_cfg = (e != nullptr && e[0] >= 'A' && e[0] <= 'F') ? e[0] - 'A' : 2;
     }
-    static const int kW[5] = {XaCfgA::W, XaCfgB::W, XaCfgC::W, XaCfgD::W, XaCfgE::W};
-    static const int kST[5] = {XaCfgA::ST, XaCfgB::ST, XaCfgC::ST, XaCfgD::ST, XaCfgE::ST};
-    static const int kCK[5] = {XaCfgA::CK, XaCfgB::CK, XaCfgC::CK, XaCfgD::CK, XaCfgE::CK};
+    static const int kW[6] = {XaCfgA::W, XaCfgB::W, XaCfgC::W, XaCfgD::W, XaCfgE::W, XaCfgF::W};
+    static const int kST[6] = {XaCfgA::ST, XaCfgB::ST, XaCfgC::ST, XaCfgD::ST, XaCfgE::ST, XaCfgF::ST};
+    static const int kCK[6] = {XaCfgA::CK, XaCfgB::CK, XaCfgC::CK, XaCfgD::CK, XaCfgE::CK, XaCfgF::CK};
+    static const int kOCC[6] = {1, 1, 1, 1, 1, XaCfgF::OCC};
     const int W = kW[g_xa_cfg], ST = kST[g_xa_cfg], CKi = kCK[g_xa_cfg];
     if (g_xa_mode < 0)
     {
@@ -1170,7 +1173,8 @@ static XaPlan xattn_plan(int R, int H, int S, int int8)
     pl.rowhead = g_xa_mode == 2 ? ((long long) R * H * 2 >= num_sms() ? 1 : 0) : g_xa_mode;
     if (pl.rowhead)
     {
-        pl.blocks = R * H < num_sms() ? R * H : num_sms();
+        const int slots = num_sms() * kOCC[g_xa_cfg];
+        pl.blocks = R * H < slots ? R * H : slots;
         pl.smem = (size_t) W * ST * 2 * ck * kDh * (int8 ? 1 : 2) + sizeof(uint64_t) * W * ST
             + sizeof(float) * 2 * W * (kDh + 4);
         pl.ws_bytes = 0;
@@ -1212,6 +1216,9 @@ static int xattn_launch_rowhead(const XAttnParams& p, const XaPlan& pl, cudaStre
     if (!attr_set)
     {
         B200_CUDA(cudaFuncSetAttribute(cross_attention_rowhead_kernel<INT8, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
+        if (getenv("B200_XA_NOCARVE") == nullptr)
+            B200_CUDA(cudaFuncSetAttribute(cross_attention_rowhead_kernel<INT8, CFG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     B200_LAUNCH((cross_attention_rowhead_kernel<INT8, CFG>), dim3(pl.blocks), dim3(CFG::W * 32), pl.smem, st, p);
@@ -1273,7 +1280,9 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
         case 6: return xattn_launch_rowhead<false, XaCfgD>(p, pl, st);
         case 7: return xattn_launch_rowhead<true, XaCfgD>(p, pl, st);
         case 8: return xattn_launch_rowhead<false, XaCfgE>(p, pl, st);
-        default: return xattn_launch_rowhead<true, XaCfgE>(p, pl, st);
+        case 9: return xattn_launch_rowhead<true, XaCfgE>(p, pl, st);
+        case 10: return xattn_launch_rowhead<false, XaCfgF>(p, pl, st);
+        default: return xattn_launch_rowhead<true, XaCfgF>(p, pl, st);
         }
     }
     B200_REQUIRE(workspace && workspace_bytes >= pl.ws_bytes, B200_ERR_WORKSPACE,
@@ -1292,7 +1301,9 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     case 6: return xattn_launch<false, XaCfgD>(p, pl, st);
     case 7: return xattn_launch<true, XaCfgD>(p, pl, st);
     case 8: return xattn_launch<false, XaCfgE>(p, pl, st);
-    default: return xattn_launch<true, XaCfgE>(p, pl, st);
+    case 9: return xattn_launch<true, XaCfgE>(p, pl, st);
+    case 10: return xattn_launch<false, XaCfgF>(p, pl, st);
+    default: return xattn_launch<true, XaCfgF>(p, pl, st);
     }
 }
 

@@ -16,6 +16,7 @@ size_t woq_tc_workspace_bytes(int max_m, int N, int K);
 int tc_init();
 void tc_set_debug_buffer(long long* p);
 void tc_set_debug_filter(int n, int fold);
+void tc_set_timeline_buffer(long long* p, int max_launches);
 bool woq_tc_can_fold_ln(int M, int N, int K);
 
 static int g_policy = 0; // 0 auto, 1 simt, 2 tcgen05
@@ -182,6 +183,15 @@ extern "C" int b200_init(void)
 
 // Debug aid: device buffer of >= 16 int64 that receives clock64() stamps of CTA (0,0,0) of every following tcgen05
 // GEMM launch (phase boundaries, see TC_STAMP in woq_gemm_tc.cu); NULL switches it off.
+// Debug aid: every following tcgen05 GEMM launch (up to max_launches) records, in launch order, 4 int64 global-timer
+// values: [0] earliest CTA entry, [1] earliest return of the dependency wait, [2] latest CTA exit.  The caller
+// initialises [0] and [1] to INT64_MAX and [2] to 0.  NULL switches it off.
+extern "C" int b200_debug_tc_timeline(void* device_buffer, int max_launches)
+{
+    tc_set_timeline_buffer(static_cast<long long*>(device_buffer), max_launches);
+    return B200_OK;
+}
+
 extern "C" int b200_debug_tc_timing_filter(int n, int folded_ln)
 {
     tc_set_debug_filter(n, folded_ln);

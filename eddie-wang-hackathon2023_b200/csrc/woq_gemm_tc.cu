@@ -56,15 +56,40 @@ struct TcParams
     int kb_total; // K / 64
     int splits;
     int cluster;  // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
+    long long* gt;  // optional: 4 global-timer values of this launch (min entry, min dependency return, max store, -)
     long long* dbg; // optional: clock64() stamps of CTA (0,0,0) at the phase boundaries (b200_debug_tc_timing)
 };
 
+__device__ __forceinline__ long long global_timer_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+#if defined(B200_TC_DEBUG)
 #define TC_STAMP(slot)                                                                                                 \
     do                                                                                                                 \
     {                                                                                                                  \
         if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)                                 \
             p.dbg[slot] = clock64();                                                                                   \
     } while (0)
+#define TC_GT(op, slot)                                                                                                \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (p.gt != nullptr)                                                                                           \
+            op(reinterpret_cast<unsigned long long*>(p.gt + (slot)), (unsigned long long) global_timer_ns());          \
+    } while (0)
+#else // release build: no stamps in the kernel (python __graft_entry__.py build with B200_TC_DEBUG=1 enables them)
+#define TC_STAMP(slot)                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+    } while (0)
+#define TC_GT(op, slot)                                                                                                \
+    do                                                                                                                 \
+    {                                                                                                                  \
+    } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -257,7 +282,9 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms (TMA and UMMA agree on address bits 7..9)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (pointer arithmetic on the __shared__ array itself, so the compiler keeps the shared address space: LDS/STS, not
+    // generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smW = smem;
     uint8_t* smX = smem + SS * kWTileBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smX + SS * XTileBytes); // weight tile of block i has landed
@@ -284,7 +311,11 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     const int nkb = kb_end - kb_begin;
     const bool fold = p.fold_gamma != nullptr;
     if (threadIdx.x == 0)
+    {
         TC_STAMP(0);
+        TC_GT(atomicMin, 0);
+        TC_GT(atomicMax, 3);
+    }
 
     // ---- prologue.  The producer thread owns the `full` barriers: it initialises them and immediately starts the
     // weight stream (weights never depend on the previous kernel), while the other warps set up the rest. ----
@@ -370,6 +401,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         {
             grid_dep_wait();
             TC_STAMP(15);
+            TC_GT(atomicMin, 1);
             if (x_single)
             {
                 mbar_arrive_expect_tx(&xfull[0], (uint32_t) (nkb * XTileBytes));
@@ -794,6 +826,12 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                     for (uint32_t q = 0; q < 8; ++q)
                         if (q < S)
                             sum += src[(size_t) q * MT * nslice];
+                    if (S > 8) // 16-CTA clusters (opt-in)
+                    {
+#pragma unroll
+                        for (uint32_t q = 8; q < 16; ++q)
+                            sum += src[(size_t) q * MT * nslice];
+                    }
                     float mean = 0.f, rstd = 1.f;
                     if (fold)
                         ln_row_stats(ml, mean, rstd);
@@ -885,6 +923,8 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         }
     }
 
+    if (threadIdx.x == 0)
+        TC_GT(atomicMax, 2);
     // ---- teardown: no CTA-wide barrier; the MMA warp waits for the epilogue warps' last TMEM read only ----
     if (warp == kMmaWarp)
     {
@@ -930,7 +970,9 @@ __global__ void __launch_bounds__(192, 1)
     constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t) (MT >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (pointer arithmetic on the __shared__ array itself, so the compiler keeps the shared address space: LDS/STS, not
+    // generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smE = smem;
     uint8_t* smX = smem + SS * ETileBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smX + SS * XTileBytes);
@@ -1089,6 +1131,14 @@ struct TcPlan
     size_t slab_bytes;
 };
 
+static long long* g_tc_gt = nullptr; // per-launch global-timer records [launch][4]
+static int g_tc_gt_cap = 0, g_tc_gt_seq = 0;
+void tc_set_timeline_buffer(long long* p, int max_launches)
+{
+    g_tc_gt = p;
+    g_tc_gt_cap = max_launches;
+    g_tc_gt_seq = 0;
+}
 static long long* g_tc_dbg = nullptr;
 static int g_tc_dbg_n = 0, g_tc_dbg_fold = 0; // optional filter: only launches with this N (and folded-LN flag) stamp
 void tc_set_debug_filter(int n, int fold)
@@ -1103,8 +1153,15 @@ void tc_set_debug_buffer(long long* p)
 
 static int g_splitk_mode = -1; // -1 auto (env B200_SPLITK: "cluster" | "global"), 0 global slabs, 1 cluster
 
+static int g_cluster16 = -1; // env B200_CLUSTER16=1 enables 16-CTA (non-portable) clusters for deep-K decode GEMMs
+
 TcPlan plan_tc(int M, int N, int K)
 {
+    if (g_cluster16 < 0)
+    {
+        const char* e = getenv("B200_CLUSTER16");
+        g_cluster16 = (e != nullptr && e[0] == '1') ? 1 : 0; // opt-in: measured neutral on the decoder step
+    }
     if (g_splitk_mode < 0)
     {
         const char* e = getenv("B200_SPLITK");
@@ -1130,6 +1187,10 @@ TcPlan plan_tc(int M, int N, int K)
             int s2 = 8;
             while (s2 > 1 && (tiles * s2 > cap || kb_total < 2 * s2))
                 s2 >>= 1;
+            // deep-K decode GEMMs (fc2): an 8-way split leaves more k-blocks per CTA than the TMEM ring holds, so part
+            // of the dequant would run after the dependency resolves; a 16-CTA (non-portable) cluster halves that
+            if (g_cluster16 && pl.MT <= 32 && s2 == 8 && kb_total > 8 * 6 && tiles * 16 <= cap && kb_total >= 32)
+                s2 = 16;
             splits = s2;
             cluster = s2 > 1 ? 1 : 0;
         }
@@ -1188,6 +1249,8 @@ static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcPar
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         // decode tiles are sized so that two CTAs (this GEMM's and the next one's, launched early) share an SM
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (g_cluster16 > 0)
+            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         attr_smem = smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -1225,8 +1288,8 @@ bool woq_tc_can_fold_ln(int M, int N, int K)
     if (M > 32)
         return false;
     const TcPlan pl = plan_tc(M, N, K);
-    if (!(pl.cluster || pl.splits == 1))
-        return false; // the statistics travel through the cluster inbox
+    if (!(pl.cluster || pl.splits == 1) || pl.splits > 8)
+        return false; // the statistics travel through the cluster inbox (8 sender slots)
     const int nkb = (K / 64 + pl.splits - 1) / pl.splits;
     return nkb <= (pl.MT == 16 ? 10 : 7); // the activation stages must not be recycled before they are summed
 }
@@ -1277,6 +1340,7 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     p.kb_total = K / 64;
     p.splits = pl.splits;
     p.cluster = pl.cluster;
+    p.gt = (g_tc_gt != nullptr && g_tc_gt_seq < g_tc_gt_cap) ? g_tc_gt + 4 * (size_t) (g_tc_gt_seq++) : nullptr;
     p.dbg = (g_tc_dbg_n == 0 || (g_tc_dbg_n == N && g_tc_dbg_fold == (fold_gamma != nullptr ? 1 : 0))) ? g_tc_dbg : nullptr;
     dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
     switch (pl.MT)

@@ -124,6 +124,16 @@ class WhisperDecoding:
                        self.lib.b200_cross_attention_workspace_bytes(max_rows, self.H, self.Dh, self.S_enc), 1 << 20)
         self.ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         self.graph = None
+        # Independent utterances can be stepped as several interleaved chains of kernels (each on its own stream, all
+        # inside the same CUDA graph): while one chain sits in the dependency latency between two small GEMMs, or
+        # streams its cross-KV cache, the other chains' kernels fill the SMs.  Weights are read once per chain (the
+        # second read is normally an L2 hit).  B200_CHAINS=1 restores the single chain.
+        self.n_chains = int(os.environ.get("B200_CHAINS", "1"))
+        if self.n_chains < 1 or B % self.n_chains != 0:
+            self.n_chains = 1
+        self._chain_streams = [torch.cuda.Stream(device=dev) for _ in range(self.n_chains - 1)] \
+            if torch.cuda.is_available() else []
+        self._chain_ws = [torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) for _ in range(self.n_chains - 1)]
         # side stream that pulls the next layer's cross-KV cache into L2 while the current layer's small kernels run
         self.prefetch_cross_kv = os.environ.get("B200_XKV_PREFETCH", "0") != "0"
         self._side = torch.cuda.Stream(device=dev) if torch.cuda.is_available() else None
@@ -134,29 +144,31 @@ class WhisperDecoding:
     def _st(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _gemm(self, x, rows, lin, out, bias=True, act=_lib.ACT_NONE, residual=None):
+    def _gemm(self, x, rows, lin, out, bias=True, act=_lib.ACT_NONE, residual=None, ws=None):
+        ws = self.ws if ws is None else ws
         rc = self.lib.b200_woq_int8_gemm_fused(
             x.data_ptr(), rows, lin.k, lin.weight.data_ptr(), lin.scales.data_ptr(), lin.n,
             lin.bias.data_ptr() if (bias and lin.bias is not None) else None, act,
-            residual.data_ptr() if residual is not None else None, out.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+            residual.data_ptr() if residual is not None else None, out.data_ptr(), ws.data_ptr(), ws.numel(),
             self._st())
         _lib.check(rc, "woq gemm")
 
-    def _gemm_ln(self, x, wb, rows, lin, out, act=_lib.ACT_NONE):
+    def _gemm_ln(self, x, wb, rows, lin, out, act=_lib.ACT_NONE, ws=None):
         """out = act(LayerNorm(x; wb) @ W + bias) with the LayerNorm folded into the GEMM kernel (decode-sized row
         counts; larger ones take the two-launch route inside the same entry point)."""
+        ws = self.ws if ws is None else ws
         rc = self.lib.b200_woq_int8_gemm_ln_folded(
             x.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), lin.c1s.data_ptr(), lin.c2.data_ptr(), 1e-5, rows, lin.k,
             lin.weight.data_ptr(), lin.scales.data_ptr(), lin.n, lin.bias.data_ptr() if lin.bias is not None else None,
-            act, None, out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), self._st())
+            act, None, out.data_ptr(), ws.data_ptr(), ws.numel(), self._st())
         _lib.check(rc, "woq gemm (folded LayerNorm)")
 
     def _ln(self, x, wb, out, rows):
         _lib.check(self.lib.b200_layernorm_fp16(x.data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), out.data_ptr(), rows,
                                                 self.d, 1e-5, self._st()), "layernorm")
 
-    def _buf(self, name, rows, cols):
-        key = (name, rows, cols)
+    def _buf(self, name, rows, cols, chain=0):
+        key = (name, rows, cols, chain)
         if key not in self._bufs:
             self._bufs[key] = torch.empty((rows, cols), dtype=torch.float16, device=self.device)
         return self._bufs[key]
@@ -188,62 +200,67 @@ class WhisperDecoding:
         self.seq_len.zero_()
 
     # ---- one pass over the decoder stack for `rows` query rows ----------------------------------------------
-    def _stack(self, x, rows, s_q, context, input_lengths=None):
+    def _stack(self, x, rows, s_q, context, input_lengths=None, b0=0, nb=None, chain=0):
+        """x [rows, d] are the rows of the batch elements [b0, b0 + nb) (nb * s_q == rows)."""
         d, H, Dh = self.d, self.H, self.Dh
-        h = self._buf("h", rows, d)
-        qkv = self._buf("qkv", rows, 3 * d)
-        ctx = self._buf("ctx", rows, d)
-        q = self._buf("q", rows, d)
-        u = self._buf("u", rows, 4 * d)
+        nb = self.B if nb is None else nb
+        ws = self.ws if chain == 0 else self._chain_ws[chain - 1]
+        h = self._buf("h", rows, d, chain)
+        qkv = self._buf("qkv", rows, 3 * d, chain)
+        ctx = self._buf("ctx", rows, d, chain)
+        q = self._buf("q", rows, d, chain)
+        u = self._buf("u", rows, 4 * d, chain)
         st = self._st()
         main = torch.cuda.current_stream(self.device)
-        prefetch = self.prefetch_cross_kv and not context and self._side is not None
+        prefetch = self.prefetch_cross_kv and not context and self._side is not None and self.n_chains == 1
         if prefetch:
             self._side.wait_stream(main)
             self._prefetch(0)
         for i, lay in enumerate(self.layers):
             if self.fuse_ln:
-                self._gemm_ln(x, lay["attn_ln"], rows, lay["qkv"], qkv)
+                self._gemm_ln(x, lay["attn_ln"], rows, lay["qkv"], qkv, ws=ws)
             else:
                 self._ln(x, lay["attn_ln"], h, rows)
-                self._gemm(h, rows, lay["qkv"], qkv)
+                self._gemm(h, rows, lay["qkv"], qkv, ws=ws)
+            kv_i = self.self_kv[i] if nb == self.B else self.self_kv[i][b0:b0 + nb]
+            ckv_i = self.cross_kv[i] if nb == self.B else self.cross_kv[i][b0:b0 + nb]
             if context:
                 rc = self.lib.b200_attention_context(
                     qkv.data_ptr(), input_lengths.data_ptr() if input_lengths is not None else None, ctx.data_ptr(),
-                    self.self_kv[i].data_ptr(), lay["kv_oq"].data_ptr(), self.B, s_q, H, Dh, self.Smax, 1, 1.0, st)
+                    kv_i.data_ptr(), lay["kv_oq"].data_ptr(), nb, s_q, H, Dh, self.Smax, 1, 1.0, st)
                 _lib.check(rc, "attention_context")
             else:
                 p = _lib.MmhaParams()
                 p.qkv, p.qkv_bias, p.out = qkv.data_ptr(), None, ctx.data_ptr()
-                p.kv_cache = self.self_kv[i].data_ptr()
-                p.sequence_lengths = self.seq_len.data_ptr()
+                p.kv_cache = kv_i.data_ptr()
+                p.sequence_lengths = self.seq_len[b0:b0 + nb].data_ptr()
                 p.masked_tokens = None
                 p.kv_scale_orig_quant = lay["kv_oq"].data_ptr()
                 p.kv_scale_quant_orig = lay["kv_qo"].data_ptr()
-                p.batch_size, p.num_heads, p.head_size = self.B, H, Dh
+                p.batch_size, p.num_heads, p.head_size = nb, H, Dh
                 p.max_seq_len, p.past_kv_length, p.int8_kv_cache, p.q_scaling = self.Smax, 0, 1, 1.0
                 _lib.check(self.lib.b200_mmha_generation(ctypes.byref(p), st), "mmha_generation")
-            self._gemm(ctx, rows, lay["attn_out"], x, residual=x)
+            self._gemm(ctx, rows, lay["attn_out"], x, residual=x, ws=ws)
             if self.fuse_ln:
-                self._gemm_ln(x, lay["cross_ln"], rows, lay["cross_q"], q)
+                self._gemm_ln(x, lay["cross_ln"], rows, lay["cross_q"], q, ws=ws)
             else:
                 self._ln(x, lay["cross_ln"], h, rows)
-                self._gemm(h, rows, lay["cross_q"], q)
-            rc = self.lib.b200_cross_attention(q.data_ptr(), self.cross_kv[i].data_ptr(), lay["ckv_qo"].data_ptr(),
-                                               ctx.data_ptr(), rows, s_q, H, Dh, self.S_enc, 1, self.ws.data_ptr(),
-                                               self.ws.numel(), st)
+                self._gemm(h, rows, lay["cross_q"], q, ws=ws)
+            rc = self.lib.b200_cross_attention(q.data_ptr(), ckv_i.data_ptr(), lay["ckv_qo"].data_ptr(),
+                                               ctx.data_ptr(), rows, s_q, H, Dh, self.S_enc, 1, ws.data_ptr(),
+                                               ws.numel(), st)
             _lib.check(rc, "cross_attention")
             if prefetch and i + 1 < self.L:
                 # layer i's cross-KV is dead now: start pulling layer i+1's while the MLP and the next self-attention run
                 self._side.wait_stream(main)
                 self._prefetch(i + 1)
-            self._gemm(ctx, rows, lay["cross_out"], x, residual=x)
+            self._gemm(ctx, rows, lay["cross_out"], x, residual=x, ws=ws)
             if self.fuse_ln:
-                self._gemm_ln(x, lay["mlp_ln"], rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF)
+                self._gemm_ln(x, lay["mlp_ln"], rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF, ws=ws)
             else:
                 self._ln(x, lay["mlp_ln"], h, rows)
-                self._gemm(h, rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF)
-            self._gemm(u, rows, lay["fc2"], x, residual=x)
+                self._gemm(h, rows, lay["fc1"], u, act=_lib.ACT_GELU_ERF, ws=ws)
+            self._gemm(u, rows, lay["fc2"], x, residual=x, ws=ws)
         if prefetch:
             main.wait_stream(self._side)
         return x
@@ -288,7 +305,18 @@ class WhisperDecoding:
         _lib.check(self.lib.b200_embed_tokens_fp16(self.tokens.data_ptr(), self.seq_len.data_ptr(),
                                                    self.tok_emb.data_ptr(), self.pos_emb.data_ptr(), x.data_ptr(), B,
                                                    self.d, self.V, self.Smax, self._st()), "embed")
-        self._stack(x, B, 1, context=False)
+        if self.n_chains == 1:
+            self._stack(x, B, 1, context=False)
+        else:
+            nb = B // self.n_chains
+            main = torch.cuda.current_stream(self.device)
+            for c, s_c in enumerate(self._chain_streams, start=1):
+                s_c.wait_stream(main)  # fork after the embedding
+                with torch.cuda.stream(s_c):
+                    self._stack(x[c * nb:(c + 1) * nb], nb, 1, context=False, b0=c * nb, nb=nb, chain=c)
+            self._stack(x[:nb], nb, 1, context=False, b0=0, nb=nb, chain=0)
+            for s_c in self._chain_streams:
+                main.wait_stream(s_c)  # join before the (whole-batch) logits
         self._head(x, B, self.logits, self.next_tokens)
         self.lib.b200_set_static_kv_hint(0)
         self.seq_len.add_(1)

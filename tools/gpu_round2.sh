@@ -32,8 +32,8 @@ for fam in "$@"; do
     benchvar) echo "=== bench variants (PDL x cross-KV L2 prefetch)" | tee -a gpurun_out/summary.txt
        IFS=";" read -ra VARS <<< "${BENCH_VARS:-0 C 1 rowhead;0 A 1 rowhead;0 C 1 split;0 E 1 split;0 D 1 split}"; for cfg in "${VARS[@]}"; do
          set -- $cfg
-         B200_FUSE_LN=$1 B200_XA_CFG=$2 B200_STATIC_KV=$3 B200_XA_MODE=${4:-auto} timeout 600 python bench.py --steps 64 --warmup 4 --no-cpu-baseline > gpurun_out/bench_var.log 2>&1
-         echo "fuse_ln=$1 xa_cfg=$2 static_kv=$3 xa_mode=${4:-auto}: $(grep -o '"value": [0-9.]*' gpurun_out/bench_var.log | head -1) $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench_var.log | head -1) $(grep -o '"frac": [0-9.]*' gpurun_out/bench_var.log | head -1) $(tail -n 2 gpurun_out/bench_var.log | grep -v '^{' | cut -c1-200)" | tee -a gpurun_out/summary.txt
+         B200_FUSE_LN=$1 B200_XA_CFG=$2 B200_STATIC_KV=$3 B200_XA_MODE=${4:-auto} B200_CHAINS=${5:-1} timeout 600 python bench.py --steps 64 --warmup 4 --no-cpu-baseline > gpurun_out/bench_var.log 2>&1
+         echo "fuse_ln=$1 xa_cfg=$2 static_kv=$3 xa_mode=${4:-auto} chains=${5:-1}: $(grep -o '"value": [0-9.]*' gpurun_out/bench_var.log | head -1) $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench_var.log | head -1) $(grep -o '"frac": [0-9.]*' gpurun_out/bench_var.log | head -1) $(tail -n 2 gpurun_out/bench_var.log | grep -v '^{' | cut -c1-200)" | tee -a gpurun_out/summary.txt
        done;;
     ncufull) echo "=== ncu full" | tee -a gpurun_out/summary.txt
        timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:cross_attention -c 2 \

@@ -1,6 +1,9 @@
 """Prints the phase timeline (SM cycles) of CTA (0,0,0) of the tcgen05 weight-only GEMM for the decode shapes."""
 import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+os.environ["B200_TC_DEBUG"] = "1"  # the stamps only exist in a debug build of the library
+import importlib
+importlib.import_module("eddie-wang-hackathon2023_b200._build").build()
 import torch
 import b200_whisper as bw
 from b200_whisper import _lib

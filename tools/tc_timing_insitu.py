@@ -4,6 +4,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+os.environ["B200_TC_DEBUG"] = "1"  # the stamps only exist in a debug build of the library
+import importlib
+importlib.import_module("eddie-wang-hackathon2023_b200._build").build()
 import torch
 
 import bench
