@@ -261,28 +261,38 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
     char* kc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 0) * H + h) * Smax * kDh * esz;
     char* vc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 1) * H + h) * Smax * kDh * esz;
 
-    // ---- speculative first pass: rows [0, 8*NIT) of K and V (clamped to the cache capacity) ----
-    // (only when the caller promised that the cache is not written by the kernel right before this one)
-    KvChunk<INT8> kreg[NIT], vreg[NIT];
+    // ---- speculative first pass: rows [0, 8*NIT) of K and V (clamped to the cache capacity), converted to fp16
+    // registers, plus the length and the scales -- all of it BEFORE the dependency wait when the caller promised that
+    // these are not written by the kernel right before this one (b200_set_static_kv_hint).  After the wait only the
+    // dot products, the softmax and the output remain. ----
+    __half2 kw[NIT][8], vw[NIT][8];
     grid_dep_launch_dependents();
     if (!early_kv)
         grid_dep_wait();
-#pragma unroll
-    for (int it = 0; it < NIT; ++it)
     {
-        const int key = min(it * 8 + kl, Smax - 1);
-        kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
-        vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
+        KvChunk<INT8> kreg[NIT], vreg[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            const int key = min(it * 8 + kl, Smax - 1);
+            kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
+            vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+        {
+            kreg[it].unpack(kw[it]);
+            vreg[it].unpack(vw[it]);
+        }
     }
-    if (early_kv)
-        grid_dep_wait(); // qkv (and the lengths) come from the previous kernels
-
     int tlen = p.sequence_lengths ? p.sequence_lengths[b] : p.past_kv_length;
     tlen = min(tlen, Smax - 1);
     const float inv_sqrt_dh = 1.f / (sqrtf((float) kDh) * p.q_scaling); // gptAttentionCommon.cpp:163
     const float s_qo = INT8 ? p.kv_scale_quant_orig[0] : 1.f;
     const float s_oq = INT8 ? p.kv_scale_orig_quant[0] : 1.f;
     const float sscale = s_qo * inv_sqrt_dh;
+    if (early_kv)
+        grid_dep_wait(); // qkv comes from the previous kernel
     const int* mask = p.masked_tokens ? p.masked_tokens + (size_t) b * Smax : nullptr;
 
     const __half* qkv = static_cast<const __half*>(p.qkv) + (size_t) b * 3 * hidden + h * kDh + chunk * 16;
@@ -323,6 +333,7 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
     {
         if (k0 > 0)
         {
+            KvChunk<INT8> kreg[NIT], vreg[NIT];
 #pragma unroll
             for (int it = 0; it < NIT; ++it)
             {
@@ -330,31 +341,39 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
                 kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
                 vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
             }
+#pragma unroll
+            for (int it = 0; it < NIT; ++it)
+            {
+                kreg[it].unpack(kw[it]);
+                vreg[it].unpack(vw[it]);
+            }
         }
         float sc[NIT];
         float m_new = m_run;
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
         {
-            const int key = k0 + it * 8 + kl;
-            __half2 w[8];
-            kreg[it].unpack(w);
-            __half2 h0 = __hmul2(q2[0], w[0]);
-            __half2 h1 = __hmul2(q2[4], w[4]);
-            h0 = __hfma2(q2[1], w[1], h0);
-            h1 = __hfma2(q2[5], w[5], h1);
-            h0 = __hfma2(q2[2], w[2], h0);
-            h1 = __hfma2(q2[6], w[6], h1);
-            h0 = __hfma2(q2[3], w[3], h0);
-            h1 = __hfma2(q2[7], w[7], h1);
-            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-            float sv = (f0.x + f0.y) + (f1.x + f1.y);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-            const bool valid = key < tlen && !(mask && mask[key]); // masked keys: probability 0, not in the max
-            sv = valid ? sv * sscale : -FLT_MAX;
-            sc[it] = sv;
-            m_new = fmaxf(m_new, sv);
+            sc[it] = -FLT_MAX;
+            if (k0 + it * 8 < tlen) // warp-uniform: groups of 8 keys beyond the length cost nothing
+            {
+                const int key = k0 + it * 8 + kl;
+                __half2 h0 = __hmul2(q2[0], kw[it][0]);
+                __half2 h1 = __hmul2(q2[4], kw[it][4]);
+                h0 = __hfma2(q2[1], kw[it][1], h0);
+                h1 = __hfma2(q2[5], kw[it][5], h1);
+                h0 = __hfma2(q2[2], kw[it][2], h0);
+                h1 = __hfma2(q2[6], kw[it][6], h1);
+                h0 = __hfma2(q2[3], kw[it][3], h0);
+                h1 = __hfma2(q2[7], kw[it][7], h1);
+                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                float sv = (f0.x + f0.y) + (f1.x + f1.y);
+                sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+                sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+                const bool valid = key < tlen && !(mask && mask[key]); // masked keys: probability 0, not in the max
+                sv = valid ? sv * sscale : -FLT_MAX;
+                sc[it] = sv;
+                m_new = fmaxf(m_new, sv);
+            }
         }
         m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 4));
         m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
@@ -372,16 +391,14 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
         {
-            if (sc[it] == -FLT_MAX)
-                continue; // invalid / masked key (also keeps stale cache bits out of the fp16 path)
+            if (k0 + it * 8 >= tlen || sc[it] == -FLT_MAX)
+                continue; // beyond the length / masked key (also keeps stale cache bits out of the fp16 path)
             const float e = __expf(sc[it] - m_new);
             l_run += e;
             const __half2 p2 = __float2half2_rn(e);
-            __half2 w[8];
-            vreg[it].unpack(w);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                o2[i] = __hfma2(p2, w[i], o2[i]);
+                o2[i] = __hfma2(p2, vw[it][i], o2[i]);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)

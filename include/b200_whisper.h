@@ -56,10 +56,11 @@ const char* b200_last_error(void);
 /* Programmatic dependent launch for the hot-path kernels (default on; env B200_PDL=0 disables): each kernel may start
  * while its predecessor on the stream drains and waits (griddepcontrol.wait) before touching the predecessor's output. */
 int b200_set_pdl(int enabled);
-/* Promise that the KV caches read by b200_mmha_generation / b200_cross_attention are NOT written by the kernel
- * launched right before them on the stream (true inside a decoder step: a cache row is written one step before it
- * is read).  With the hint the attention kernels stream the cache before griddepcontrol.wait, so the bytes are in
- * flight while the preceding projection finishes.  Default off (always safe). */
+/* Promise that the KV caches, sequence_lengths and KV scales read by b200_mmha_generation / b200_cross_attention are
+ * NOT written by the kernel launched right before them on the stream (true inside a decoder step: a cache row is
+ * written one step before it is read, the lengths are bumped after the step's last kernel).  With the hint the
+ * attention kernels fetch (and, for self-attention, convert) the cache before griddepcontrol.wait, so only the dot
+ * products remain once the preceding projection has finished.  Default off (always safe). */
 int b200_set_static_kv_hint(int enabled);
 /* Fire-and-forget prefetch of [ptr, ptr+bytes) into L2 (cp.async.bulk.prefetch.L2); ptr 16-byte aligned. */
 int b200_l2_prefetch(const void* ptr, size_t bytes, b200_stream_t stream);
