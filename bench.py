@@ -242,8 +242,8 @@ def main():
     launches_before = lib.b200_launch_count()
     if not args.no_graph:
         dec.capture()
-    # capture() runs the step body twice (one warm-up, one captured)
-    launches_per_step = (lib.b200_launch_count() - launches_before) // 2 if not args.no_graph else None
+    # capture() runs the step body three times (warm-up, device-resident graph, host-I/O graph)
+    launches_per_step = (lib.b200_launch_count() - launches_before) // 3 if not args.no_graph else None
     torch.cuda.synchronize(dev)
 
     def barrier():

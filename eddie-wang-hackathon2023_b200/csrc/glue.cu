@@ -9,6 +9,7 @@
 
 namespace b200
 {
+int* tc_counter_slot(int needed);
 
 // y = (x - mean) * rsqrt(var + eps) * gamma + beta, statistics in fp32 (torch_model.py:25-27 casts to float).
 // one CTA (128 threads) per row; cols % 8 == 0; row cached in registers (cols <= 8192).
@@ -192,61 +193,73 @@ __global__ void __launch_bounds__(256) logits_simt_kernel(const __half* __restri
     }
 }
 
-// argmax over fp32 logits, first index on ties (torch.argmax).  grid = rows, 1024 threads.
-__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int* __restrict__ next_token, int vocab)
+// argmax over fp32 logits, first index on ties (torch.argmax).  grid (parts, rows), 256 threads: every CTA scans a
+// slice of the row with 8 independent loads in flight per thread, publishes (value, index) as one order-preserving
+// 64-bit key with atomicMax, and the last CTA of a row to arrive writes the token and resets the scratch words.
+__device__ __forceinline__ unsigned long long argmax_key(float x, int idx)
+{
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t u = (b & 0x80000000u) ? ~b : (b | 0x80000000u); // monotone in x
+    return ((unsigned long long) u << 32) | (unsigned long long) (0xffffffffu - (uint32_t) idx); // ties: lowest index wins
+}
+
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int* __restrict__ next_token, int vocab,
+    unsigned long long* __restrict__ packed, int* __restrict__ counters)
 {
     grid_dep_wait();
     grid_dep_launch_dependents();
-    const int r = blockIdx.x;
+    const int r = blockIdx.y, parts = gridDim.x;
     const float* lr = logits + (size_t) r * vocab;
+    const int per = (vocab + parts - 1) / parts;
+    const int v0 = blockIdx.x * per, v1 = min(vocab, v0 + per);
     float best = -FLT_MAX;
     int bi = 0x7fffffff;
-    for (int v = threadIdx.x; v < vocab; v += blockDim.x)
+    for (int base = v0 + threadIdx.x; base < v1; base += 8 * 256)
     {
-        const float x = lr[v];
-        if (x > best || (x == best && v < bi))
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
         {
-            best = x;
-            bi = v;
+            const int v = base + j * 256;
+            x[j] = v < v1 ? __ldcs(lr + v) : -FLT_MAX;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+            const int v = base + j * 256;
+            if (x[j] > best || (x[j] == best && v < bi))
+            {
+                best = x[j];
+                bi = v;
+            }
         }
     }
-    __shared__ float sb[32];
-    __shared__ int si[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long key = argmax_key(best, bi);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1)
     {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi))
-        {
-            best = ob;
-            bi = oi;
-        }
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+        key = ok > key ? ok : key;
     }
+    __shared__ unsigned long long sk[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0)
-    {
-        sb[warp] = best;
-        si[warp] = bi;
-    }
+        sk[warp] = key;
     __syncthreads();
-    if (warp == 0)
+    if (threadIdx.x == 0)
     {
-        best = sb[lane];
-        bi = si[lane];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1)
+        for (int w = 1; w < 8; ++w)
+            key = sk[w] > key ? sk[w] : key;
+        atomicMax(&packed[r], key);
+        __threadfence();
+        if (atomicAdd(&counters[r], 1) == parts - 1)
         {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi))
-            {
-                best = ob;
-                bi = oi;
-            }
+            __threadfence();
+            const unsigned long long win = atomicExch(&packed[r], 0ull); // read + reset for the next launch
+            next_token[r] = (int) (0xffffffffu - (uint32_t) (win & 0xffffffffull));
+            counters[r] = 0;
         }
-        if (lane == 0)
-            next_token[r] = bi;
     }
 }
 
@@ -377,7 +390,15 @@ extern "C" int b200_logits_argmax_fp16(const void* x, const void* emb, void* log
     }
     if (next_token != nullptr)
     {
-        B200_LAUNCH(argmax_kernel, dim3(rows), dim3(1024), 0, st, static_cast<const float*>(lg), next_token, vocab);
+        // scratch: one 64-bit key and one arrival counter per row (library owned, self-resetting)
+        B200_REQUIRE(rows <= 4096, B200_ERR_UNSUPPORTED, "argmax: %d rows exceed the scratch slot", rows);
+        int* slot = tc_counter_slot(3 * rows + 2);
+        B200_REQUIRE(slot != nullptr, B200_ERR_CUDA, "argmax: no scratch slot");
+        unsigned long long* packed = reinterpret_cast<unsigned long long*>(slot);
+        int* counters = slot + 2 * rows;
+        const int parts = rows >= 64 ? 2 : 8;
+        B200_LAUNCH(argmax_kernel, dim3(parts, rows), dim3(256), 0, st, static_cast<const float*>(lg), next_token, vocab, packed,
+            counters);
     }
     return B200_OK;
 }

@@ -124,6 +124,7 @@ class WhisperDecoding:
                        self.lib.b200_cross_attention_workspace_bytes(max_rows, self.H, self.Dh, self.S_enc), 1 << 20)
         self.ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         self.graph = None
+        self.graph_host = None
         # Independent utterances can be stepped as several interleaved chains of kernels (each on its own stream, all
         # inside the same CUDA graph): while one chain sits in the dependency latency between two small GEMMs, or
         # streams its cross-KV cache, the other chains' kernels fill the SMs.  Weights are read once per chain (the
@@ -342,6 +343,17 @@ class WhisperDecoding:
         self.seq_len.copy_(saved)
         self.tokens.copy_(saved_tokens)
         self.graph = g
+        # the same step with its host traffic inside the graph: pinned token ids -> device, step, next ids -> pinned.
+        # step_host() then costs one graph launch and one stream synchronize.
+        gh = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gh):
+            self.tokens.copy_(self._pinned_in, non_blocking=True)
+            self._step_body()
+            self._pinned_out.copy_(self.next_tokens, non_blocking=True)
+        torch.cuda.synchronize(self.device)
+        self.seq_len.copy_(saved)
+        self.tokens.copy_(saved_tokens)
+        self.graph_host = gh
         return g
 
     def step(self):
@@ -354,6 +366,11 @@ class WhisperDecoding:
 
     def step_host(self, tokens_host=None):
         """End-to-end step with HOST buffers: pinned token ids in -> pinned next-token ids out."""
+        if tokens_host is not None and getattr(self, "graph_host", None) is not None:
+            self._pinned_in.copy_(torch.as_tensor(tokens_host, dtype=torch.int32))
+            self.graph_host.replay()
+            torch.cuda.current_stream(self.device).synchronize()
+            return self._pinned_out
         if tokens_host is not None:
             self._pinned_in.copy_(torch.as_tensor(tokens_host, dtype=torch.int32))
             self.tokens.copy_(self._pinned_in, non_blocking=True)
