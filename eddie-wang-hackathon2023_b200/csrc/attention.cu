@@ -236,45 +236,43 @@ struct KvChunk<false>
 };
 
 // =====================================================================================================
-// Generation step.  One WARP per (batch, head): no shared memory, no CTA barrier.  Lane geometry: 4 lanes x 16 dims
-// per key, 8 keys per warp instruction (512 contiguous cache bytes for int8).  Keys are processed in passes of
-// 8 * NIT with an online softmax; the K and V rows of the first pass are requested BEFORE griddepcontrol.wait (cache
-// rows below the current length were written by earlier steps), so under programmatic dependent launch they are in
-// registers when the qkv projection of this step lands.  The first version (CTA per (b, h), three block-wide
-// reductions, loads issued after the dependency) was pure latency: 6 us for 350 KB.
+// Generation step.  A PAIR of warps per (batch, head), no block-wide barrier except the final merge.  Lane geometry:
+// 4 lanes x 16 dims per key, 8 keys per warp instruction (512 contiguous cache bytes for int8); the two warps of a
+// pair take alternating groups of 8 keys, so a pass of the pair covers 16 * NIT keys.  Under programmatic dependent
+// launch everything that does not depend on this step's projection happens BEFORE griddepcontrol.wait when the
+// caller promised a static cache (b200_set_static_kv_hint): the first pass of K and V is fetched and converted to
+// fp16 registers, the length and the scales are read.  After the wait only q.k, the softmax, p.v and the merge of
+// the two halves (shared memory) remain.  64 fp16 registers of K/V per thread keep the CTA small enough to share an
+// SM with a GEMM CTA of the preceding projection.
 // =====================================================================================================
-constexpr int kMmhaWarps = 8; // (4 warps per CTA, 80 CTAs, measured slower inside the captured step)
+constexpr int kMmhaWarps = 8; // 4 (batch, head) pairs per CTA
 
 template <bool INT8>
-__global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const b200_mmha_params p, const int early_kv)
+__global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(const b200_mmha_params p, const int early_kv)
 {
-    constexpr int NIT = INT8 ? 8 : 4; // keys per pass = 8 * NIT (same register budget for both cache types)
+    constexpr int NIT = INT8 ? 4 : 2; // key groups of 8 per warp and pass
+    constexpr int kPart = kDh + 4;    // m, l, 2 pad, o[64]
+    __shared__ __align__(16) float parts[kMmhaWarps / 2][kPart];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = lane & 3, kl = lane >> 2;
+    const int half = warp & 1, pair = warp >> 1;
     const int H = p.num_heads, Smax = p.max_seq_len;
     const int hidden = H * kDh;
-    const int gw = blockIdx.x * kMmhaWarps + warp;
-    if (gw >= p.batch_size * H)
-        return;
-    const int b = gw / H, h = gw - b * H;
+    const int gp = blockIdx.x * (kMmhaWarps / 2) + pair;
+    const bool active = gp < p.batch_size * H;
+    const int b = active ? gp / H : 0, h = active ? gp - b * H : 0;
     const size_t esz = INT8 ? 1 : 2;
     char* kc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 0) * H + h) * Smax * kDh * esz;
     char* vc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 1) * H + h) * Smax * kDh * esz;
 
-    // ---- speculative first pass: rows [0, 8*NIT) of K and V (clamped to the cache capacity), converted to fp16
-    // registers, plus the length and the scales -- all of it BEFORE the dependency wait when the caller promised that
-    // these are not written by the kernel right before this one (b200_set_static_kv_hint).  After the wait only the
-    // dot products, the softmax and the output remain. ----
     __half2 kw[NIT][8], vw[NIT][8];
-    grid_dep_launch_dependents();
-    if (!early_kv)
-        grid_dep_wait();
+    auto fetch = [&](int k0)
     {
         KvChunk<INT8> kreg[NIT], vreg[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
         {
-            const int key = min(it * 8 + kl, Smax - 1);
+            const int key = min(k0 + (2 * it + half) * 8 + kl, Smax - 1);
             kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
             vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
         }
@@ -284,7 +282,11 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
             kreg[it].unpack(kw[it]);
             vreg[it].unpack(vw[it]);
         }
-    }
+    };
+    grid_dep_launch_dependents();
+    if (!early_kv)
+        grid_dep_wait();
+    fetch(0);
     int tlen = p.sequence_lengths ? p.sequence_lengths[b] : p.past_kv_length;
     tlen = min(tlen, Smax - 1);
     const float inv_sqrt_dh = 1.f / (sqrtf((float) kDh) * p.q_scaling); // gptAttentionCommon.cpp:163
@@ -299,8 +301,11 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
     const __half* bias = p.qkv_bias ? static_cast<const __half*>(p.qkv_bias) + h * kDh + chunk * 16 : nullptr;
     __half qh[16], kh[16], vh[16];
     load16_half(qkv, bias, qh);
-    load16_half(qkv + hidden, bias ? bias + hidden : nullptr, kh);
-    load16_half(qkv + 2 * hidden, bias ? bias + 2 * hidden : nullptr, vh);
+    if (half == 0)
+    {
+        load16_half(qkv + hidden, bias ? bias + hidden : nullptr, kh);
+        load16_half(qkv + 2 * hidden, bias ? bias + 2 * hidden : nullptr, vh);
+    }
     __half2 q2[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -308,20 +313,26 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
         q2[2 * i] = __halves2half2(qh[4 * i], qh[4 * i + 2]);
         q2[2 * i + 1] = __halves2half2(qh[4 * i + 1], qh[4 * i + 3]);
     }
-    // append this step's K and V (lane group 0 writes K, group 1 writes V; 16 dims per lane)
-    if (kl == 0)
-        store16<INT8>(kc, (size_t) tlen * kDh + chunk * 16, s_oq, kh);
-    else if (kl == 1)
-        store16<INT8>(vc, (size_t) tlen * kDh + chunk * 16, s_oq, vh);
-
-    // current token: unquantized k and v (Template.h:1503,1517,1920,1933)
-    float s_cur = 0.f;
+    // warp 0 of the pair: append this step's K and V (lane group 0 writes K, group 1 writes V; 16 dims per lane) and
+    // score the current token with its unquantized k (Template.h:1503,1517,1920,1933)
+    float s_cur = -FLT_MAX;
+    if (half == 0)
+    {
+        if (active)
+        {
+            if (kl == 0)
+                store16<INT8>(kc, (size_t) tlen * kDh + chunk * 16, s_oq, kh);
+            else if (kl == 1)
+                store16<INT8>(vc, (size_t) tlen * kDh + chunk * 16, s_oq, vh);
+        }
+        float sc0 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        s_cur = fmaf(__half2float(qh[i]), __half2float(kh[i]), s_cur);
-    s_cur += __shfl_xor_sync(0xffffffffu, s_cur, 1);
-    s_cur += __shfl_xor_sync(0xffffffffu, s_cur, 2);
-    s_cur *= inv_sqrt_dh;
+        for (int i = 0; i < 16; ++i)
+            sc0 = fmaf(__half2float(qh[i]), __half2float(kh[i]), sc0);
+        sc0 += __shfl_xor_sync(0xffffffffu, sc0, 1);
+        sc0 += __shfl_xor_sync(0xffffffffu, sc0, 2);
+        s_cur = sc0 * inv_sqrt_dh;
+    }
 
     float m_run = s_cur, l_run = 0.f; // l_run: this lane group's share of the cached keys' denominator
     float o[16];                      // in units of the dequant scale (integer V values)
@@ -329,34 +340,20 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
     for (int i = 0; i < 16; ++i)
         o[i] = 0.f;
 
-    for (int k0 = 0; k0 < tlen; k0 += 8 * NIT)
+    for (int k0 = 0; k0 < tlen; k0 += 16 * NIT)
     {
         if (k0 > 0)
-        {
-            KvChunk<INT8> kreg[NIT], vreg[NIT];
-#pragma unroll
-            for (int it = 0; it < NIT; ++it)
-            {
-                const int key = min(k0 + it * 8 + kl, Smax - 1);
-                kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
-                vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
-            }
-#pragma unroll
-            for (int it = 0; it < NIT; ++it)
-            {
-                kreg[it].unpack(kw[it]);
-                vreg[it].unpack(vw[it]);
-            }
-        }
+            fetch(k0);
         float sc[NIT];
         float m_new = m_run;
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
         {
             sc[it] = -FLT_MAX;
-            if (k0 + it * 8 < tlen) // warp-uniform: groups of 8 keys beyond the length cost nothing
+            const int kg = k0 + (2 * it + half) * 8;
+            if (kg < tlen) // warp-uniform: groups of 8 keys beyond the length cost nothing
             {
-                const int key = k0 + it * 8 + kl;
+                const int key = kg + kl;
                 __half2 h0 = __hmul2(q2[0], kw[it][0]);
                 __half2 h1 = __hmul2(q2[4], kw[it][4]);
                 h0 = __hfma2(q2[1], kw[it][1], h0);
@@ -378,7 +375,7 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
         m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 4));
         m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
         m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 16));
-        const float corr = __expf(m_run - m_new);
+        const float corr = m_new == -FLT_MAX ? 1.f : __expf(m_run - m_new);
         m_run = m_new;
         l_run *= corr;
 #pragma unroll
@@ -391,7 +388,7 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
         {
-            if (k0 + it * 8 >= tlen || sc[it] == -FLT_MAX)
+            if (k0 + (2 * it + half) * 8 >= tlen || sc[it] == -FLT_MAX)
                 continue; // beyond the length / masked key (also keeps stale cache bits out of the fp16 path)
             const float e = __expf(sc[it] - m_new);
             l_run += e;
@@ -412,8 +409,6 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 4);
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 8);
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 16);
-    const float e_cur = __expf(s_cur - m_run);
-    const float inv_sum = __fdividef(1.f, l_run + e_cur + 1.e-6f); // Template.h:1756
 #pragma unroll
     for (int i = 0; i < 16; ++i)
     {
@@ -421,19 +416,43 @@ __global__ void __launch_bounds__(kMmhaWarps * 32) mmha_generation_kernel(const 
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        o[i] = v * s_qo;
+        o[i] = v;
     }
-    if (kl == 0)
+    // warp 1 of the pair hands its state to warp 0 through shared memory
+    float* pr = parts[pair];
+    if (half == 1 && kl == 0)
     {
         // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
-        __half* dst = static_cast<__half*>(p.out) + (size_t) b * hidden + h * kDh + chunk * 16;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(pr + 4 + chunk * 16 + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        if (chunk == 0)
         {
-            dst[4 * j + 0] = __float2half_rn((o[4 * j + 0] + e_cur * __half2float(vh[4 * j + 0])) * inv_sum);
-            dst[4 * j + 2] = __float2half_rn((o[4 * j + 1] + e_cur * __half2float(vh[4 * j + 2])) * inv_sum);
-            dst[4 * j + 1] = __float2half_rn((o[4 * j + 2] + e_cur * __half2float(vh[4 * j + 1])) * inv_sum);
-            dst[4 * j + 3] = __float2half_rn((o[4 * j + 3] + e_cur * __half2float(vh[4 * j + 3])) * inv_sum);
+            pr[0] = m_run;
+            pr[1] = l_run;
+        }
+    }
+    __syncthreads();
+    if (half == 0 && active)
+    {
+        const float m1 = pr[0], l1 = pr[1];
+        const float m = fmaxf(m_run, m1); // m_run >= s_cur > -FLT_MAX
+        const float w0 = __expf(m_run - m), w1 = m1 == -FLT_MAX ? 0.f : __expf(m1 - m);
+        const float e_cur = __expf(s_cur - m);
+        const float inv_sum = __fdividef(1.f, l_run * w0 + l1 * w1 + e_cur + 1.e-6f); // Template.h:1756
+        if (kl == 0)
+        {
+            __half* dst = static_cast<__half*>(p.out) + (size_t) b * hidden + h * kDh + chunk * 16;
+            const float a0 = w0 * s_qo, a1 = w1 * s_qo;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const float4 q4 = *reinterpret_cast<const float4*>(pr + 4 + chunk * 16 + 4 * j);
+                dst[4 * j + 0] = __float2half_rn((o[4 * j + 0] * a0 + q4.x * a1 + e_cur * __half2float(vh[4 * j + 0])) * inv_sum);
+                dst[4 * j + 2] = __float2half_rn((o[4 * j + 1] * a0 + q4.y * a1 + e_cur * __half2float(vh[4 * j + 2])) * inv_sum);
+                dst[4 * j + 1] = __float2half_rn((o[4 * j + 2] * a0 + q4.z * a1 + e_cur * __half2float(vh[4 * j + 1])) * inv_sum);
+                dst[4 * j + 3] = __float2half_rn((o[4 * j + 3] * a0 + q4.w * a1 + e_cur * __half2float(vh[4 * j + 3])) * inv_sum);
+            }
         }
     }
 }
@@ -1113,7 +1132,7 @@ extern "C" int b200_mmha_generation(const b200_mmha_params* p, b200_stream_t str
     if (p->batch_size == 0)
         return B200_OK;
     B200_REQUIRE_DEVICE();
-    const dim3 grid((p->num_heads * p->batch_size + kMmhaWarps - 1) / kMmhaWarps);
+    const dim3 grid((p->num_heads * p->batch_size + kMmhaWarps / 2 - 1) / (kMmhaWarps / 2));
     if (p->int8_kv_cache)
         B200_LAUNCH(mmha_generation_kernel<true>, grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, static_kv_hint() ? 1 : 0);
     else
