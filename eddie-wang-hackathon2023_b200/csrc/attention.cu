@@ -245,7 +245,7 @@ struct KvChunk<false>
 // the two halves (shared memory) remain.  64 fp16 registers of K/V per thread keep the CTA small enough to share an
 // SM with a GEMM CTA of the preceding projection.
 // =====================================================================================================
-constexpr int kMmhaWarps = 8; // 4 (batch, head) pairs per CTA
+constexpr int kMmhaWarps = 4; // 2 (batch, head) pairs per CTA
 
 template <bool INT8>
 __global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(const b200_mmha_params p, const int early_kv)
