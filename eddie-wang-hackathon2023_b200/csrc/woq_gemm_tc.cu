@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace b200
 {
@@ -91,26 +92,6 @@ __device__ __forceinline__ long long global_timer_ns()
     } while (0)
 #endif
 
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_smem_addr, uint32_t cta_rank)
-{
-    uint32_t remote;
-    float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-    return v;
-}
 
 // bias / activation / residual with the reference's per-layer fp16 rounding (see epilogue_apply in common.cuh);
 // the residual value is passed in so callers can issue all residual loads before the dependent stores.
@@ -128,118 +109,8 @@ __device__ __forceinline__ __half finish_output(float acc, bool has_bias, float 
     return o;
 }
 
-// true in exactly one (converged) lane of the warp
-__device__ __forceinline__ bool elect_one_sync()
-{
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void tc_fence_before()
-{
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-
-__device__ __forceinline__ void tc_fence_after()
-{
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-
-__device__ __forceinline__ void tc_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-// D[tmem] (+)= A[tmem] * B[smem]   (kind::f16, fp32 accumulate)
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_st_x32(uint32_t taddr, const uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-        "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_ld_x16(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-        "[%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
 
 constexpr int kWTileBytes = 64 * 128; // 64 row pairs x 128 B = 128 columns x 64 k
-
-__host__ __device__ constexpr uint32_t tmem_cols_pow2(uint32_t c)
-{
-    return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
-}
-
-// K-major, 128B-swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-// start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_128B(=2)<<61
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
-{
-    return (uint64_t) ((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void tc_st_x16(uint32_t taddr, const uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_ld_x8(uint32_t taddr, uint32_t (&r)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-
-// remote (or own) shared-memory store that completes `bytes` on the destination CTA's mbarrier
-__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar)
-{
-    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
-                 "r"(__float_as_uint(v)), "r"(remote_mbar)
-                 : "memory");
-}
-
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank)
-{
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
-    return remote;
-}
 
 constexpr int kTcDequantWarps = 8;
 constexpr int kTcThreads = (kTcDequantWarps + 2) * 32; // + TMA producer warp + MMA/TMEM warp
@@ -936,18 +807,6 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     }
 }
 
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
 
 // =====================================================================================================
 // fp16 x fp16 -> fp32 "swap-AB" GEMM for the logits projection: out[m, v] = sum_k X[m, k] * E[v, k].
@@ -1121,6 +980,24 @@ int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uin
     CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
+    return B200_OK;
+}
+
+// 3-D variant with a traversal (element) stride on dimension 1: box1 counts tensor elements, so box1 / estride1 rows land
+// in shared memory (used by the strided Conv1d: every second time step).
+int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+    uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, uint32_t estride1,
+    CUtensorMapSwizzle swz)
+{
+    PFN_encodeTiled enc = get_encode();
+    B200_REQUIRE(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {dim0, dim1, dim2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {box0, box1, box2};
+    cuuint32_t estr[3] = {1, estride1, 1};
+    CUresult r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int) r);
     return B200_OK;
 }
 

@@ -117,10 +117,11 @@ def cross_kv_pack(k, v, kv_orig_quant_scale, num_heads, head_size, use_int8_kv_c
     return cache
 
 
-def conv1d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, activation=None):
+def conv1d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, activation=None, impl="tc"):
     """input [B, Cin, T] fp16, weight [Cout, Cin, k] or the reference's [Cout, Cin, k, 1] -> [B, Cout, Tout] fp16.
     `activation` ('gelu') is a B200 extension fused into the epilogue (the reference applies gelu as a separate layer,
-    T/tensorrt_llm/models/whisper/model.py:154-157)."""
+    T/tensorrt_llm/models/whisper/model.py:154-157).  impl: 'tc' = tcgen05 implicit GEMM (default), 'simt' = the
+    CUDA-core direct convolution (no workspace)."""
     if dilation != 1 or groups != 1:
         raise NotImplementedError("dilation / groups are not used by the Whisper stem")
     _need_cuda(input, weight)
@@ -133,8 +134,15 @@ def conv1d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, 
     t_out = (t_in + 2 * padding - ksize) // stride + 1
     out = torch.empty((B, cout, t_out), dtype=torch.float16, device=input.device)
     act = {None: _lib.ACT_NONE, "gelu": _lib.ACT_GELU_ERF, "gelu_tanh": _lib.ACT_GELU_TANH}[activation]
-    rc = lib.b200_conv1d_fp16(_lib.ptr(input.contiguous()), _lib.ptr(weight.contiguous()), _lib.ptr(bias),
-                              _lib.ptr(out), B, cin, cout, t_in, ksize, stride, padding, act, _lib.stream_ptr())
+    if impl == "simt":
+        rc = lib.b200_conv1d_fp16(_lib.ptr(input.contiguous()), _lib.ptr(weight.contiguous()), _lib.ptr(bias),
+                                  _lib.ptr(out), B, cin, cout, t_in, ksize, stride, padding, act, _lib.stream_ptr())
+    else:
+        ws = torch.empty((lib.b200_conv1d_workspace_bytes(B, cin, cout, t_in, ksize),), dtype=torch.uint8,
+                         device=input.device)
+        rc = lib.b200_conv1d_fp16_tc(_lib.ptr(input.contiguous()), _lib.ptr(weight.contiguous()), _lib.ptr(bias),
+                                     _lib.ptr(out), B, cin, cout, t_in, ksize, stride, padding, act, _lib.ptr(ws),
+                                     ws.numel(), _lib.stream_ptr())
     _lib.check(rc, "conv1d")
     return out
 

@@ -220,6 +220,15 @@ int b200_cross_kv_pack(const void* k, const void* v, void* cross_kv, const float
  * ---------------------------------------------------------------------------------------------- */
 int b200_conv1d_fp16(const void* x, const void* w, const void* bias, void* y, int batch_size, int c_in, int c_out,
     int t_in, int ksize, int stride, int pad, int activation, b200_stream_t stream);
+/* The same operator as an implicit GEMM on the tensor cores (tcgen05, TMEM accumulator): the weights are re-laid to
+ * [tap][Cout][Cin_pad] and the input is transposed to time-major [B][T][Cin_pad] inside the workspace (Cin_pad = Cin
+ * rounded up to 64), then every k-block's im2col tile is ONE 3-D TMA box whose row traversal stride is the convolution
+ * stride and whose out-of-bounds rows are the zero padding.  workspace: b200_conv1d_workspace_bytes(), 256-byte
+ * aligned.  ksize 1..8, stride 1 or 2. */
+size_t b200_conv1d_workspace_bytes(int batch_size, int c_in, int c_out, int t_in, int ksize);
+int b200_conv1d_fp16_tc(const void* x, const void* w, const void* bias, void* y, int batch_size, int c_in, int c_out,
+    int t_in, int ksize, int stride, int pad, int activation, void* workspace, size_t workspace_bytes,
+    b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Decoder-step glue (TensorRT-native layers in the reference:

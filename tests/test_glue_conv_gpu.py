@@ -59,13 +59,15 @@ def test_logits_argmax(policy, rows, cols, vocab):
 @pytest.mark.parametrize("B,cin,cout,T,stride", [(1, 80, 1280, 3000, 1), (2, 80, 384, 3000, 1), (1, 1280, 1280, 3000, 2),
                                                  (2, 128, 128, 192, 2), (1, 80, 128, 191, 1), (3, 48, 72, 77, 2)])
 @pytest.mark.parametrize("act", [None, "gelu"])
-def test_conv1d(B, cin, cout, T, stride, act):
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_conv1d(B, cin, cout, T, stride, act, impl):
     from b200_whisper.functional import conv1d
     torch.manual_seed(cin + T)
     x = torch.randn((B, cin, T), device="cuda").clamp(-1, 1).half()
     w = (torch.randn((cout, cin, 3), device="cuda") / (3 * cin) ** 0.5).half()
     b = (torch.randn((cout,), device="cuda") * 0.02).half()
-    y = conv1d(x, w.unsqueeze(-1), b, stride=stride, padding=1, activation=act)  # reference weight shape [out,in,k,1]
+    # reference weight shape [out,in,k,1]; impl: tcgen05 implicit GEMM / CUDA-core direct convolution
+    y = conv1d(x, w.unsqueeze(-1), b, stride=stride, padding=1, activation=act, impl=impl)
     ref = F.conv1d(x.float(), w.float(), b.float(), stride=stride, padding=1)
     if act:
         ref = F.gelu(ref)
