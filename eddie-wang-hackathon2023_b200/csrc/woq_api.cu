@@ -1,8 +1,8 @@
 // woq_api.cu -- C ABI entry points of the weight-only matmul and their dispatch.
 // Mirrors WeightOnlyQuantMatmulPlugin::enqueue's m == 1 -> GEMV / else -> tensor-core GEMM split
 // (T/cpp/tensorrt_llm/plugins/weightOnlyQuantMatmulPlugin/weightOnlyQuantMatmulPlugin.cpp:162-222), with the
-// B200 crossover: SIMT GEMV for M <= 4, tcgen05 for M > 4 (CUDA cores cannot sustain 16 MACs per weight byte at
-// HBM rate).
+// B200 crossover (measured): the tcgen05 kernel for every M (its weight stream and dequant run ahead of the
+// dependency wait, which a register-resident SIMT GEMV cannot do), the SIMT GEMV only for a single row with deep K.
 #include "common.cuh"
 
 namespace b200
@@ -92,7 +92,9 @@ static int woq_dispatch(const void* A, int M, int K, const int8_t* Wproc, const 
     if (M == 0)
         return B200_OK; // empty batch: nothing to do (the reference would launch an empty grid)
     B200_REQUIRE_DEVICE();
-    const bool simt = (g_policy == 1) || (g_policy == 0 && M <= 4);
+    // measured crossover (tools/gemv_crossover.py, graph replays over 32 weight sets): the tcgen05 kernel wins from
+    // M = 1 on every decoder shape but the deep-K single row (K = 5120, M = 1: 4.3 vs 5.1 us)
+    const bool simt = (g_policy == 1) || (g_policy == 0 && M == 1 && K >= 4096);
     const bool fold = ln_gamma != nullptr && fold_c1s != nullptr && fold_c2 != nullptr && !simt && woq_tc_can_fold_ln(M, N, K);
     if (!fold)
     {

@@ -22,6 +22,9 @@ def build(force=False):
     if os.path.isdir("/root/reference/tensorrt_llm_july-release-v1") and (
             force or not os.path.exists(os.path.join(_HERE, "_ref", "libref_quant.so"))):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference") and not os.path.exists(os.path.join(_HERE, "_ref", "libref_gpu.so")):
+        # the reference's GEMV + MMHA kernels for sm_100a (about 3 minutes, once; GPU tests use them as a second pin)
+        subprocess.call(["make", "-C", _HERE, "refgpu"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def lib():
@@ -95,7 +98,7 @@ def woq_matmul(a: np.ndarray, raw: np.ndarray, scales: np.ndarray, mode="cutlass
     M, K = a.shape
     N = raw.shape[1]
     c = np.empty((M, N), np.float16)
-    lib().oracle_woq_matmul(_p(a), M, K, _p(raw), _p(scales), N, _p(c), {"cutlass": 0, "gemv": 1, "ideal": 2}[mode])
+    lib().oracle_woq_matmul(_p(a), M, K, _p(raw), _p(scales), N, _p(c), {"cutlass": 0, "gemv": 1, "ideal": 2, "gemv_exact": 3}[mode])
     return c
 
 
@@ -140,3 +143,22 @@ def ref_preprocess_weights_int8(raw: np.ndarray):
     if r.ref_preprocess_weights(_p(raw), K, N, _p(proc)) != 0:
         raise ValueError("reference preprocess_weights_for_mixed_gemm threw")
     return proc
+
+
+# ---- the reference's own CUDA kernels on the GPU (oracle/_ref/libref_gpu.so, `make -C oracle refgpu`) ----------
+
+_REFGPU = None
+
+
+def ref_gpu_lib():
+    """The reference GEMV and MMHA kernels compiled for sm_100a behind extern "C" (None if not built)."""
+    global _REFGPU
+    if _REFGPU is None:
+        p = os.path.join(_HERE, "_ref", "libref_gpu.so")
+        if os.path.exists(p):
+            _REFGPU = ctypes.CDLL(p)
+            _REFGPU.ref_gpu_gemv.restype = ctypes.c_int
+            _REFGPU.ref_gpu_gemv.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+            _REFGPU.ref_gpu_mmha.restype = ctypes.c_int
+            _REFGPU.ref_gpu_mmha.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_void_p]
+    return _REFGPU

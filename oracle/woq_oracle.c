@@ -240,7 +240,13 @@ int oracle_symmetric_quantize_int8(const void* w, int w_is_f16, int K, int N, in
  *   mode 0 ("cutlass"): C = fp16( sum_k fp32(a16) * fp32(w16) )         exact products, fp32 accumulate
  *   mode 1 ("gemv")   : C = fp16( sum_k fp32( fp16(a16 * w16) ) )       product rounded to fp16 first
  *   mode 2 ("ideal")  : C = fp16( double sum_k a16 * w16 )              rounding-order independent centre
- * Accumulation order is plain k = 0..K-1 (the GPU kernels use other orders; tests compare with a
+ *   mode 3 ("gemv_exact"): mode 1 with the reference GEMV kernel's exact summation order
+ *                       (weightOnlyMatrixVectorMultiplication.cu:165-203): 16 lanes per weight column, lane (o, q)
+ *                       (o = lane/8, q = lane%4) sums k = 64*(o + 4j) + 16q + p serially over j, p in fp32; then the
+ *                       butterfly xor 16, 8, 2, 1 = ((T0+T2)+(T1+T3)) over o, then ((V0+V2)+(V1+V3)) over q.
+ *                       Pinned bit-exactly against the reference kernel running on B200
+ *                       (tests/test_reference_kernels_gpu.py).
+ * Accumulation order of modes 0-2 is plain k = 0..K-1 (the GPU kernels use other orders; tests compare with a
  * tolerance, see tests/test_woq_matmul.py).
  * A: [M][K] fp16 bits, raw: [K][N] int8, scales: [N] fp16 bits, C: [M][N] fp16 bits.
  * ------------------------------------------------------------------------------------------- */
@@ -260,6 +266,29 @@ void oracle_woq_matmul(const uint16_t* A, int M, int K, const int8_t* raw, const
         {
             float acc = 0.f;
             double accd = 0.0;
+            if (mode == 3)
+            {
+                float T[4][4];
+                for (int o = 0; o < 4; ++o)
+                    for (int q = 0; q < 4; ++q)
+                    {
+                        float v = 0.f;
+                        for (int blk = o; blk * 64 < K; blk += 4)
+                            for (int p16 = 0; p16 < 16; ++p16)
+                            {
+                                const int k = 64 * blk + 16 * q + p16;
+                                const f16 a = bits_to_f16(A[(size_t) m * K + k]);
+                                v += (float) (f16) ((float) a * (float) wcol[k]);
+                            }
+                        T[o][q] = v;
+                    }
+                float V[4];
+                for (int q = 0; q < 4; ++q)
+                    V[q] = (T[0][q] + T[2][q]) + (T[1][q] + T[3][q]);
+                acc = (V[0] + V[2]) + (V[1] + V[3]);
+                C[(size_t) m * N + n] = f16_to_bits((f16) acc);
+                continue;
+            }
             for (int k = 0; k < K; ++k)
             {
                 const f16 a = bits_to_f16(A[(size_t) m * K + k]);
