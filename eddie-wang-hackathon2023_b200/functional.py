@@ -188,3 +188,34 @@ def logits_argmax(x, token_embedding, want_logits=True, logits_out=None, tokens_
                                      _lib.ptr(tokens_out), rows, cols, vocab, None, 0, _lib.stream_ptr())
     _lib.check(rc, "logits_argmax")
     return (logits_out if want_logits else None), tokens_out
+
+
+class WhisperLogitFilter:
+    """Device-side state of the Whisper logit filters + greedy update for a batch of sequences (the reference keeps
+    Python lists per sequence: T/examples/whisper/decoding.py:134-300).  suppress: iterable of token ids."""
+
+    def __init__(self, batch, vocab, eot, no_timestamps, timestamp_begin, blank_token, suppress=(),
+                 max_initial_timestamp_index=None, device="cuda"):
+        self.batch, self.vocab = batch, vocab
+        self.eot, self.no_timestamps, self.timestamp_begin, self.blank = eot, no_timestamps, timestamp_begin, blank_token
+        self.max_initial = -1 if max_initial_timestamp_index is None else int(max_initial_timestamp_index)
+        words = torch.zeros(((vocab + 31) // 32,), dtype=torch.int64)
+        for t in suppress:
+            words[t >> 5] |= 1 << (t & 31)
+        self.bitmap = (words & 0xFFFFFFFF).to(torch.uint32).to(device) if len(tuple(suppress)) else None
+        self.state = torch.zeros((batch, 4), dtype=torch.int32, device=device)
+        self.sum_logprobs = torch.zeros((batch,), dtype=torch.float32, device=device)
+
+    def reset(self):
+        self.state.zero_()
+        self.sum_logprobs.zero_()
+
+    def __call__(self, logits, next_token):
+        """logits [batch, vocab] fp32 CUDA (not modified); next_token int32 [batch] receives the chosen tokens."""
+        lib = _lib.load()
+        rc = lib.b200_whisper_filtered_argmax(
+            _lib.ptr(logits), self.batch, self.vocab, _lib.ptr(self.bitmap), self.eot,
+            -1 if self.no_timestamps is None else self.no_timestamps, self.timestamp_begin, self.blank, self.max_initial,
+            _lib.ptr(self.state), _lib.ptr(next_token), _lib.ptr(self.sum_logprobs), _lib.stream_ptr())
+        _lib.check(rc, "whisper_filtered_argmax")
+        return next_token

@@ -199,6 +199,8 @@ class WhisperDecoding:
 
     def reset(self):
         self.seq_len.zero_()
+        if getattr(self, "logit_filter", None) is not None:
+            self.logit_filter.reset()
 
     # ---- one pass over the decoder stack for `rows` query rows ----------------------------------------------
     def _stack(self, x, rows, s_q, context, input_lengths=None, b0=0, nb=None, chain=0):
@@ -272,12 +274,25 @@ class WhisperDecoding:
             _lib.check(self.lib.b200_l2_prefetch(c.data_ptr(), c.numel() * c.element_size(), self._side.cuda_stream),
                        "l2_prefetch")
 
+    def enable_logit_filters(self, eot, no_timestamps, timestamp_begin, blank_token, suppress=(),
+                             max_initial_timestamp_index=None):
+        """Greedy decoding with the reference's logit filters (SuppressBlank, SuppressTokens, ApplyTimestampRules,
+        decoding.py:134-217,332-348) evaluated on the device inside the captured step.  Call before prefill()."""
+        from ..functional import WhisperLogitFilter
+        self.logit_filter = WhisperLogitFilter(self.B, self.V, eot, no_timestamps, timestamp_begin, blank_token, suppress,
+                                               max_initial_timestamp_index, device=self.device)
+        self.graph = self.graph_host = None
+
     def _head(self, x_rows, rows, logits, next_tokens):
         h = self._buf("hf", rows, self.d)
         self._ln(x_rows, (self.ln_w, self.ln_b), h, rows)
+        filt = getattr(self, "logit_filter", None)
         rc = self.lib.b200_logits_argmax_fp16(h.data_ptr(), self.tok_emb.data_ptr(), logits.data_ptr(),
-                                              next_tokens.data_ptr(), rows, self.d, self.V, None, 0, self._st())
+                                              None if filt is not None else next_tokens.data_ptr(), rows, self.d,
+                                              self.V, None, 0, self._st())
         _lib.check(rc, "logits_argmax")
+        if filt is not None:
+            filt(logits, next_tokens)
 
     # ---- public API ----------------------------------------------------------------------------------------
     def prefill(self, prompt_tokens):
@@ -323,25 +338,38 @@ class WhisperDecoding:
         self.seq_len.add_(1)
         self.tokens.copy_(self.next_tokens)
 
+    def _snapshot(self):
+        snap = [self.seq_len.clone(), self.tokens.clone()]
+        filt = getattr(self, "logit_filter", None)
+        if filt is not None:
+            snap += [filt.state.clone(), filt.sum_logprobs.clone()]
+        return snap
+
+    def _restore(self, snap):
+        self.seq_len.copy_(snap[0])
+        self.tokens.copy_(snap[1])
+        filt = getattr(self, "logit_filter", None)
+        if filt is not None:
+            filt.state.copy_(snap[2])
+            filt.sum_logprobs.copy_(snap[3])
+
     def capture(self):
-        """Captures one generation step in a CUDA graph (all shapes static; lengths and tokens live on the device)."""
+        """Captures one generation step in a CUDA graph (all shapes static; lengths, tokens and the logit-filter state
+        live on the device)."""
         # warm-up outside capture: sets function attributes, allocates buffers
-        saved = self.seq_len.clone()
-        saved_tokens = self.tokens.clone()
+        snap = self._snapshot()
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             self._step_body()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
-        self.seq_len.copy_(saved)
-        self.tokens.copy_(saved_tokens)
+        self._restore(snap)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._step_body()
         torch.cuda.synchronize(self.device)
-        self.seq_len.copy_(saved)
-        self.tokens.copy_(saved_tokens)
+        self._restore(snap)
         self.graph = g
         # the same step with its host traffic inside the graph: pinned token ids -> device, step, next ids -> pinned.
         # step_host() then costs one graph launch and one stream synchronize.
@@ -351,8 +379,7 @@ class WhisperDecoding:
             self._step_body()
             self._pinned_out.copy_(self.next_tokens, non_blocking=True)
         torch.cuda.synchronize(self.device)
-        self.seq_len.copy_(saved)
-        self.tokens.copy_(saved_tokens)
+        self._restore(snap)
         self.graph_host = gh
         return g
 

@@ -212,6 +212,19 @@ int b200_cross_kv_pack(const void* k, const void* v, void* cross_kv, const float
     int kv_len, int num_heads, int head_size, int int8_kv_cache, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Whisper logit filters + greedy token update on the device (one launch per step, graph-capturable).
+ * Replaces the per-sequence Python loops of T/examples/whisper/decoding.py: SuppressBlank :202-209, SuppressTokens
+ * :212-217, ApplyTimestampRules :134-199, GreedyDecoder.update :274-293 (temperature 0).
+ * logits [rows, vocab] fp32 (not modified); suppress_bitmap: bit v of word v/32 set = token v suppressed (may be NULL);
+ * no_timestamps / max_initial_timestamp_index: -1 = absent; decode_state [rows][4] int32, zero-initialised when a
+ * sequence starts (sampled count, last, penultimate, last timestamp + 1), advanced by the call;
+ * next_token [rows]; sum_logprobs [rows] fp32 accumulated in place (may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int b200_whisper_filtered_argmax(const float* logits, int rows, int vocab, const uint32_t* suppress_bitmap, int eot,
+    int no_timestamps, int timestamp_begin, int blank_token, int max_initial_timestamp_index, int32_t* decode_state,
+    int32_t* next_token, float* sum_logprobs, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Conv1d encoder stem (fp16, fp32 accumulate), optional fused GELU.
  * Replaces  functional.conv1d -> TensorRT IConvolutionLayer  T/tensorrt_llm/functional.py:2202-2244,
  *           layers.Conv1d T/tensorrt_llm/layers/conv.py:52-94 (use: T/tensorrt_llm/models/whisper/model.py:135-157).
