@@ -190,6 +190,20 @@ def logits_argmax(x, token_embedding, want_logits=True, logits_out=None, tokens_
     return (logits_out if want_logits else None), tokens_out
 
 
+def bidirectional_attention(qkv, num_heads, head_size=64, out=None):
+    """qkv [B, S, 3*H*Dh] fp16 (q | k | v) -> softmax(q k^T / sqrt(Dh)) v as [B, S, H*Dh] (encoder self-attention)."""
+    _need_cuda(qkv)
+    lib = _lib.load()
+    B, S, three_hidden = qkv.shape
+    assert three_hidden == 3 * num_heads * head_size
+    if out is None:
+        out = torch.empty((B, S, num_heads * head_size), dtype=torch.float16, device=qkv.device)
+    rc = lib.b200_attention_bidirectional_fp16(_lib.ptr(qkv.contiguous()), _lib.ptr(out), B, S, num_heads, head_size,
+                                               _lib.stream_ptr())
+    _lib.check(rc, "bidirectional_attention")
+    return out
+
+
 class WhisperLogitFilter:
     """Device-side state of the Whisper logit filters + greedy update for a batch of sequences (the reference keeps
     Python lists per sequence: T/examples/whisper/decoding.py:134-300).  suppress: iterable of token ids."""

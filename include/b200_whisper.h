@@ -212,6 +212,15 @@ int b200_cross_kv_pack(const void* k, const void* v, void* cross_kv, const float
     int kv_len, int num_heads, int head_size, int int8_kv_cache, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Bidirectional (encoder) attention, head size 64: out = softmax(q k^T / 8) v per (batch, head), no mask, no cache.
+ * Replaces the unfused encoder attention of T/tensorrt_llm/layers/attention.py:283-406 as used by
+ * T/tensorrt_llm/models/whisper/model.py:124-172 (oracle W/torch_model.py:88-103).
+ * qkv [B, S, 3*H*64] fp16 (q | k | v, the output of one fused projection); out [B, S, H*64] fp16.
+ * ---------------------------------------------------------------------------------------------- */
+int b200_attention_bidirectional_fp16(const void* qkv, void* out, int batch_size, int seq_len, int num_heads,
+    int head_size, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Whisper logit filters + greedy token update on the device (one launch per step, graph-capturable).
  * Replaces the per-sequence Python loops of T/examples/whisper/decoding.py: SuppressBlank :202-209, SuppressTokens
  * :212-217, ApplyTimestampRules :134-199, GreedyDecoder.update :274-293 (temperature 0).

@@ -186,3 +186,19 @@ def test_attention_argument_errors():
     with pytest.raises(NotImplementedError):
         gpt_attention(qkv, cache, z, torch.tensor([0, 1], dtype=torch.int32), None, z, z, ci, 1, 64, 1.0, 32, False,
                       False, False, None, None, False)
+
+
+@pytest.mark.parametrize("B,S,H", [(2, 1500, 20), (1, 100, 3), (2, 64, 1), (1, 1, 2), (3, 77, 6), (1, 129, 4)])
+def test_bidirectional_attention(B, S, H):
+    """Encoder self-attention (no mask, no cache) against W/torch_model.py:88-103 evaluated in fp32."""
+    from b200_whisper.functional import bidirectional_attention
+    torch.manual_seed(B * 7 + S)
+    D = 64
+    qkv = (torch.randn((B, S, 3 * H * D), device="cuda") * 1.2).half()
+    out = bidirectional_attention(qkv, H, D)
+    torch.cuda.synchronize()
+    q, k, v = [t.float().view(B, S, H, D).permute(0, 2, 1, 3) for t in qkv.split(H * D, dim=-1)]
+    w = torch.softmax((q * D ** -0.25) @ (k * D ** -0.25).transpose(-1, -2), dim=-1)
+    ref = (w @ v).permute(0, 2, 1, 3).reshape(B, S, H * D)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"bidirectional attention err {err}"
