@@ -59,6 +59,7 @@ _SIGS = {
     "b200_cross_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b200_cross_kv_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200_conv1d_fp16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200_transpose_add_pos_fp16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_attention_bidirectional_fp16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_whisper_filtered_argmax": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b200_conv1d_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -193,6 +193,35 @@ __global__ void __launch_bounds__(256) logits_simt_kernel(const __half* __restri
     }
 }
 
+// [B, C, T] -> [B, T, C] + pos[T, C]: the encoder's `x.permute(0, 2, 1) + positional_embedding`
+// (T/tensorrt_llm/models/whisper/model.py:158-162, oracle torch_model.py:159-162).  32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) transpose_add_pos_kernel(const __half* __restrict__ x, const __half* __restrict__ pos,
+    __half* __restrict__ y, int C, int T)
+{
+    __shared__ __half tile[32][33];
+    grid_dep_wait();
+    grid_dep_launch_dependents();
+    const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const __half* xb = x + (size_t) b * C * T;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const int c = c0 + ty + 8 * r, t = t0 + tx;
+        tile[ty + 8 * r][tx] = (c < C && t < T) ? xb[(size_t) c * T + t] : __float2half(0.f);
+    }
+    __syncthreads();
+    __half* yb = y + (size_t) b * T * C;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const int t = t0 + ty + 8 * r, c = c0 + tx;
+        if (t < T && c < C)
+            yb[(size_t) t * C + c]
+                = __float2half_rn(__half2float(tile[tx][ty + 8 * r]) + __half2float(pos[(size_t) t * C + c]));
+    }
+}
+
 // argmax over fp32 logits, first index on ties (torch.argmax).  grid (parts, rows), 256 threads: every CTA scans a
 // slice of the row with 8 independent loads in flight per thread, publishes (value, index) as one order-preserving
 // 64-bit key with atomicMax, and the last CTA of a row to arrive writes the token and resets the scratch words.
@@ -400,5 +429,18 @@ extern "C" int b200_logits_argmax_fp16(const void* x, const void* emb, void* log
         B200_LAUNCH(argmax_kernel, dim3(parts, rows), dim3(256), 0, st, static_cast<const float*>(lg), next_token, vocab, packed,
             counters);
     }
+    return B200_OK;
+}
+
+extern "C" int b200_transpose_add_pos_fp16(const void* x, const void* pos, void* y, int batch_size, int channels, int t,
+    b200_stream_t stream)
+{
+    B200_REQUIRE(x && pos && y, B200_ERR_INVALID_ARG, "null pointer (x/pos/y)");
+    B200_REQUIRE(channels > 0 && t > 0, B200_ERR_INVALID_ARG, "bad sizes");
+    if (batch_size <= 0)
+        return B200_OK;
+    B200_REQUIRE_DEVICE();
+    B200_LAUNCH(transpose_add_pos_kernel, dim3((t + 31) / 32, (channels + 31) / 32, batch_size), dim3(256), 0,
+        as_stream(stream), static_cast<const __half*>(x), static_cast<const __half*>(pos), static_cast<__half*>(y), channels, t);
     return B200_OK;
 }

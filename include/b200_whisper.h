@@ -211,6 +211,11 @@ int b200_cross_attention(const void* q, const void* cross_kv, const float* kv_sc
 int b200_cross_kv_pack(const void* k, const void* v, void* cross_kv, const float* kv_scale_orig_quant, int batch_size,
     int kv_len, int num_heads, int head_size, int int8_kv_cache, b200_stream_t stream);
 
+/* x [B, C, T] fp16 -> y [B, T, C] = x^T + pos [T, C]: the encoder's permute + positional embedding
+ * (T/tensorrt_llm/models/whisper/model.py:158-162). */
+int b200_transpose_add_pos_fp16(const void* x, const void* pos, void* y, int batch_size, int channels, int t,
+    b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Bidirectional (encoder) attention, head size 64: out = softmax(q k^T / 8) v per (batch, head), no mask, no cache.
  * Replaces the unfused encoder attention of T/tensorrt_llm/layers/attention.py:283-406 as used by

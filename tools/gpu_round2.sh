@@ -21,6 +21,7 @@ for fam in "$@"; do
     plugin) run plugin 600 tests/test_plugin_gpu.py;;
     refk) run refk 600 tests/test_reference_kernels_gpu.py;;
     filters) run filters 600 tests/test_logit_filters_gpu.py;;
+    encoder) run encoder 600 tests/test_encoder_gpu.py;;
     smoke) echo "=== smoke" | tee -a gpurun_out/summary.txt
        timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "exit $?" >> gpurun_out/smoke.log
        tail -n 4 gpurun_out/smoke.log | tee -a gpurun_out/summary.txt;;
