@@ -28,6 +28,7 @@
 
 #include <mutex>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -93,9 +94,29 @@ __device__ __forceinline__ long long global_timer_ns()
 #endif
 
 
-// bias / activation / residual with the reference's per-layer fp16 rounding (see epilogue_apply in common.cuh);
-// the residual value is passed in so callers can issue all residual loads before the dependent stores.
-__device__ __forceinline__ __half finish_output(float acc, bool has_bias, float biasv, int activation, bool has_res, float res)
+// bias / activation / residual with the reference's per-layer fp16 rounding (see epilogue_apply in common.cuh).
+// The activation is a template parameter: with a run-time switch the compiler predicates the erf / tanh polynomials
+// into every output's instruction stream (they cost issue slots even when masked off; the 256-row epilogue spent 70 %
+// of the kernel there).
+template <int ACT>
+__device__ __forceinline__ __half finish_output(float acc, bool has_bias, float biasv, bool has_res, float res)
+{
+    __half o = __float2half_rn(acc);
+    if (has_bias)
+        o = __float2half_rn(__half2float(o) + biasv);
+    if constexpr (ACT == B200_ACT_GELU_ERF)
+        o = __float2half_rn(gelu_erf(__half2float(o)));
+    else if constexpr (ACT == B200_ACT_GELU_TANH)
+        o = __float2half_rn(gelu_tanh(__half2float(o)));
+    if (has_res)
+        o = __float2half_rn(__half2float(o) + res);
+    return o;
+}
+
+// Run-time activation: used by the decode-sized cluster reduction, where ONE compact instruction stream matters more than
+// the masked-off instructions (six specialised copies of that epilogue measured 8 % slower on the decoder step:
+// instruction-cache misses on the critical path of a 3 us kernel).
+__device__ __forceinline__ __half finish_output_rt(float acc, bool has_bias, float biasv, int activation, bool has_res, float res)
 {
     __half o = __float2half_rn(acc);
     if (has_bias)
@@ -107,6 +128,41 @@ __device__ __forceinline__ __half finish_output(float acc, bool has_bias, float 
     if (has_res)
         o = __float2half_rn(__half2float(o) + res);
     return o;
+}
+
+// calls f(activation tag, folded-LayerNorm tag) with compile-time constants; the branch is warp-uniform
+template <typename F>
+__device__ __forceinline__ void tc_dispatch(int activation, bool fold, F&& f)
+{
+    if (activation == B200_ACT_GELU_ERF)
+    {
+        if (fold)
+            f(std::integral_constant<int, B200_ACT_GELU_ERF>{}, std::true_type{});
+        else
+            f(std::integral_constant<int, B200_ACT_GELU_ERF>{}, std::false_type{});
+    }
+    else if (activation == B200_ACT_GELU_TANH)
+    {
+        if (fold)
+            f(std::integral_constant<int, B200_ACT_GELU_TANH>{}, std::true_type{});
+        else
+            f(std::integral_constant<int, B200_ACT_GELU_TANH>{}, std::false_type{});
+    }
+    else
+    {
+        if (fold)
+            f(std::integral_constant<int, B200_ACT_NONE>{}, std::true_type{});
+        else
+            f(std::integral_constant<int, B200_ACT_NONE>{}, std::false_type{});
+    }
+}
+
+__device__ __forceinline__ void tc_ld_x8p(uint32_t taddr, uint32_t* r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 
 
@@ -587,14 +643,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
         };
-        auto ln_row_stats = [&](int ml, float& mean, float& rstd)
-        {
-            mean = ln_fin[2 * ml];
-            rstd = ln_fin[2 * ml + 1];
-        };
-        // y = rstd * (acc - mean * c1s) + c2 when the LayerNorm is folded, acc otherwise
-        auto ln_apply = [&](float acc, float mean, float rstd, float c1v, float c2v) -> float
-        { return fold ? rstd * (acc - mean * c1v) + c2v : acc; };
+        // (folded LayerNorm: y = rstd * (acc - mean * c1s) + c2, applied in the epilogue variants below)
 
         // ---- epilogue: thread (T, kh) owns accumulator row T, columns [kh*MT/2, (kh+1)*MT/2) ----
         const int n_tiles = gridDim.x, m_tiles = gridDim.y;
@@ -623,34 +672,79 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
             asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory"); // this CTA's own partial is complete
             ln_finish();
         }
+        if (direct)
+        {
+            if constexpr (MT >= 64)
+            {
+            // ---- unsplit tile (large M): every thread finishes its column for its half of the rows; TMEM is read in
+            // batches of up to 32 columns per wait ----
+            tc_dispatch(p.activation, fold, [&](auto act_c, auto fold_c)
+            {
+                constexpr int ACT = decltype(act_c)::value;
+                constexpr bool FOLD = decltype(fold_c)::value;
+                constexpr int CB = kHalfCols >= 32 ? 32 : kHalfCols;
 #pragma unroll 1
-        for (int c8 = 0; c8 < kHalfCols / 8; ++c8)
+                for (int cb = 0; cb < kHalfCols / CB; ++cb)
+                {
+                    uint32_t acc[CB];
+#pragma unroll
+                    for (int q = 0; q < CB / 8; ++q)
+                        tc_ld_x8p(tmem_base + lane_field + kDCol + kh * kHalfCols + cb * CB + q * 8, &acc[q * 8]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int ml0 = kh * kHalfCols + cb * CB;
+                    if (n < p.N)
+                    {
+#pragma unroll
+                        for (int i = 0; i < CB; ++i)
+                        {
+                            const int ml = ml0 + i;
+                            if (ml < m_valid)
+                            {
+                                float v = __uint_as_float(acc[i]) * scf;
+                                if constexpr (FOLD)
+                                    v = ln_fin[2 * ml + 1] * (v - ln_fin[2 * ml] * own_c1) + own_c2;
+                                const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
+                                const float res = has_res ? __half2float(p.residual[idx]) : 0.f;
+                                p.C[idx] = finish_output<ACT>(v, has_bias, own_bias, has_res, res);
+                            }
+                        }
+                    }
+                }
+            });
+                    }
+            else
+            {
+                // decode-sized tiles: one compact instruction stream (code size is latency in a 3 us kernel)
+#pragma unroll 1
+                for (int c8 = 0; c8 < kHalfCols / 8; ++c8)
+                {
+                    uint32_t acc[8];
+                    tc_ld_x8(tmem_base + lane_field + kDCol + kh * kHalfCols + c8 * 8, acc);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int ml0 = kh * kHalfCols + c8 * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (ml0 + i < m_valid && n < p.N)
+                        {
+                            const int ml = ml0 + i;
+                            float v = __uint_as_float(acc[i]) * scf;
+                            if (fold)
+                                v = ln_fin[2 * ml + 1] * (v - ln_fin[2 * ml] * own_c1) + own_c2;
+                            const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
+                            const float res = has_res ? __half2float(p.residual[idx]) : 0.f;
+                            p.C[idx] = finish_output_rt(v, has_bias, own_bias, p.activation, has_res, res);
+                        }
+                }
+            }
+        }
+#pragma unroll 1
+        for (int c8 = 0; !direct && c8 < kHalfCols / 8; ++c8)
         {
             uint32_t acc[8];
             tc_ld_x8(tmem_base + lane_field + kDCol + kh * kHalfCols + c8 * 8, acc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int ml0 = kh * kHalfCols + c8 * 8;
-            if (direct)
-            {
-                float res[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    res[i] = (has_res && ml0 + i < m_valid && n < p.N)
-                        ? __half2float(p.residual[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n])
-                        : 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (ml0 + i < m_valid && n < p.N)
-                    {
-                        float mean = 0.f, rstd = 1.f;
-                        if (fold)
-                            ln_row_stats(ml0 + i, mean, rstd);
-                        p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
-                            = finish_output(ln_apply(__uint_as_float(acc[i]) * scf, mean, rstd, own_c1, own_c2), has_bias,
-                                own_bias, p.activation, has_res, res[i]);
-                    }
-            }
-            else if (p.cluster)
+            if (p.cluster)
             {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -703,17 +797,15 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                         for (uint32_t q = 8; q < 16; ++q)
                             sum += src[(size_t) q * MT * nslice];
                     }
-                    float mean = 0.f, rstd = 1.f;
                     if (fold)
-                        ln_row_stats(ml, mean, rstd);
-                    p.C[idx] = finish_output(ln_apply(sum, mean, rstd, own_c1, own_c2), has_bias, own_bias, p.activation,
-                        has_res, res);
+                        sum = ln_fin[2 * ml + 1] * (sum - ln_fin[2 * ml] * own_c1) + own_c2;
+                    p.C[idx] = finish_output_rt(sum, has_bias, own_bias, p.activation, has_res, res);
                 };
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (ml_first + j * ml_step < m_valid)
                         reduce_one(ml_first + j * ml_step, own_res[j]);
-                for (int ml = ml_first + 4 * ml_step; ml < m_valid; ml += ml_step) // only MT = 32 with 2 splits
+                for (int ml = ml_first + 4 * ml_step; ml < m_valid; ml += ml_step) // more than 4 rows per thread
                     reduce_one(ml, has_res ? __half2float(p.residual[(size_t) (m_tile * MT + ml) * p.ldc + own_nn]) : 0.f);
             }
             if (tq == 0)
@@ -785,7 +877,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                         for (int i = 0; i < 8; ++i)
                             if (ml0 + i < m_valid)
                                 p.C[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n]
-                                    = finish_output(sum[i], has_bias, own_bias, p.activation, has_res, res[i]); // (no fold here)
+                                    = finish_output_rt(sum[i], has_bias, own_bias, p.activation, has_res, res[i]); // (no fold here)
                     }
                 }
                 if (tq == 0)
@@ -1055,7 +1147,7 @@ TcPlan plan_tc(int M, int N, int K)
     int cluster = 0;
     if (tiles < sms && tiles <= 4096)
     {
-        if (g_splitk_mode == 1 && pl.MT <= 64)
+        if (g_splitk_mode == 1 && pl.MT <= 128)
         {
             // cluster split-K: power-of-two cluster (<= 8, portable) along z, at least two k-blocks per CTA.
             // Decode tiles (MT <= 32) fit two CTAs per SM, so a grid may exceed the SM count a little; it must still
@@ -1078,6 +1170,10 @@ TcPlan plan_tc(int M, int N, int K)
             if (splits > kb_total / 2)
                 splits = kb_total / 2;
             if (splits < 1)
+                splits = 1;
+            // 256-row tiles: the fp32 slab round trip of a 128 KB tile costs more than the split saves (measured:
+            // 53 us split 4-way vs ~12 us unsplit at M = 256, 1280 -> 3840)
+            if (pl.MT == 256 && g_splitk_mode == 1)
                 splits = 1;
         }
     }
