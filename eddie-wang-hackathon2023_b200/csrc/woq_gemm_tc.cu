@@ -192,11 +192,14 @@ struct TcSmem
     }
 };
 
-template <int MT, int SS, int AS>
+// CL = true: the instantiation launched for cluster split-K contains ONLY that epilogue (no unsplit, no global-slab
+// code): a smaller instruction footprint is measurably faster for the decode-sized kernels.
+template <int MT, int SS, int AS, bool CL>
 __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     woq_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const TcParams p)
 {
     using L = TcSmem<MT, SS, AS>;
+    const bool is_cluster = CL || p.cluster != 0;
     constexpr int XTileBytes = L::XTileBytes;
     constexpr uint32_t kTmemCols = tmem_cols_pow2(32 * AS + MT);
     constexpr uint32_t kDCol = 32 * AS;
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
     uint8_t* extra = reinterpret_cast<uint8_t*>(full) + L::bars;
     float* rbuf = reinterpret_cast<float*>(extra);                       // cluster mode: [S][MT][128/S]
-    uint8_t* ln_base = extra + (p.cluster ? L::rbuf : 0);
+    uint8_t* ln_base = extra + (is_cluster ? L::rbuf : 0);
     __half* ln_g = reinterpret_cast<__half*>(ln_base);                   // folded LN: gamma of this split's k range
     float* ln_part = reinterpret_cast<float*>(ln_g + p.K);               // [sender rank <= 8][MT][2] partial mean, M2
     float* ln_fin = ln_part + 8 * MT * 2;                                // [MT][2] merged mean, rstd
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         {
             mbar_init(red_bar, 1);
             mbar_init(stat_bar, 1);
-            if (p.cluster)
+            if (is_cluster)
             {
                 mbar_arrive_expect_tx(red_bar, (uint32_t) (128 * MT * sizeof(float))); // inbox bytes from all ranks
                 if (fold)
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (p.cluster)
+    if (is_cluster)
         cluster_sync_all(); // every rank's inbox barrier is armed before anybody can push into it
     grid_dep_launch_dependents(); // PDL: the next kernel may start its own prologue / weight prefetch now
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         const int m_valid = min(MT, p.M - m_tile * MT);
         // cluster geometry of the split-K reduction (also used by the LayerNorm statistics exchange)
         const uint32_t S = (uint32_t) p.splits;
-        const uint32_t my_rank = p.cluster ? cluster_ctarank() : 0u;
+        const uint32_t my_rank = is_cluster ? cluster_ctarank() : 0u;
         // cluster mode: element (ml, n) goes to the rank that owns column slice n / nslice
         const int nslice = 128 / (int) S;
         uint32_t push_addr = 0, push_bar = 0;
@@ -496,7 +499,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         const int ml_first = tq >> ns_shift, ml_step = kDq >> ns_shift;
         int own_nn = 0;
         bool own_valid = false;
-        if (p.cluster)
+        if (is_cluster)
         {
             const uint32_t owner = (uint32_t) (T >> ns_shift);
             // inbox layout [sender rank][ml][nl]
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                 {
                     const uint32_t r = (uint32_t) (tq & (TPR - 1));
                     float* mine = ln_part + ((size_t) my_rank * MT + row) * 2; // [sender rank][row][mean, M2]
-                    if (p.cluster)
+                    if (is_cluster)
                     {
                         if (r < S)
                         {
@@ -648,17 +651,17 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         // ---- epilogue: thread (T, kh) owns accumulator row T, columns [kh*MT/2, (kh+1)*MT/2) ----
         const int n_tiles = gridDim.x, m_tiles = gridDim.y;
         const int tile_id = m_tile * n_tiles + n_tile;
-        const bool direct = (p.splits == 1);
+        const bool direct = !CL && (p.splits == 1);
         const bool has_res = p.residual != nullptr;
         const size_t slab_elems = (size_t) 128 * MT;
-        float* slab = (direct || p.cluster)
+        float* slab = (direct || is_cluster)
             ? nullptr
             : p.slabs + ((size_t) split * m_tiles * n_tiles + tile_id) * slab_elems + (size_t) T * MT + kh * kHalfCols;
         mbar_wait(acc_done, 0);
         tc_fence_after();
         // the residual is an earlier kernel's output: it may only be read after the dependency wait, which acc_done
         // implies (activation TMA -> MMA -> commit); its latency hides behind the cluster exchange below
-        if (own_valid && p.cluster && has_res)
+        if (own_valid && is_cluster && has_res)
         {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -667,11 +670,12 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         }
         if (tq == 0)
             TC_STAMP(7);
-        if (fold && !p.cluster)
+        if (fold && !is_cluster)
         {
             asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory"); // this CTA's own partial is complete
             ln_finish();
         }
+        if constexpr (!CL)
         if (direct)
         {
             if constexpr (MT >= 64)
@@ -738,19 +742,19 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
             }
         }
 #pragma unroll 1
-        for (int c8 = 0; !direct && c8 < kHalfCols / 8; ++c8)
+        for (int c8 = 0; (CL || !direct) && c8 < kHalfCols / 8; ++c8)
         {
             uint32_t acc[8];
             tc_ld_x8(tmem_base + lane_field + kDCol + kh * kHalfCols + c8 * 8, acc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int ml0 = kh * kHalfCols + c8 * 8;
-            if (p.cluster)
+            if (is_cluster)
             {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     st_async_f32(push_addr + (uint32_t) ((ml0 + i) * nslice) * 4u, __uint_as_float(acc[i]) * scf, push_bar);
             }
-            else
+            else if constexpr (!CL)
             {
                 float4* dst = reinterpret_cast<float4*>(slab + c8 * 8);
                 __stcg(dst, make_float4(__uint_as_float(acc[0]) * scf, __uint_as_float(acc[1]) * scf,
@@ -764,7 +768,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         // the accumulator has been read: let the MMA warp free the TMEM columns while the reduction runs
         tc_fence_before();
         asm volatile("bar.arrive 2, %0;" ::"n"(kDq + 32) : "memory");
-        if (p.cluster)
+        if (is_cluster)
         {
             // ---- split-K reduction through distributed shared memory: every rank received the partial values of its
             // column slice from all ranks (st.async + complete_tx on its inbox barrier) and sums them in rank order ----
@@ -811,7 +815,8 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
             if (tq == 0)
                 TC_STAMP(10);
         }
-        else if (!direct)
+        else if constexpr (!CL)
+        if (!direct)
         {
             __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
@@ -1210,10 +1215,10 @@ int* tc_counter_slot(int needed)
     return g_counters + (size_t) (g_counter_slot++ % kCounterSlots) * kCounterSlotInts;
 }
 
-template <int MT, int SS, int AS>
-static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcParams& p, dim3 grid, cudaStream_t stream)
+template <int MT, int SS, int AS, bool CL>
+static int launch_tc_impl(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcParams& p, dim3 grid, cudaStream_t stream)
 {
-    auto kern = woq_gemm_tc_kernel<MT, SS, AS>;
+    auto kern = woq_gemm_tc_kernel<MT, SS, AS, CL>;
     const size_t smem = TcSmem<MT, SS, AS>::total(p.cluster != 0, p.fold_gamma != nullptr, p.K);
     B200_REQUIRE(smem <= 227 * 1024, B200_ERR_UNSUPPORTED, "woq gemm: %zu bytes of shared memory needed", smem);
     static size_t attr_smem = 0;
@@ -1252,6 +1257,18 @@ static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcPar
     count_launch();
     B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmW, tmX, p));
     return B200_OK;
+}
+
+template <int MT, int SS, int AS>
+static int launch_tc(const CUtensorMap& tmW, const CUtensorMap& tmX, const TcParams& p, dim3 grid, cudaStream_t stream)
+{
+    // cluster split-K (every decode GEMM) runs the instantiation that carries only that epilogue
+    if constexpr (MT <= 128)
+    {
+        if (p.cluster)
+            return launch_tc_impl<MT, SS, AS, true>(tmW, tmX, p, grid, stream);
+    }
+    return launch_tc_impl<MT, SS, AS, false>(tmW, tmX, p, grid, stream);
 }
 
 // Can LayerNorm be folded into the GEMM for this shape?  (decode-sized m-tiles, cluster or unsplit reduction, the
