@@ -58,6 +58,7 @@ struct TcParams
     int kb_total; // K / 64
     int splits;
     int cluster;  // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
+    int x3_depth; // > 0: tmX is a 3-D map (64 k, rows, k-blocks) whose box holds this many k-blocks: ONE activation load
     long long* gt;  // optional: 4 global-timer values of this launch (min entry, min dependency return, max store, -)
     long long* dbg; // optional: clock64() stamps of CTA (0,0,0) at the phase boundaries (b200_debug_tc_timing)
 };
@@ -332,7 +333,14 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
             grid_dep_wait();
             TC_STAMP(15);
             TC_GT(atomicMin, 1);
-            if (x_single)
+            if (p.x3_depth > 0)
+            {
+                // the whole k range of this CTA as one 3-D box (a rank with one block less also receives its
+                // neighbour's first block into an unused stage: the byte count is the full box either way)
+                mbar_arrive_expect_tx(&xfull[0], (uint32_t) (p.x3_depth * XTileBytes));
+                tma_load_3d(smX, &tmX, 0, m_tile * MT, kb_begin, &xfull[0]);
+            }
+            else if (x_single)
             {
                 mbar_arrive_expect_tx(&xfull[0], (uint32_t) (nkb * XTileBytes));
                 for (int i = 0; i < nkb; ++i)
@@ -1304,10 +1312,22 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     if (int rc = make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, W, (uint64_t) 2 * K, (uint64_t) N / 2,
             (uint64_t) 2 * K, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
-    if (int rc = make_tmap_2d(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A, (uint64_t) K, (uint64_t) M, (uint64_t) K * 2, 64,
-            (uint32_t) pl.MT, CU_TENSOR_MAP_SWIZZLE_128B))
+    // decode-sized launches whose per-CTA k range fits the ring fetch their activations with ONE 3-D TMA box
+    const int nkb_max = (K / 64 + pl.splits - 1) / pl.splits;
+    const int ring = pl.MT == 16 ? 10 : pl.MT == 32 ? 7 : pl.MT == 64 ? 6 : 4;
+    static const bool x3_enabled = getenv("B200_X3") == nullptr || getenv("B200_X3")[0] != '0';
+    const int x3_depth = (x3_enabled && pl.MT <= 32 && pl.cluster && nkb_max <= ring) ? nkb_max : 0;
+    if (x3_depth > 0)
+    {
+        if (int rc = make_tmap_3d(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A, 64, (uint64_t) M, (uint64_t) K / 64,
+                (uint64_t) K * 2, 128, 64, (uint32_t) pl.MT, (uint32_t) x3_depth, 1, CU_TENSOR_MAP_SWIZZLE_128B))
+            return rc;
+    }
+    else if (int rc = make_tmap_2d(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A, (uint64_t) K, (uint64_t) M, (uint64_t) K * 2, 64,
+                 (uint32_t) pl.MT, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
     TcParams p{};
+    p.x3_depth = x3_depth;
     p.scales = scales;
     p.bias = bias;
     p.residual = residual;
