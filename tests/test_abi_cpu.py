@@ -60,6 +60,17 @@ def test_argument_validation_without_gpu(lib):
     assert rc == 1
     assert lib.b200_woq_workspace_bytes(16, 1280, 1280) > 0
     assert lib.b200_cross_attention_workspace_bytes(1, 20, 64, 1500) > 0  # few (row, head) pairs: split across CTAs
+    # the entry points added around the three operators validate their arguments the same way (1 = invalid argument,
+    # 2 = unsupported configuration), without a device
+    assert lib.b200_woq_ln_fold_prepare(None, None, None, None, 1280, 1280, None, None, None) == 1
+    assert lib.b200_woq_int8_gemm_ln_folded(None, None, None, None, None, 1e-5, 16, 1280, None, None, 1280, None, 0,
+                                            None, None, None, 0, None) == 1
+    assert lib.b200_conv1d_workspace_bytes(16, 80, 1280, 3000, 3) == ((3 * 1280 * 128 * 2 + 1023) // 1024) * 1024 \
+        + 16 * 3000 * 128 * 2
+    assert lib.b200_conv1d_fp16_tc(None, None, None, None, 1, 80, 1280, 3000, 3, 1, 1, 0, None, 0, None) == 1
+    assert lib.b200_attention_bidirectional_fp16(None, None, 1, 1500, 20, 64, None) == 1
+    assert lib.b200_whisper_filtered_argmax(None, 1, 51865, None, 50257, 50363, 50364, 220, -1, None, None, None, None) == 1
+    assert lib.b200_transpose_add_pos_fp16(None, None, None, 1, 1280, 1500, None) == 1
 
 
 def test_quant_mode_flags():
