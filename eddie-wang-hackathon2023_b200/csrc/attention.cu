@@ -1205,8 +1205,10 @@ static XaPlan xattn_plan(int R, int H, int S, int int8)
     pl.cfg = g_xa_cfg;
     const int ck = int8 ? CKi : CKi / 2;
     pl.nch = (S + ck - 1) / ck;
-    // enough (row, head) pairs to give every SM whole pairs: merge inside the CTA, no workspace
-    pl.rowhead = g_xa_mode == 2 ? ((long long) R * H * 2 >= num_sms() ? 1 : 0) : g_xa_mode;
+    // whole (row, head) pairs per CTA: merge inside the CTA, no workspace
+    // measured at batch 1-3 (20-60 pairs): whole pairs per CTA beat the split-across-CTAs kernel by 15-20 % of the step,
+    // so the split kernel is only kept for a handful of pairs
+    pl.rowhead = g_xa_mode == 2 ? ((long long) R * H >= 8 ? 1 : 0) : g_xa_mode;
     if (pl.rowhead)
     {
         const int slots = num_sms() * kOCC[g_xa_cfg];
