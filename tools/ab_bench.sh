@@ -7,6 +7,6 @@ python __graft_entry__.py build > /dev/null 2>&1
 for rep in 1 2; do
   for v in "$@" cur; do
     if [ $v = cur ]; then d=$ROOT; else d=$ROOT/ab/$v; fi
-    echo "$v: $(cd $d && python bench.py --steps 64 --warmup 4 --no-cpu-baseline 2>&1 | grep -o '"ms_per_step": [0-9.]*')"
+    echo "$v: $(cd $d && timeout 240 python bench.py --steps 64 --warmup 4 --no-cpu-baseline 2>&1 | grep -o '"ms_per_step": [0-9.]*')"
   done
 done
