@@ -12,8 +12,9 @@
 //               softmax T/cpp/tensorrt_llm/kernels/unfusedAttentionKernels.cu:179-257 (mask adds -10000, 1e-6 in the sum),
 //               cache fill unfusedAttentionKernels.cu:1552-1646
 //   cross       T/tensorrt_llm/layers/attention.py:308-323,385-406; oracle T/examples/whisper/torch_model.py:88-103
-// Deliberate deviation (more accurate, inside the reference tests' tolerances): probabilities stay fp32 instead of
-// being rounded to fp16 before P.V (Template.h:1765).
+// Like the reference (Template.h:1765) the probabilities of cached keys are rounded to fp16 before P.V (HFMA2 chains of
+// at most 8 keys, flushed to fp32); the current token's term and all sums stay fp32.  Pinned against the reference
+// kernel itself running on B200 (tests/test_reference_kernels_gpu.py): identical cache bytes, outputs within 2e-3.
 //
 // Cache layout: [B, 2, H, Smax, Dh] (KVLinearBuffer, T/cpp/tensorrt_llm/kernels/kvCacheUtils.h:114-170). Dh = 64.
 #include <float.h>
@@ -578,10 +579,14 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
 //      * every warp owns a CONTIGUOUS range of chunks of the flattened (row, head, chunk) space and carries the
 //        online-softmax state (m, l, o) across consecutive chunks of the same (row, head); the cross-lane reduction
 //        of o (48 shuffles) happens once per (row, head) range, not per chunk;
-//      * lane geometry 4 lanes x 16 dims per key, 8 keys per warp instruction; int8 -> fp16 by xor 0x80 + PRMT +
-//        HSUB2 (exact integers), products chained 4 (q.k) / 8 (p.v) at a time with HFMA2 and flushed to fp32, the
-//        dequant scale hoisted out of both dot products;
+//      * lane geometry 4 lanes x 16 dims per key, 8 keys per warp instruction; the int8 cross cache is stored in
+//        offset-binary form, so PRMT + HSUB2 alone give exact fp16 integers; the scores of 16 keys (two warp
+//        iterations) are ONE mma.sync.m16n8k16 chain (the converted registers are already the A fragment, q is
+//        column 0 of B), p.v is chained 8 keys at a time with HFMA2 and flushed to fp32, the dequant scale is hoisted
+//        out of both products, the softmax runs in the log2 domain;
 //      * the ranges of a (row, head) are merged by the last warp to arrive (self-resetting counter).
+//   v5: cross_attention_rowhead_kernel below (whole (row, head) pairs per CTA, merge in shared memory) is what runs
+//      from 8 pairs up; this split kernel remains for a handful of pairs.
 // =====================================================================================================
 // (warps per CTA, ring stages per warp, keys per chunk) -- one CTA per SM; WARPS*STAGES*CK*128 B of shared memory (int8)
 // OCC = CTAs per SM the row-head kernel is sized for (F: half-size CTAs, so a GEMM CTA of another stream can share the SM)

@@ -8,21 +8,27 @@
 //
 // B200 design ("swap-AB", weights are the UMMA A operand and live in TMEM):
 //   D[n, m] = sum_k W16[n, k] * X[m, k]      UMMA M = 128 weight columns n, UMMA N = MT activation rows m.
-//  * warp 4 (one lane): TMA producer.  Per 64-wide k-block it loads the int8 weight tile (64 row pairs x 128 B,
-//    one 2-D box of the [N/2][2K] byte matrix, 128B-swizzled so the dequant warps' 128-bit reads are
-//    conflict-free) and the fp16 activation tile (MT rows x 64 k, K-major, 128B swizzle = the canonical UMMA
-//    B layout) into a shared-memory ring.  Weight loads are issued before griddepcontrol.wait (PDL).
-//  * warps 0-3: dequant.  Thread T owns weight column n0+T: it reads its 64 bytes of the k-block, converts
-//    them with PRMT/HSUB2 (the 0x6400|b trick), multiplies by the fp16 column scale (effective weight
-//    fp16(q*s), identical to the reference's mma_tensorop_dequantizer.h:253-270) and writes 32 packed-half2
-//    registers straight into TMEM lane T with one tcgen05.st.32x32b.x32.  The reference layout's row
-//    permutation + byte swizzle make every converted register a k-adjacent pair, i.e. exactly one 32-bit
-//    TMEM column of the K-major A operand -- no shuffles, no second shared-memory round trip.
-//  * warp 5 (one lane): issues tcgen05.mma.kind::f16 with A from TMEM and B from shared memory, fp32
-//    accumulator in TMEM, and tcgen05.commit to release the stages.
-//  * warps 0-3 again: epilogue.  tcgen05.ld the accumulator (lane = n, column = m), fused bias / GELU /
-//    residual, fp16 store (lanes of a warp write 32 consecutive n: coalesced).  With split-K, partial tiles
-//    go to fp32 slabs in the workspace and the last CTA of a tile reduces them in split order (deterministic).
+// 320 threads per CTA:
+//  * warp 8 (one elected lane): TMA producer.  Per 64-wide k-block it loads the int8 weight tile (64 row pairs x 128 B,
+//    one 2-D box of the [N/2][2K] byte matrix, 128B-swizzled so the dequant warps' 128-bit reads are conflict-free) into
+//    an SS-deep ring BEFORE griddepcontrol.wait (weights never depend on the previous kernel), and after the wait the
+//    fp16 activation tiles (MT rows x 64 k, K-major, 128B swizzle = the canonical UMMA B layout) -- for decode launches
+//    as ONE 3-D box covering the CTA's whole k range.  Weights and activations complete on separate mbarriers.
+//  * warps 0-7: dequant.  Thread = weight column (TMEM lane) x k-half: it reads its 32 bytes of the k-block, converts
+//    them with PRMT/HSUB2 (the 0x6400|b trick: exact fp16 integers; the fp16 column scale is applied to the fp32
+//    accumulator in the epilogue) and writes 16 packed-half2 registers straight into TMEM with tcgen05.st.32x32b.x16.
+//    The reference layout's row permutation + byte swizzle make every converted register a k-adjacent pair, i.e.
+//    exactly one 32-bit TMEM column of the K-major A operand -- no shuffles, no second shared-memory round trip.
+//    With a folded LayerNorm the pairs are multiplied by gamma here and the row statistics are reduced from the
+//    activation tiles in shared memory (see TcParams).
+//  * warp 9: issues tcgen05.mma.kind::f16 (elect.sync lane) with A from TMEM and B from shared memory, fp32
+//    accumulator in TMEM, tcgen05.commit to release stages; allocates / frees TMEM.
+//  * warps 0-7 again: epilogue.  Split-K CTAs of a tile form a thread-block cluster: partial accumulators are pushed
+//    with st.async into the inbox of the CTA that owns the column slice (complete_tx on its mbarrier), summed in rank
+//    order (deterministic) and finished with bias / GELU / residual.  Unsplit tiles (large M) finish their own columns;
+//    B200_SPLITK=global selects fp32 slabs in the workspace + last-CTA reduction.
+// Decode tiles (MT <= 32) use 96 registers, 115 KB of shared memory and 256 TMEM columns so that two CTAs -- this GEMM's
+// and the next one's, launched programmatically -- share an SM.
 // HBM traffic: every weight byte is read once per m-tile; activations are re-read per n-tile from L2.
 #include <cuda.h>
 
