@@ -79,3 +79,47 @@ def test_tiny_dims_two_steps():
         torch.cuda.synchronize()
         err = (dec.logits.cpu() - ref_logits[t]).abs().max().item()
         assert err <= 2e-2 * ref_logits[t].abs().max().item(), f"step {t} logits err {err}"
+
+
+def test_large_v2_full_size_determinism_and_utterance_independence():
+    """BASELINE full size (large-v2 decoder, 32 layers, 1500 encoder frames), size-independent properties:
+      * run-to-run determinism: two decoders built from the same seeds produce bit-identical logits and tokens
+        (every split-K / split-KV reduction is in fixed order);
+      * utterance independence -- the multi-GPU sharding property: the logits of an utterance do not depend,
+        bit for bit, on which other utterances share its batch (here: rows 0-1 decoded in a batch of 4 and in a batch of 2),
+        CUDA graph and eager."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from b200_whisper.runtime import WhisperDecoding
+    dev = torch.device("cuda")
+    dims = bench.Dims()
+    L = dims.n_text_layer
+    sd = bench.gpu_state_dict(dims, dev, seed=0)
+    g = torch.Generator(device=dev).manual_seed(7)
+    caches = [torch.randint(-127, 128, (4, 2, dims.n_text_head, dims.n_audio_ctx, 64), generator=g, device=dev,
+                            dtype=torch.int8) for _ in range(L)]
+
+    def run(batch, use_graph):
+        dec = WhisperDecoding(dims, sd, batch, kv_scales=[0.05] * L, cross_kv_scales=[0.03] * L, device=dev)
+        dec.set_cross_kv([c[:batch].contiguous() for c in caches])
+        dec.reset()
+        toks = [dec.prefill([bench.PROMPT] * batch).clone()]
+        logits = [dec.logits.clone()]
+        if use_graph:
+            dec.capture()
+        for _ in range(3):
+            toks.append((dec.step() if use_graph else (dec._step_body() or dec.next_tokens)).clone())
+            logits.append(dec.logits.clone())
+        torch.cuda.synchronize()
+        return torch.stack(toks), torch.stack(logits)
+
+    t4, l4 = run(4, True)
+    t4b, l4b = run(4, True)
+    assert torch.equal(t4, t4b) and torch.equal(l4, l4b), "two identical runs differ"
+    assert torch.isfinite(l4).all()
+    t2, l2 = run(2, True)
+    assert torch.equal(l2, l4[:, :2]) and torch.equal(t2, t4[:, :2]), "an utterance's logits depend on its batch mates"
+    t2e, l2e = run(2, False)
+    assert torch.equal(l2e, l2) and torch.equal(t2e, t2), "CUDA-graph replay and eager launches differ"
