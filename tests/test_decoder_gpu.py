@@ -123,3 +123,35 @@ def test_large_v2_full_size_determinism_and_utterance_independence():
     assert torch.equal(l2, l4[:, :2]) and torch.equal(t2, t4[:, :2]), "an utterance's logits depend on its batch mates"
     t2e, l2e = run(2, False)
     assert torch.equal(l2e, l2) and torch.equal(t2e, t2), "CUDA-graph replay and eager launches differ"
+
+
+def test_large_v2_width_two_layers_against_oracle():
+    """Whisper large-v2 WIDTH (d = 1280, 20 heads, fc 5120, vocab 51865, 1500 encoder frames) with 2 layers, batch 3:
+    every decode-shape kernel of the headline configuration (qkv 1280->3840, fc1 1280->5120 with folded LayerNorm, fc2
+    5120->1280 with its recycled TMEM stages, cross-attention over 1500 frames, the 256-row cross-K/V projections)
+    against the oracle with identically dequantized weights: logits within tolerance, greedy tokens identical while
+    the oracle's own top-1 margin is above the fp16 noise floor."""
+    dims = wo.ModelDimensions(80, 1500, 1280, 20, 2, 51865, 448, 1280, 20, 2)
+    B, n_new = 3, 5
+    sdq, xa, kv_s, ckv_s, dec = build(dims, seed=5, B=B)  # seed 5: the greedy tokens vary (36316, 20855, ..., 26186)
+    with torch.no_grad():
+        ref_tokens, ref_logits = wo.greedy_decode(sdq, dims, xa, PROMPT, n_new, kv_s, ckv_s, act_fp16=True)
+    dec.reset()
+    got = [dec.prefill([PROMPT] * B).clone()]
+    torch.cuda.synchronize()
+    err = (dec.logits.cpu() - ref_logits[0]).abs().max().item()
+    assert err <= 2e-2 * ref_logits[0].abs().max().item(), f"prefill logits err {err}"
+    dec.capture()
+    for t in range(1, n_new):
+        got.append(dec.step().clone())
+        torch.cuda.synchronize()
+        same_history = all(int(got[s][b]) == int(ref_tokens[b, s]) for s in range(t) for b in range(B))
+        if same_history:
+            err = (dec.logits.cpu() - ref_logits[t]).abs().max().item()
+            assert err <= 3e-2 * ref_logits[t].abs().max().item(), f"step {t} logits err {err}"
+    got = torch.stack(got, 1).cpu().long()
+    margins = torch.stack([(l.topk(2).values[:, 0] - l.topk(2).values[:, 1]) for l in ref_logits], 1)
+    for b in range(B):
+        weak = (margins[b] < 0.05).nonzero()
+        upto = int(weak[0]) + 1 if len(weak) else n_new
+        assert got[b, :upto].tolist() == ref_tokens[b, :upto].tolist(), (b, got[b].tolist(), ref_tokens[b].tolist())
