@@ -86,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -96,7 +96,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Number of samples taken so far (brackets the timed region: the sampler itself starts before the warm-up
+        because nvidia-smi needs ~0.1 s to come up, longer than a 64-step timed region)."""
+        return len(self.lines)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -106,7 +111,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        window = self.lines[first:last] if last is not None and last > first else self.lines[max(0, first - 2):]
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -252,12 +258,23 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- value: device-resident steps -------------------------------------------------------------
-    for _ in range(args.warmup):
-        dec.step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        dec.step()
+    if rank == 0:
+        # nvidia-smi needs ~0.1 s to deliver its first sample; keep the GPU busy with filler work meanwhile (NOT decoder
+        # steps: they would advance the sequence length and change the measured workload)
+        filler = torch.randn((4096, 4096), device=dev, dtype=torch.float16)
+        t_w = time.perf_counter()
+        while sampler.mark() == 0 and time.perf_counter() - t_w < 1.5:
+            for _ in range(8):
+                filler @ filler
+            torch.cuda.synchronize(dev)
+        del filler
+    barrier()
+    s_first = sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.b200_launch_count()
     ev0.record()
@@ -267,7 +284,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     eager_launches = lib.b200_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(s_first, sampler.mark()) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
