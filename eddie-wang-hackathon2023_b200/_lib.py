@@ -50,6 +50,7 @@ _SIGS = {
     "b200_woq_int8_gemm_ln_folded": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz,
                                           _vp]),
     "b200_woq_set_kernel_policy": (_i, [_i]),
+    "b200_debug_woq_plan": (_i, [_i, _i, _i, _vp]),
     "b200_debug_tc_timing": (_i, [_vp]),
     "b200_debug_tc_timing_filter": (_i, [_i, _i]),
     "b200_debug_tc_timeline": (_i, [_vp, _i]),

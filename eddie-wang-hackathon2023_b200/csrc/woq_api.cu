@@ -18,6 +18,7 @@ void tc_set_debug_buffer(long long* p);
 void tc_set_debug_filter(int n, int fold);
 void tc_set_timeline_buffer(long long* p, int max_launches);
 bool woq_tc_can_fold_ln(int M, int N, int K);
+void woq_tc_plan_query(int M, int N, int K, int* mt, int* m_tiles, int* n_tiles, int* splits, int* cluster);
 
 static int g_policy = 0; // 0 auto, 1 simt, 2 tcgen05
 
@@ -175,6 +176,14 @@ extern "C" int b200_woq_int8_gemm(const void* A, int M, int K, const int8_t* Wpr
 {
     return b200_woq_int8_gemm_fused(
         A, M, K, Wproc, scales, N, nullptr, B200_ACT_NONE, nullptr, C, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200_debug_woq_plan(int M, int N, int K, int* plan5)
+{
+    B200_REQUIRE(plan5 != nullptr && M >= 1 && N >= 64 && K >= 64 && K % 64 == 0 && N % 64 == 0, B200_ERR_INVALID_ARG,
+        "bad arguments");
+    woq_tc_plan_query(M, N, K, &plan5[0], &plan5[1], &plan5[2], &plan5[3], &plan5[4]);
+    return B200_OK;
 }
 
 extern "C" int b200_init(void)

@@ -1369,6 +1369,17 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     }
 }
 
+// Host-side launch plan of the tcgen05 path, exported for tests (no device work; without a GPU the SM count is 148).
+void woq_tc_plan_query(int M, int N, int K, int* mt, int* m_tiles, int* n_tiles, int* splits, int* cluster)
+{
+    const TcPlan pl = plan_tc(M, N, K);
+    *mt = pl.MT;
+    *m_tiles = pl.m_tiles;
+    *n_tiles = pl.n_tiles;
+    *splits = pl.splits;
+    *cluster = pl.cluster;
+}
+
 size_t woq_tc_workspace_bytes(int max_m, int N, int K)
 {
     // plan_tc never uses more than num_sms() slabs of one 128 x MT fp32 tile (splits * tiles <= num_sms), and MT

@@ -135,6 +135,9 @@ int b200_woq_int8_gemm_ln_folded(const void* X, const void* ln_gamma, const void
 int b200_woq_set_kernel_policy(int policy);
 /* Debug aid: device buffer of >= 16 int64 receiving clock64() stamps of CTA (0,0,0) of each following tcgen05 GEMM
  * launch at its phase boundaries; NULL switches it off. */
+/* Debug / test aid (host only): the launch plan of the tcgen05 path for a shape: plan5 = {m-tile rows, m tiles, n tiles,
+ * k splits, 1 if the splits form a thread-block cluster}. */
+int b200_debug_woq_plan(int M, int N, int K, int* plan5);
 /* Debug aid: the next max_launches tcgen05 GEMM launches record (launch order) 4 int64 %globaltimer values each:
  * earliest CTA entry, earliest dependency-wait return, latest CTA exit, unused.  Caller presets INT64_MAX/INT64_MAX/0. */
 int b200_debug_tc_timeline(void* device_buffer, int max_launches);

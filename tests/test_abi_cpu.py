@@ -94,3 +94,30 @@ def test_quant_mode_flags():
     m = QuantMode.use_weight_only().set_int8_kv_cache()
     assert m.is_int8_weight_only() and m.is_weight_only() and m.has_int8_kv_cache() and not m.has_fp8_kv_cache()
     assert m.has_any_quant() and not QuantMode(0).has_any_quant()
+
+
+def test_tc_launch_plan_for_the_decoder_shapes(lib):
+    """The split-K planner (host logic, 148 SMs assumed without a GPU): the decode shapes of large-v2 get cluster splits
+    that keep each CTA's k range inside the weight ring, 256-row tiles are not split, the M = 128 cliff stays fixed."""
+    import ctypes
+    if os.environ.get("B200_SPLITK", "cluster") != "cluster":
+        pytest.skip("planner defaults are tested in cluster mode")
+
+    def plan(m, n, k):
+        out = (ctypes.c_int * 5)()
+        assert lib.b200_debug_woq_plan(m, n, k, out) == 0
+        return tuple(out)
+
+    # (MT, m_tiles, n_tiles, splits, cluster)
+    assert plan(16, 3840, 1280) == (16, 1, 30, 4, 1)
+    assert plan(16, 1280, 1280) == (16, 1, 10, 8, 1)
+    assert plan(16, 5120, 1280) == (16, 1, 40, 4, 1)   # 160 CTAs: two per SM on a few SMs
+    assert plan(16, 1280, 5120) == (16, 1, 10, 8, 1)   # 10 k-blocks per CTA = the whole weight ring
+    assert plan(1, 3840, 1280)[0] == 16 and plan(1, 3840, 1280)[4] == 1
+    mt, mtiles, ntiles, splits, cluster = plan(128, 3840, 1280)
+    assert mt == 128 and cluster == 1 and 2 <= splits <= 8
+    assert plan(256, 3840, 1280)[3] == 1                # 256-row tiles: unsplit
+    assert plan(24000, 3840, 1280)[:4] == (256, 94, 30, 1)
+    for m, n, k in [(16, 3840, 1280), (16, 1280, 5120), (32, 1280, 1280), (32, 3840, 1280), (4, 1280, 1280)]:
+        mt, _, nt, s, c = plan(m, n, k)
+        assert c == 1 and (k // 64 + s - 1) // s <= {16: 10, 32: 7}[mt]  # decode tiles: k range resident in the ring
