@@ -9,6 +9,7 @@ ctypes to the C ABI in include/b200_whisper.h.  Import as ``b200_whisper`` (see 
     quantization.mode.QuantMode                          <- tensorrt_llm/quantization/mode.py
     functional.gpt_attention / conv1d / ...              <- tensorrt_llm/functional.py:2202-2244,2738-2971
     runtime.WhisperDecoding                              <- examples/whisper/decoding.py (greedy loop, CUDA graph)
+    whisper_utils.log_mel_spectrogram / pad_or_trim      <- examples/whisper/whisper_utils.py:56-145 (GPU log-Mel front end)
 """
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401
@@ -16,8 +17,9 @@ from . import functional  # noqa: F401
 from . import quantization  # noqa: F401
 from .quantization import QuantMode  # noqa: F401
 from . import runtime  # noqa: F401
+from . import whisper_utils  # noqa: F401
 
-__all__ = ["ops", "functional", "quantization", "QuantMode", "load", "launch_count"]
+__all__ = ["ops", "functional", "quantization", "QuantMode", "whisper_utils", "load", "launch_count"]
 
 
 def load():

@@ -261,6 +261,22 @@ int b200_conv1d_fp16_tc(const void* x, const void* w, const void* bias, void* y,
     b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Whisper log-Mel front end (the data format in front of the encoder stem).
+ * Replaces  log_mel_spectrogram  T/examples/whisper/whisper_utils.py:99-145 (host torch.stft in the reference,
+ *           callers run.py:44-46, summarize.py:120-122).
+ * audio [B, n_samples] fp32 on the device, 16 kHz; `padding` zero samples are appended to every utterance (:129-130);
+ * mel_filters [n_mels, 201] fp32 on the device (the reference's assets/mel_filters.npz, whisper_utils.py:81-97);
+ * out [B, n_mels, n_frames], n_frames = (n_samples + padding) / 160, dtype B200_DTYPE_F32 (the reference's result) or
+ * B200_DTYPE_F16 (what the encoder consumes, run.py:45).  The max - 8 floor uses the maximum of each utterance: the
+ * reference is called with one utterance at a time.  n_samples + padding > 200 (reflect padding of torch.stft).
+ * workspace: b200_log_mel_workspace_bytes(), 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+int b200_log_mel_frames(int n_samples, int padding);
+size_t b200_log_mel_workspace_bytes(int batch_size, int n_samples, int padding, int n_mels);
+int b200_log_mel_spectrogram(const float* audio, int batch_size, int n_samples, int padding, const float* mel_filters,
+    int n_mels, void* out, int out_dtype, void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Decoder-step glue (TensorRT-native layers in the reference:
  * T/tensorrt_llm/models/whisper/model.py:74-118,257-292).
  * ---------------------------------------------------------------------------------------------- */
