@@ -10,6 +10,8 @@ ctypes to the C ABI in include/b200_whisper.h.  Import as ``b200_whisper`` (see 
     functional.gpt_attention / conv1d / ...              <- tensorrt_llm/functional.py:2202-2244,2738-2971
     runtime.WhisperDecoding                              <- examples/whisper/decoding.py (greedy loop, CUDA graph)
     whisper_utils.log_mel_spectrogram / pad_or_trim      <- examples/whisper/whisper_utils.py:56-145 (GPU log-Mel front end)
+    tokenizer.get_tokenizer / Tokenizer                  <- examples/whisper/tokenizer.py:125-265, decoding.py:423-486
+    runtime.WhisperPipeline, load_checkpoint, *_kv_scales <- examples/whisper/run.py:33-66, build.py:146-154, weight.py:236-243
 """
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401
@@ -18,8 +20,9 @@ from . import quantization  # noqa: F401
 from .quantization import QuantMode  # noqa: F401
 from . import runtime  # noqa: F401
 from . import whisper_utils  # noqa: F401
+from . import tokenizer  # noqa: F401
 
-__all__ = ["ops", "functional", "quantization", "QuantMode", "whisper_utils", "load", "launch_count"]
+__all__ = ["ops", "functional", "quantization", "QuantMode", "whisper_utils", "tokenizer", "load", "launch_count"]
 
 
 def load():
