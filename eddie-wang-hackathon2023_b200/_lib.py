@@ -63,6 +63,7 @@ _SIGS = {
     "b200_transpose_add_pos_fp16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200_attention_bidirectional_fp16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_whisper_filtered_argmax": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "b200_logits_range_softmax": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b200_conv1d_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "b200_conv1d_fp16_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b200_log_mel_frames": (_i, [_i, _i]),

@@ -202,3 +202,139 @@ extern "C" int b200_whisper_filtered_argmax(const float* logits, int rows, int v
         suppress_bitmap, prm, reinterpret_cast<int4*>(decode_state), next_token, sum_logprobs, scratch, counters);
     return B200_OK;
 }
+
+// =====================================================================================================
+// Language detection and the no-speech probability (T/examples/whisper/decoding.py:703-741 and :762-766): both read
+// the logits of the start-of-transcript position.
+//   * range softmax: the logits outside [range_lo, range_hi) (the 99 language tokens are contiguous) count as -inf;
+//     range_argmax[row] = the most probable token of the range, range_probs[row][j] = softmax over the range;
+//   * probe_prob[row] = softmax over the WHOLE vocabulary evaluated at probe_token (the nospeech token).
+// One CTA per row: two passes over the row (max, then sum of exponentials, like torch's softmax), fp32 throughout.
+// =====================================================================================================
+namespace b200
+{
+__global__ void __launch_bounds__(256) range_softmax_kernel(const float* __restrict__ logits, int vocab, int range_lo,
+    int range_hi, int probe_token, int32_t* __restrict__ range_argmax, float* __restrict__ range_probs,
+    float* __restrict__ probe_prob)
+{
+    __shared__ float red_f[8];
+    __shared__ int red_i[8];
+    __shared__ float bc[2];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* x = logits + (size_t) row * vocab;
+    grid_dep_wait();
+    grid_dep_launch_dependents();
+
+    auto block_max = [&](float v) -> float
+    {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1)
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0)
+            red_f[warp] = v;
+        __syncthreads();
+        float r = red_f[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w)
+            r = fmaxf(r, red_f[w]);
+        __syncthreads();
+        return r;
+    };
+    auto block_sum = [&](float v) -> float
+    {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0)
+            red_f[warp] = v;
+        __syncthreads();
+        float r = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+            r += red_f[w];
+        __syncthreads();
+        return r;
+    };
+
+    if (probe_prob != nullptr)
+    {
+        float m = -CUDART_INF_F;
+        for (int i = tid; i < vocab; i += 256)
+            m = fmaxf(m, x[i]);
+        m = block_max(m);
+        float s = 0.f;
+        for (int i = tid; i < vocab; i += 256)
+            s += expf(x[i] - m);
+        s = block_sum(s);
+        if (tid == 0)
+            probe_prob[row] = expf(x[probe_token] - m) / s;
+    }
+    if (range_argmax != nullptr || range_probs != nullptr)
+    {
+        float m = -CUDART_INF_F;
+        int arg = range_hi;
+        for (int i = range_lo + tid; i < range_hi; i += 256)
+            if (x[i] > m)
+            {
+                m = x[i];
+                arg = i;
+            }
+        // (max, lowest index) across the block: torch.argmax returns the first maximum
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1)
+        {
+            const float om = __shfl_xor_sync(0xffffffffu, m, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (om > m || (om == m && oa < arg))
+            {
+                m = om;
+                arg = oa;
+            }
+        }
+        if (lane == 0)
+        {
+            red_f[warp] = m;
+            red_i[warp] = arg;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int w = 1; w < 8; ++w)
+                if (red_f[w] > m || (red_f[w] == m && red_i[w] < arg))
+                {
+                    m = red_f[w];
+                    arg = red_i[w];
+                }
+            bc[0] = m;
+            if (range_argmax != nullptr)
+                range_argmax[row] = arg;
+        }
+        __syncthreads();
+        m = bc[0];
+        float s = 0.f;
+        for (int i = range_lo + tid; i < range_hi; i += 256)
+            s += expf(x[i] - m);
+        s = block_sum(s);
+        if (range_probs != nullptr)
+            for (int i = range_lo + tid; i < range_hi; i += 256)
+                range_probs[(size_t) row * (range_hi - range_lo) + (i - range_lo)] = expf(x[i] - m) / s;
+    }
+}
+} // namespace b200
+
+extern "C" int b200_logits_range_softmax(const float* logits, int rows, int vocab, int range_lo, int range_hi,
+    int probe_token, int32_t* range_argmax, float* range_probs, float* probe_prob, b200_stream_t stream)
+{
+    B200_REQUIRE(logits != nullptr, B200_ERR_INVALID_ARG, "null pointer (logits)");
+    B200_REQUIRE(vocab > 0 && range_lo >= 0 && range_lo < range_hi && range_hi <= vocab, B200_ERR_INVALID_ARG,
+        "bad token range [%d, %d) for a vocabulary of %d", range_lo, range_hi, vocab);
+    B200_REQUIRE(probe_prob == nullptr || (probe_token >= 0 && probe_token < vocab), B200_ERR_INVALID_ARG,
+        "probe token %d outside the vocabulary", probe_token);
+    B200_REQUIRE(range_argmax || range_probs || probe_prob, B200_ERR_INVALID_ARG, "no output requested");
+    if (rows <= 0)
+        return B200_OK;
+    B200_REQUIRE_DEVICE();
+    B200_LAUNCH(range_softmax_kernel, dim3(rows), dim3(256), 0, as_stream(stream), logits, vocab, range_lo, range_hi,
+        probe_token, range_argmax, range_probs, probe_prob);
+    return B200_OK;
+}

@@ -77,10 +77,22 @@ class WhisperPipeline:
                                           tokenizer.suppress_tokens(suppress), mi)
         self._filter_tokenizer = tokenizer
 
-    def transcribe(self, audio, tokenizer, sample_len=None):
+    def detect_language(self, audio_features, tokenizer):
+        """decoding.py:703-741 for the decoder's batch: -> (language codes, [{code: probability}], no-speech
+        probabilities).  Installs the cross-KV caches of `audio_features` in the decoder."""
+        self.decoder.set_encoder_output(audio_features)
+        toks = tokenizer.all_language_tokens
+        lang, probs, nsp = self.decoder.detect_language(tokenizer.sot, toks[0], toks[-1] + 1, tokenizer.no_speech)
+        codes = tokenizer.all_language_codes
+        lang, probs, nsp = lang.cpu().tolist(), probs.cpu().tolist(), nsp.cpu().tolist()
+        return [codes[t - toks[0]] for t in lang], [dict(zip(codes, row)) for row in probs], nsp
+
+    def transcribe(self, audio, tokenizer, sample_len=None, detect_language=False):
         """run.py:57-66 for a batch of waveforms: greedy decode from the tokenizer's sot sequence with the logit filters
         on, tokens cut at the first end-of-text (decoding.py:836-840), text when the tokenizer has a vocabulary.
-        -> list of {"tokens": [...], "text": str or None, "sum_logprob": float}."""
+        -> list of {"tokens": [...], "text": str or None, "sum_logprob": float}; with detect_language also "language",
+        "language_probs" and "no_speech_prob" (run.py:58; the prompt keeps the tokenizer's language, as the reference
+        does when options.language is set)."""
         if getattr(self, "_filter_tokenizer", None) is not tokenizer:
             self.enable_filters(tokenizer)
         prompt = list(tokenizer.sot_sequence)
@@ -94,11 +106,17 @@ class WhisperPipeline:
             nb = m.shape[0]
             if nb < self.B:
                 m = torch.cat([m, m[:1].expand(self.B - nb, -1, -1)], dim=0)
-            self.decoder.set_encoder_output(self.get_audio_features(m.contiguous()))
+            xa = self.get_audio_features(m.contiguous())
+            extra = self.detect_language(xa, tokenizer) if detect_language else None
+            if extra is None:
+                self.decoder.set_encoder_output(xa)
             tok = self.decoder.decode([prompt] * self.B, sample_len).cpu().tolist()
             lp = self.decoder.logit_filter.sum_logprobs.cpu().tolist()
             for row, s in zip(tok[:nb], lp[:nb]):
                 ids = row[:row.index(tokenizer.eot)] if tokenizer.eot in row else row
                 text = tokenizer.decode(ids).strip() if tokenizer.encoding is not None else None
                 results.append({"tokens": ids, "text": text, "sum_logprob": s})
+                if extra is not None:
+                    i = len(results) - 1 - b0
+                    results[-1].update(language=extra[0][i], language_probs=extra[1][i], no_speech_prob=extra[2][i])
         return results

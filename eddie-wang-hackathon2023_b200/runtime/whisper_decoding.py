@@ -314,6 +314,30 @@ class WhisperDecoding:
         self.tokens.copy_(self.next_tokens)
         return self.next_tokens
 
+    def detect_language(self, sot, language_lo, language_hi, no_speech=None):
+        """Forward pass over a lone start-of-transcript token (decoding.py:712-719), then on the device: the most
+        probable language token and the softmax over the language tokens [language_lo, language_hi) (:721-725), and the
+        no-speech probability = softmax over the whole vocabulary at `no_speech` (:762-766).
+        Returns (language_tokens int32 [B], language_probs fp32 [B, n_languages], no_speech_probs fp32 [B] or None);
+        the decoder state is reset afterwards, the logit-filter state is not touched."""
+        filt = getattr(self, "logit_filter", None)
+        self.logit_filter = None
+        try:
+            self.reset()
+            self.prefill([[int(sot)]] * self.B)
+        finally:
+            self.logit_filter = filt
+        self.reset()
+        n = language_hi - language_lo
+        lang = torch.empty((self.B,), dtype=torch.int32, device=self.device)
+        probs = torch.empty((self.B, n), dtype=torch.float32, device=self.device)
+        nsp = torch.empty((self.B,), dtype=torch.float32, device=self.device) if no_speech is not None else None
+        rc = self.lib.b200_logits_range_softmax(self.logits.data_ptr(), self.B, self.V, language_lo, language_hi,
+                                                -1 if no_speech is None else int(no_speech), lang.data_ptr(),
+                                                probs.data_ptr(), None if nsp is None else nsp.data_ptr(), self._st())
+        _lib.check(rc, "logits_range_softmax")
+        return lang, probs, nsp
+
     def _step_body(self):
         B = self.B
         self.lib.b200_set_static_kv_hint(1 if self.static_kv else 0)

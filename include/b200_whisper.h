@@ -241,6 +241,14 @@ int b200_whisper_filtered_argmax(const float* logits, int rows, int vocab, const
     int no_timestamps, int timestamp_begin, int blank_token, int max_initial_timestamp_index, int32_t* decode_state,
     int32_t* next_token, float* sum_logprobs, b200_stream_t stream);
 
+/* Language detection and the no-speech probability, both from the logits of the start-of-transcript position
+ * (T/examples/whisper/decoding.py:703-741: logits outside the language tokens set to -inf, argmax, softmax; :762-766:
+ * softmax over the whole vocabulary at the nospeech token).  logits [rows, vocab] fp32; [range_lo, range_hi) = the
+ * language tokens (contiguous ids); range_argmax [rows] int32, range_probs [rows, range_hi - range_lo] fp32,
+ * probe_prob [rows] fp32 -- each output may be NULL. */
+int b200_logits_range_softmax(const float* logits, int rows, int vocab, int range_lo, int range_hi, int probe_token,
+    int32_t* range_argmax, float* range_probs, float* probe_prob, b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Conv1d encoder stem (fp16, fp32 accumulate), optional fused GELU.
  * Replaces  functional.conv1d -> TensorRT IConvolutionLayer  T/tensorrt_llm/functional.py:2202-2244,

@@ -71,6 +71,11 @@ def test_argument_validation_without_gpu(lib):
     assert lib.b200_attention_bidirectional_fp16(None, None, 1, 1500, 20, 64, None) == 1
     assert lib.b200_whisper_filtered_argmax(None, 1, 51865, None, 50257, 50363, 50364, 220, -1, None, None, None, None) == 1
     assert lib.b200_transpose_add_pos_fp16(None, None, None, 1, 1280, 1500, None) == 1
+    x = torch.zeros(8)
+    assert lib.b200_logits_range_softmax(None, 1, 51865, 50259, 50358, 50362, None, None, None, None) == 1
+    assert lib.b200_logits_range_softmax(x.data_ptr(), 1, 8, 5, 3, 0, x.data_ptr(), None, None, None) == 1   # empty range
+    assert lib.b200_logits_range_softmax(x.data_ptr(), 1, 8, 2, 6, 9, None, None, x.data_ptr(), None) == 1   # probe outside
+    assert lib.b200_logits_range_softmax(x.data_ptr(), 1, 8, 2, 6, 0, None, None, None, None) == 1           # no output
 
 
 def test_quant_mode_flags():

@@ -95,3 +95,58 @@ def test_transcribe_with_filters_and_tokenizer():
     for r, row in zip(res[:B], rows):
         assert r["tokens"] == (row[:row.index(tk.eot)] if tk.eot in row else row)
     assert isinstance(dec, WhisperDecoding)
+
+
+def test_range_softmax_kernel_against_torch():
+    """b200_logits_range_softmax vs the reference's own lines (decoding.py:721-725 and :765-766) evaluated with torch."""
+    import b200_whisper
+    from b200_whisper import _lib
+    lib = b200_whisper.load()
+    torch.manual_seed(3)
+    rows, V, lo, hi, probe = 5, 51865, 50259, 50358, 50362
+    logits = (torch.randn(rows, V) * 4).cuda()
+    logits[2, lo + 7] = logits[2, lo + 40] = 30.0          # a tie: the first maximum wins, like torch.argmax
+    lang = torch.empty(rows, dtype=torch.int32, device="cuda")
+    probs = torch.empty(rows, hi - lo, device="cuda")
+    nsp = torch.empty(rows, device="cuda")
+    _lib.check(lib.b200_logits_range_softmax(logits.data_ptr(), rows, V, lo, hi, probe, lang.data_ptr(), probs.data_ptr(),
+                                             nsp.data_ptr(), _lib.stream_ptr()))
+    ref = logits.clone().cpu()
+    mask = torch.ones(V, dtype=torch.bool)
+    mask[lo:hi] = False
+    ref[:, mask] = -float("inf")
+    assert lang.cpu().tolist() == ref.argmax(dim=-1).tolist() and lang[2].item() == lo + 7
+    torch.testing.assert_close(probs.cpu(), ref.softmax(dim=-1)[:, lo:hi], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(nsp.cpu(), logits.cpu().float().softmax(dim=-1)[:, probe], rtol=1e-4, atol=1e-9)
+    assert abs(probs.sum(dim=-1).cpu() - 1).max().item() < 1e-5
+
+
+def test_detect_language_and_no_speech():
+    """WhisperPipeline.detect_language against the oracle decoder's logits for a lone sot token."""
+    from b200_whisper.runtime import WhisperPipeline
+    from b200_whisper.tokenizer import Tokenizer
+    dims = wo.ModelDimensions(80, 96, 128, 2, 2, 2048, 64, 128, 2, 2)
+    tk = Tokenizer("en", "transcribe", n_ranks=2048 - 1608)
+    B, n = 2, 2 * dims.n_audio_ctx * 160
+    sd = wo.synthetic_state_dict(dims, seed=2)
+    sdq = wo.quantize_state_dict(sd, dims, decoder_only=False)
+    scales = [0.05] * dims.n_text_layer
+    pipe = WhisperPipeline(dims, sd, B, scales, scales)
+    audio = np.stack([speech_like(n, 61), speech_like(n, 62, amp=0.4)])
+    xa = pipe.get_audio_features(pipe.log_mel(audio))
+    languages, probs, nsp = pipe.detect_language(xa, tk)
+    with torch.no_grad():
+        _, ref_logits = wo.greedy_decode(sdq, dims, xa.float().cpu(), [tk.sot], 1, scales, scales, act_fp16=True)
+    ref = ref_logits[0].float()
+    lo, hi = tk.all_language_tokens[0], tk.all_language_tokens[-1] + 1
+    ref_p = ref[:, lo:hi].softmax(dim=-1)
+    ref_nsp = ref.softmax(dim=-1)[:, tk.no_speech]
+    for b in range(B):
+        got = torch.tensor([probs[b][c] for c in tk.all_language_codes])
+        assert (got - ref_p[b]).abs().max().item() <= 2e-2 * ref_p[b].max().item() + 1e-4
+        top = ref_p[b].topk(2).values
+        if (top[0] - top[1]).item() > 1e-2 * top[0].item():
+            assert languages[b] == tk.all_language_codes[int(ref_p[b].argmax())]
+        assert abs(nsp[b] - ref_nsp[b].item()) <= 2e-2 * ref_nsp[b].item() + 1e-6
+    res = pipe.transcribe(audio, tk, sample_len=6, detect_language=True)
+    assert [r["language"] for r in res] == languages and all(0.0 <= r["no_speech_prob"] <= 1.0 for r in res)
