@@ -145,9 +145,15 @@ __global__ void __launch_bounds__(256) whisper_filtered_argmax_kernel(const floa
             RangeAcc T{-CUDART_INF_F, 0.f, 0x7fffffff}, S{-CUDART_INF_F, 0.f, 0x7fffffff};
             for (int q = 0; q < parts; ++q) // fixed order: bit-reproducible
             {
-                const volatile float* pq = scratch + ((size_t) r * parts + q) * 6;
+                volatile float* pq = scratch + ((size_t) r * parts + q) * 6;
                 T = acc_merge(T, RangeAcc{pq[0], pq[1], __float_as_int(pq[2])});
                 S = acc_merge(S, RangeAcc{pq[3], pq[4], __float_as_int(pq[5])});
+                // the scratch lives in the library's shared pool of self-resetting counter slots: every word must be
+                // zero again when the launch ends, or the next user of the slot (split-K / split-KV arrival counters)
+                // starts from garbage
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    pq[j] = 0.f;
             }
             const float lse_t = T.s > 0.f ? T.m + logf(T.s) : -CUDART_INF_F;
             const float lse_s = S.s > 0.f ? S.m + logf(S.s) : -CUDART_INF_F;

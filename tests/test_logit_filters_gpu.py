@@ -86,3 +86,29 @@ def test_decoder_with_filters_matches_oracle_filters_on_its_own_logits():
     for _ in range(n_new - 1):
         check(dec.step())
     np.testing.assert_allclose(dec.logit_filter.sum_logprobs.cpu().numpy(), sums, rtol=1e-4, atol=1e-3)
+
+
+def test_filter_kernel_leaves_the_shared_scratch_pool_clean():
+    """The filter kernel borrows a slot of the library's pool of self-resetting arrival counters (64 slots handed out
+    round-robin).  Regression: it used to leave its partial results behind, so after 64 more allocations another kernel
+    (here the split cross-attention, which merges its parts when an arrival counter reaches the part count) started from
+    non-zero counters and never merged.  Run the filter, cycle through the whole pool with cross-attention calls, and
+    require every one of them to match the first."""
+    from b200_whisper.functional import WhisperLogitFilter, cross_attention
+    torch.manual_seed(0)
+    B, H, S = 2, 2, 96            # 4 (row, head) pairs: the split kernel with global partials + counters
+    q = torch.randn(B, H * 64, device="cuda").half()
+    kv = torch.randint(-127, 128, (B, 2, H, S, 64), dtype=torch.int8, device="cuda")
+    scale = torch.tensor([0.02], device="cuda")
+    want = cross_attention(q, kv, scale, H, 64)
+    V = 4096
+    filt = WhisperLogitFilter(8, V, V - 40, None, V - 30, 5, [1, 2, 9], 10)
+    logits = torch.randn(8, V, device="cuda")
+    nxt = torch.empty(8, dtype=torch.int32, device="cuda")
+    for _ in range(70):           # dirty (formerly) every slot of the pool
+        filt(logits, nxt)
+    torch.cuda.synchronize()
+    for i in range(70):
+        got = torch.full_like(want, float("nan"))   # a merge that never happens leaves the NaNs in place
+        cross_attention(q, kv, scale, H, 64, out=got)
+        assert torch.equal(got, want), i
