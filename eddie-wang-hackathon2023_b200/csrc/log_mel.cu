@@ -7,17 +7,18 @@
 //   201 bins, last frame dropped, mel = filters[n_mels, 201] @ power, log10(max(mel, 1e-10)),
 //   max(., max over the utterance - 8), (. + 4) / 4.
 //
-// 0.96 GFLOP per 30 s utterance as a direct real DFT -- small next to the 1.9 TFLOP encoder, so this stays on the fp32
-// CUDA cores: the spectrum spans 8 decades (the clamp sits 80 dB below the utterance maximum) and fp16/tf32 tensor-core
+// 0.96 GFLOP per 30 s utterance as a direct real DFT (0.48 after the radix-2 step below) -- small next to the
+// 1.9 TFLOP encoder, so this stays on the fp32 CUDA cores: the spectrum spans 8 decades (the clamp sits 80 dB below the utterance maximum) and fp16/tf32 tensor-core
 // products would put their rounding noise at about -66 dB of every frame's strongest bin.  A sequentially accumulated
 // fp32 DFT lands within 1e-5 of the exact value in output units (the reference's own fp32 FFT: 3.6e-5).
 //
 // log_mel_power_kernel: one CTA = 32 consecutive frames of one utterance.
 //   1. the 5360 samples the frames cover go to shared memory once (coalesced, reflect-indexed), each 160-sample row
 //      shifted by one word so that the next step is free of bank conflicts;
-//   2. windowed frames are laid out sample-major xs[n][32 frames]; thread k owns DFT bin k for all 32 frames:
-//      per sample n one twiddle (cos, sin)[k n mod 400] from a shared table (computed in fp64 per CTA) and eight
-//      128-bit broadcast loads of xs[n][0..31] feed 64 FMAs on 64 register accumulators;
+//   2. one radix-2 step (sum and difference of the two halves of every windowed frame, laid out sample-major
+//      [n < 200][32 frames]) halves the arithmetic; a thread owns one DFT bin for all 32 frames (warps 0-3 the even
+//      bins, 4-7 the odd ones): per sample n one twiddle (cos, sin)[k n mod 400] from a shared table (computed in fp64
+//      per CTA) and eight 128-bit broadcast loads feed 64 FMAs on 64 register accumulators;
 //   3. power[k][f] overwrites xs; the mel projection walks the filterbank 32 bins at a time and skips zero weights with
 //      a ballot (391 of the 16080 weights are non-zero), lanes = frames so the stores along t are 128-byte rows;
 //   4. log10 and the utterance maximum (atomicMax on an order-preserving integer encoding).
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(kMelThreads, 2) log_mel_power_kernel(const flo
     uint32_t* __restrict__ max_enc)
 {
     extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                                   // [400][32] windowed samples, later power [201][32]
+    float* xs = sm;                                   // [2][200][32] half-frame sums / differences, later power [201][32]
     float* seg = xs + kMelNfft * kMelFT;              // row-shifted raw samples
     float2* tw = reinterpret_cast<float2*>(seg + kMelSegPad); // (cos, sin)(2 pi j / 400)
     float* win = reinterpret_cast<float*>(tw + kMelNfft);
@@ -78,12 +79,18 @@ __global__ void __launch_bounds__(kMelThreads, 2) log_mel_power_kernel(const flo
     }
     __syncthreads();
 
-    // ---- 2. xs[n][f] = win[n] * sample(f*160 + n); lanes = frames: conflict-free on both sides ----
-    for (int idx = tid; idx < kMelNfft * kMelFT; idx += kMelThreads)
+    // ---- 2. one radix-2 step: exp(-2 pi i k (n + 200) / 400) = (-1)^k exp(-2 pi i k n / 400), so
+    //      X[k] = sum_{n < 200} (xw[n] + (-1)^k xw[n + 200]) tw[k n mod 400]   with xw = window * samples.
+    //      xs[0][n][f] = xw[n] + xw[n + 200] feeds the even bins, xs[1][n][f] = xw[n] - xw[n + 200] the odd ones: half the
+    //      multiply-adds of the plain DFT.  lanes = frames: conflict-free on both sides ----
+    constexpr int kHalf = kMelNfft / 2;
+    for (int idx = tid; idx < kHalf * kMelFT; idx += kMelThreads)
     {
         const int f = idx & (kMelFT - 1), n = idx >> 5;
-        const int i = f * kMelHop + n;
-        xs[idx] = win[n] * seg[i + i / kMelHop];
+        const int i0 = f * kMelHop + n, i1 = i0 + kHalf;
+        const float lo = win[n] * seg[i0 + i0 / kMelHop], hi = win[n + kHalf] * seg[i1 + i1 / kMelHop];
+        xs[idx] = lo + hi;
+        xs[kHalf * kMelFT + idx] = lo - hi;
     }
     __syncthreads();
 
@@ -91,17 +98,20 @@ __global__ void __launch_bounds__(kMelThreads, 2) log_mel_power_kernel(const flo
 #pragma unroll
     for (int f = 0; f < kMelFT; ++f)
         re[f] = im[f] = 0.f;
-    const int k = tid;
+    // warps 0-3: even bins 0, 2, ..., 200; warps 4-7: odd bins 1, 3, ..., 199 (warp-uniform source array)
+    const int odd = tid >> 7;
+    const int k = 2 * (tid & 127) + odd;
     if (k < kMelBins)
     {
+        const float* src = xs + odd * (kHalf * kMelFT);
         int j = 0;
 #pragma unroll 2
-        for (int n = 0; n < kMelNfft; ++n)
+        for (int n = 0; n < kHalf; ++n)
         {
             const float2 t = tw[j];
             j += k;
             j = j >= kMelNfft ? j - kMelNfft : j;
-            const float4* xr = reinterpret_cast<const float4*>(xs + n * kMelFT);
+            const float4* xr = reinterpret_cast<const float4*>(src + n * kMelFT);
 #pragma unroll
             for (int q = 0; q < kMelFT / 4; ++q)
             {
