@@ -8,7 +8,9 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("rows,cols", [(1, 1280), (16, 1280), (7, 384), (3, 128), (2, 5120)])
+# rows >= 1024 take the warp-per-row kernel (the encoder's 24000 x 1280), fewer rows the CTA-per-row one
+@pytest.mark.parametrize("rows,cols", [(1, 1280), (16, 1280), (7, 384), (3, 128), (2, 5120), (24000, 1280), (1500, 384),
+                                       (1027, 128), (1024, 2048), (1025, 4096)])
 def test_layernorm(rows, cols):
     from b200_whisper.functional import layer_norm
     torch.manual_seed(rows)

@@ -119,7 +119,8 @@ def test_tc_whisper_shapes(k, n, m):
     tight_check(mat1, raw.cpu(), scales.cpu(), out, f"tc m={m} k={k} n={n}")
 
 
-@pytest.mark.parametrize("policy,m", [("simt", 1), ("simt", 4), ("tc", 16), ("tc", 48)])
+@pytest.mark.parametrize("policy,m", [("simt", 1), ("simt", 4), ("tc", 16), ("tc", 48), ("tc", 100), ("tc", 300),
+                                      ("tc", 1500)])
 def test_fused_epilogue(policy, m):
     """bias, GELU and residual fused in the epilogue == the reference's separate fp16 layers (layer.py:311-312)."""
     import b200_whisper as bw
@@ -138,6 +139,39 @@ def test_fused_epilogue(policy, m):
     # deterministic: same inputs, same bits
     again = run_plugin(mat1, proc, scales, policy, bias=bias.cuda(), activation="gelu", residual=resid.cuda())
     assert torch.equal(fused, again)
+
+
+@pytest.mark.parametrize("m", [16, 200, 1500])
+def test_residual_in_place(m):
+    """x += Linear(h): the output buffer IS the residual (how the encoder and decoder runtimes update the residual stream).
+    Large tiles fetch a batch of residual rows before they store any, so the in-place form must still read every element
+    before it is overwritten."""
+    import b200_whisper as bw
+    from b200_whisper import _lib
+    lib = _lib.load()
+    k, n = 1280, 1280
+    h = gen((m, k), seed=31).cuda()
+    weight = gen((k, n), seed=32) * 0.05
+    bias = gen((n,), seed=33).cuda()
+    x0 = gen((m, n), seed=34).cuda()
+    raw, proc, scales = bw.ops._symmetric_quantize_last_axis_of_batched_matrix(weight.cuda(), torch.int8)
+    ws = torch.empty((max(lib.b200_woq_workspace_bytes(m, n, k), 1 << 20),), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(residual, out):
+        _lib.check(lib.b200_woq_int8_gemm_fused(h.data_ptr(), m, k, proc.data_ptr(), scales.data_ptr(), n, bias.data_ptr(),
+                                                _lib.ACT_NONE, residual.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), st), "fused gemm")
+        torch.cuda.synchronize()
+
+    separate = torch.empty_like(x0)
+    run(x0, separate)
+    x = x0.clone()
+    run(x, x)
+    assert torch.equal(x, separate)
+    plain = run_plugin(h.cpu(), proc.cpu(), scales.cpu(), "tc", bias=bias)
+    want = (plain.float() + x0.cpu().float()).half()
+    assert (x.cpu().float() - want.float()).abs().max().item() <= 2e-3 * want.float().abs().max().item() + 1e-3
 
 
 def test_linearity_property_large():

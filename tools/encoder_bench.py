@@ -60,3 +60,15 @@ for e in prof.events():
         agg[e.name.split("<")[0].split("(")[0][-60:]] += e.time_range.end - e.time_range.start
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]:
     print(f"   {v / 1e3:8.2f} ms  {k}")
+# launch-by-launch view of the second layer (start relative to the layer's first kernel, duration)
+evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+             key=lambda e: e.time_range.start)
+names = [e.name.split("<")[0].split("(")[0][-40:] for e in evs]
+ln_idx = [i for i, n in enumerate(names) if "layernorm" in n]
+if len(ln_idx) >= 5:
+    i0, i1 = ln_idx[2], ln_idx[4]
+    t0 = evs[i0].time_range.start
+    print("second layer, launch by launch (us):")
+    for e, n in zip(evs[i0:i1], names[i0:i1]):
+        print(f"   +{e.time_range.start - t0:8.1f}  dur {e.time_range.end - e.time_range.start:8.1f}  {n}")
+    print(f"   layer total {evs[i1].time_range.start - t0:8.1f}")
