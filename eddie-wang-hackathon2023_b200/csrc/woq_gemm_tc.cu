@@ -1155,6 +1155,10 @@ static int g_splitk_mode = -1; // -1 auto (env B200_SPLITK: "cluster" | "global"
 
 static int g_cluster16 = -1; // env B200_CLUSTER16=1 enables 16-CTA (non-portable) clusters for deep-K decode GEMMs
 
+#ifndef B200_TC_SMALL_GRID_128
+#define B200_TC_SMALL_GRID_128 1
+#endif
+
 TcPlan plan_tc(int M, int N, int K)
 {
     if (g_cluster16 < 0)
@@ -1169,6 +1173,11 @@ TcPlan plan_tc(int M, int N, int K)
     }
     TcPlan pl{};
     pl.MT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+    // 256-row tiles are never split, so a problem with fewer of them than SMs leaves the GPU under-filled (M = 256,
+    // 5120 -> 1280: 10 CTAs walking all of K, 38.8 us against 11.1 us at M = 128): take 128-row tiles there, which
+    // doubles the tile count and keeps the cluster split-K available
+    if (pl.MT == 256 && B200_TC_SMALL_GRID_128 && (long long) ((M + 255) / 256) * ((N + 127) / 128) < num_sms())
+        pl.MT = 128;
     pl.m_tiles = (M + pl.MT - 1) / pl.MT;
     pl.n_tiles = (N + 127) / 128;
     const int kb_total = K / 64;

@@ -103,7 +103,8 @@ def test_quant_mode_flags():
 
 def test_tc_launch_plan_for_the_decoder_shapes(lib):
     """The split-K planner (host logic, 148 SMs assumed without a GPU): the decode shapes of large-v2 get cluster splits
-    that keep each CTA's k range inside the weight ring, 256-row tiles are not split, the M = 128 cliff stays fixed."""
+    that keep each CTA's k range inside the weight ring, 256-row tiles are not split (and only used when they fill the
+    GPU), the M = 128 cliff stays fixed."""
     import ctypes
     if os.environ.get("B200_SPLITK", "cluster") != "cluster":
         pytest.skip("planner defaults are tested in cluster mode")
@@ -121,7 +122,9 @@ def test_tc_launch_plan_for_the_decoder_shapes(lib):
     assert plan(1, 3840, 1280)[0] == 16 and plan(1, 3840, 1280)[4] == 1
     mt, mtiles, ntiles, splits, cluster = plan(128, 3840, 1280)
     assert mt == 128 and cluster == 1 and 2 <= splits <= 8
-    assert plan(256, 3840, 1280)[3] == 1                # 256-row tiles: unsplit
+    # fewer 256-row tiles than SMs: 128-row tiles instead (twice the CTAs, cluster split-K still available)
+    assert plan(256, 3840, 1280) == (128, 2, 30, 2, 1) and plan(256, 1280, 5120) == (128, 2, 10, 4, 1)
+    assert plan(1500, 1280, 5120) == (128, 12, 10, 1, 0) and plan(1500, 3840, 1280)[:4] == (256, 6, 30, 1)
     assert plan(24000, 3840, 1280)[:4] == (256, 94, 30, 1)
     for m, n, k in [(16, 3840, 1280), (16, 1280, 5120), (32, 1280, 1280), (32, 3840, 1280), (4, 1280, 1280)]:
         mt, _, nt, s, c = plan(m, n, k)

@@ -42,7 +42,7 @@ for k, n in ((1280, 3840), (1280, 5120), (5120, 1280)):
     for i in range(L):
         w = ((torch.rand((k, n), device=dev) * 2 - 1) * 0.05).half()
         ws_.append(bw.ops.symmetric_quantize_last_axis_of_batched_matrix(w, torch.int8))
-    for m in (1, 2, 4, 8, 16, 32, 64, 128, 256, 1500, 24000):
+    for m in [int(v) for v in os.environ.get("SWEEP_M", "1,2,4,8,16,32,64,128,256,1500,24000").split(",")]:
         x = (torch.rand((m, k), device=dev) * 2 - 1).half()
         o = torch.empty((m, n), dtype=torch.float16, device=dev)
         wk = torch.empty((lib.b200_woq_workspace_bytes(m, n, k),), dtype=torch.uint8, device=dev)
