@@ -120,6 +120,52 @@ __device__ __forceinline__ __half finish_output(float acc, bool has_bias, float 
     return o;
 }
 
+// Large-tile (M >= 64 rows per tile, unsplit) epilogue arithmetic.  ncu (source counters, M = 24000, 1280 -> 5120 with
+// GELU) showed that kernel issue-bound on its EPILOGUE: 79 warp instructions per 32 outputs, led by FSEL (erff evaluates
+// both of its argument ranges and selects), per-row bounds checks and 64-bit index arithmetic.  This variant
+//   * adds bias and residual with HADD2: the sum of two fp16 values is exact in fp32 whenever it can influence the fp16
+//     rounding, so __hadd(a, b) == fp16(float(a) + float(b)) bit for bit (what finish_output computes);
+//   * evaluates erf branch-free (Abramowitz & Stegun 7.1.26 with MUFU.RCP / MUFU.EX2, |error| <= 2e-7): over all 63488
+//     finite fp16 inputs the rounded GELU differs from the erff-based one in 0.7 % of them, by at most 2 fp16 ulp
+//     (3.1e-5 absolute).  The decode-sized epilogues keep erff (finish_output_rt), so the decoder's bits do not change.
+#ifndef B200_TC_FAST_ERF
+#define B200_TC_FAST_ERF 1
+#endif
+__device__ __forceinline__ float erf_branch_free(float x)
+{
+    const float ax = fabsf(x);
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+    return copysignf(fmaf(-pl * t, e, 1.0f), x);
+}
+
+template <int ACT>
+__device__ __forceinline__ __half finish_output_tile(float acc, bool has_bias, __half bias_h, bool has_res, __half res_h)
+{
+    __half o = __float2half_rn(acc);
+    if (has_bias)
+        o = __hadd(o, bias_h);
+    if constexpr (ACT == B200_ACT_GELU_ERF)
+    {
+        const float xf = __half2float(o);
+#if B200_TC_FAST_ERF
+        o = __float2half_rn(0.5f * xf * (1.0f + erf_branch_free(xf * 0.70710678118654752440f)));
+#else
+        o = __float2half_rn(gelu_erf(xf));
+#endif
+    }
+    else if constexpr (ACT == B200_ACT_GELU_TANH)
+        o = __float2half_rn(gelu_tanh(__half2float(o)));
+    if (has_res)
+        o = __hadd(o, res_h);
+    return o;
+}
+
 // Run-time activation: used by the decode-sized cluster reduction, where ONE compact instruction stream matters more than
 // the masked-off instructions (six specialised copies of that epilogue measured 8 % slower on the decoder step:
 // instruction-cache misses on the critical path of a 3 us kernel).
@@ -702,9 +748,13 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                 constexpr bool FOLD = decltype(fold_c)::value;
                 constexpr int CB = kHalfCols >= 32 ? 32 : kHalfCols;
 #pragma unroll 1
+                const __half bias_h = __float2half_rn(own_bias); // own_bias came from an fp16 value: exact
                 for (int cb = 0; cb < kHalfCols / CB; ++cb)
                 {
                     const int ml0 = kh * kHalfCols + cb * CB;
+                    const int rows_here = m_valid - ml0; // rows of this batch inside the matrix (may be <= 0)
+                    const size_t base = (size_t) (m_tile * MT + ml0) * p.ldc + n;
+                    const bool full = rows_here >= CB;
                     // The residual usually IS the output buffer (x += ...), so the compiler must keep every residual
                     // load behind the store of the row before it: one exposed load latency per row (it made the
                     // M = 24000 GEMMs with a residual 2-5x slower than the plain ones).  Fetch the batch's residuals
@@ -712,10 +762,11 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                     __half resv[CB];
                     if (has_res && n < p.N)
                     {
+                        const __half* rp = p.residual + base;
 #pragma unroll
                         for (int i = 0; i < CB; ++i)
-                            if (ml0 + i < m_valid)
-                                resv[i] = p.residual[(size_t) (m_tile * MT + ml0 + i) * p.ldc + n];
+                            if (full || i < rows_here)
+                                resv[i] = rp[(size_t) i * p.ldc];
                     }
                     uint32_t acc[CB];
 #pragma unroll
@@ -724,19 +775,30 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (n < p.N)
                     {
-#pragma unroll
-                        for (int i = 0; i < CB; ++i)
+                        __half* cp = p.C + base;
+                        if (full)
                         {
-                            const int ml = ml0 + i;
-                            if (ml < m_valid)
+                            // whole batch inside the matrix (all but the last m-tile): no per-row predicate
+#pragma unroll
+                            for (int i = 0; i < CB; ++i)
                             {
                                 float v = __uint_as_float(acc[i]) * scf;
                                 if constexpr (FOLD)
-                                    v = ln_fin[2 * ml + 1] * (v - ln_fin[2 * ml] * own_c1) + own_c2;
-                                const size_t idx = (size_t) (m_tile * MT + ml) * p.ldc + n;
-                                const float res = has_res ? __half2float(resv[i]) : 0.f;
-                                p.C[idx] = finish_output<ACT>(v, has_bias, own_bias, has_res, res);
+                                    v = ln_fin[2 * (ml0 + i) + 1] * (v - ln_fin[2 * (ml0 + i)] * own_c1) + own_c2;
+                                cp[(size_t) i * p.ldc] = finish_output_tile<ACT>(v, has_bias, bias_h, has_res, resv[i]);
                             }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int i = 0; i < CB; ++i)
+                                if (i < rows_here)
+                                {
+                                    float v = __uint_as_float(acc[i]) * scf;
+                                    if constexpr (FOLD)
+                                        v = ln_fin[2 * (ml0 + i) + 1] * (v - ln_fin[2 * (ml0 + i)] * own_c1) + own_c2;
+                                    cp[(size_t) i * p.ldc] = finish_output_tile<ACT>(v, has_bias, bias_h, has_res, resv[i]);
+                                }
                         }
                     }
                 }
