@@ -6,7 +6,7 @@
 // Flash-attention style: one CTA per (64 query rows, head, batch), 4 warps x 16 rows; K and V tiles of 64 keys are
 // double-buffered in shared memory with cp.async (16-byte chunks XOR-swizzled by the row so every ldmatrix is
 // conflict-free); scores and P.V run on the tensor cores (mma.sync.m16n8k16, fp32 accumulate), the online softmax
-// lives in registers in the log2 domain, the score accumulators are re-used in place as the fp16 A fragments of P.
+// lives in registers (ex2 with the scale folded into one FFMA, lazily rescaled accumulators), the score accumulators are re-used in place as the fp16 A fragments of P.
 // Round 1 uses the warp-level mma.sync path (the encoder runs once per utterance, off the decoder-step metric); a
 // tcgen05 / TMEM version of this kernel is the natural round-2 upgrade.
 #include <float.h>
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) attention_bidir_kernel(const __half* __re
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             o[j][i] = 0.f;
-    float m0 = -FLT_MAX, m1 = -FLT_MAX, l0 = 0.f, l1 = 0.f; // rows g and g + 8 of the warp's 16
+    float m0 = -FLT_MAX, m1 = -FLT_MAX, l0 = 0.f, l1 = 0.f; // rows g and g + 8 of the warp's 16; m in raw score units
     const float sl2 = 0.125f * 1.4426950408889634f;       // 1/sqrt(64) * log2(e)
 
     for (int it = 0; it < n_tiles; ++it)
@@ -162,17 +162,30 @@ __global__ void __launch_bounds__(128) attention_bidir_kernel(const __half* __re
                 mma16816(s[2 * np + 1], qa[kk], kf[2], kf[3]);
             }
         }
-        // ---- online softmax (log2 domain); columns of s[j]: keys it*64 + j*8 + 2t, +1 ----
-        const int key0 = it * kBN + 2 * t;
-        float mx0 = m0, mx1 = m1;
+        // ---- online softmax; columns of s[j]: keys it*64 + j*8 + 2t, +1.  The running maxima m0 / m1 are kept in RAW
+        // score units; the 1/sqrt(64) * log2(e) factor rides on the FFMA that feeds ex2.  ncu had this kernel at 53 % tensor
+        // pipe with 6.6 other instructions per HMMA, so the loop is trimmed to what every tile needs:
+        //   * keys beyond S exist only in the last tile: no per-key predicate elsewhere;
+        //   * the accumulators are rescaled only when a row maximum grew by more than kLazy (in log2 units) since the
+        //     maximum the accumulators are expressed in; until then P is formed against that older maximum (P <= 2^kLazy:
+        //     no overflow in fp16 or fp32, and the final o / l cancels the common factor exactly).
+        if (it == n_tiles - 1 && (S % kBN) != 0)
+        {
+            const int key0 = it * kBN + 2 * t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                const int k = key0 + j * 8;
+                s[j][0] = k < S ? s[j][0] : -FLT_MAX;
+                s[j][1] = k + 1 < S ? s[j][1] : -FLT_MAX;
+                s[j][2] = k < S ? s[j][2] : -FLT_MAX;
+                s[j][3] = k + 1 < S ? s[j][3] : -FLT_MAX;
+            }
+        }
+        float mx0 = s[0][0], mx1 = s[0][2];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
         {
-            const int k = key0 + j * 8;
-            s[j][0] = k < S ? s[j][0] * sl2 : -FLT_MAX;
-            s[j][1] = k + 1 < S ? s[j][1] * sl2 : -FLT_MAX;
-            s[j][2] = k < S ? s[j][2] * sl2 : -FLT_MAX;
-            s[j][3] = k + 1 < S ? s[j][3] * sl2 : -FLT_MAX;
             mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
             mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
         }
@@ -180,25 +193,32 @@ __global__ void __launch_bounds__(128) attention_bidir_kernel(const __half* __re
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float c0 = ex2(m0 - mx0), c1 = ex2(m1 - mx1);
-        m0 = mx0;
-        m1 = mx1;
-        l0 *= c0;
-        l1 *= c1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
+        constexpr float kLazy = 8.0f;
+        const bool grow = (mx0 - m0) * sl2 > kLazy || (mx1 - m1) * sl2 > kLazy; // always true on the first tile
+        if (__any_sync(0xffffffffu, grow))
         {
-            o[j][0] *= c0;
-            o[j][1] *= c0;
-            o[j][2] *= c1;
-            o[j][3] *= c1;
+            const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
+            const float c0 = ex2((m0 - n0) * sl2), c1 = ex2((m1 - n1) * sl2);
+            m0 = n0;
+            m1 = n1;
+            l0 *= c0;
+            l1 *= c1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                o[j][0] *= c0;
+                o[j][1] *= c0;
+                o[j][2] *= c1;
+                o[j][3] *= c1;
+            }
         }
+        const float b0 = -m0 * sl2, b1 = -m1 * sl2;
         uint32_t pa[4][4]; // P as A fragments: k-step kk covers keys kk*16 .. +15 = score tiles 2kk, 2kk+1
 #pragma unroll
         for (int j = 0; j < 8; ++j)
         {
-            const float p0 = ex2(s[j][0] - mx0), p1 = ex2(s[j][1] - mx0);
-            const float p2 = ex2(s[j][2] - mx1), p3 = ex2(s[j][3] - mx1);
+            const float p0 = ex2(fmaf(s[j][0], sl2, b0)), p1 = ex2(fmaf(s[j][1], sl2, b0));
+            const float p2 = ex2(fmaf(s[j][2], sl2, b1)), p3 = ex2(fmaf(s[j][3], sl2, b1));
             l0 += p0 + p1;
             l1 += p2 + p3;
             pa[j >> 1][(j & 1) * 2 + 0] = pack_h2(p0, p1);
