@@ -56,6 +56,8 @@ _SIGS = {
     "b200_debug_tc_timeline": (_i, [_vp, _i]),
     "b200_mmha_generation": (_i, [ctypes.POINTER(MmhaParams), _vp]),
     "b200_attention_context": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "b200_mmha_generation_paged": (_i, [ctypes.POINTER(MmhaParams), _vp, _i, _i, _vp]),
+    "b200_attention_context_paged": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "b200_cross_attention_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b200_cross_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "b200_cross_kv_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -246,10 +246,38 @@ struct KvChunk<false>
 // the two halves (shared memory) remain.  64 fp16 registers of K/V per thread keep the CTA small enough to share an
 // SM with a GEMM CTA of the preceding projection.
 // =====================================================================================================
+// Paged KV cache (KVBlockArray, K/kvCacheUtils.h:34-112): a table [B, 2, max_blocks_per_seq] of pointers to blocks laid
+// out [H, tokens_per_block, Dh] (getKVLocalIdx :104-112); tokens_per_block is a power of two.  PAGED = false keeps the
+// contiguous KVLinearBuffer addressing and compiles to the same code as before the paged variant existed.
+struct KvPaged
+{
+    const void* const* table;
+    int max_blocks_per_seq;
+    int tokens_per_block_log2;
+};
+
+// start of the Dh-element row of token `key` of (sequence b, K or V, head h)
+template <bool PAGED>
+__device__ __forceinline__ char* kv_row(char* linear_base, const KvPaged& pg, int b, int kv, int h, int key, size_t esz)
+{
+    if constexpr (!PAGED)
+    {
+        return linear_base + (size_t) key * kDh * esz;
+    }
+    else
+    {
+        const unsigned long long blk = __ldg(reinterpret_cast<const unsigned long long*>(pg.table)
+            + ((size_t) (b * 2 + kv)) * pg.max_blocks_per_seq + (key >> pg.tokens_per_block_log2));
+        const int local = key & ((1 << pg.tokens_per_block_log2) - 1);
+        return reinterpret_cast<char*>(blk) + ((size_t) ((h << pg.tokens_per_block_log2) + local) * kDh) * esz;
+    }
+}
+
 constexpr int kMmhaWarps = 4; // 2 (batch, head) pairs per CTA
 
-template <bool INT8>
-__global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(const b200_mmha_params p, const int early_kv)
+template <bool INT8, bool PAGED>
+__global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(const b200_mmha_params p, const int early_kv,
+    const KvPaged pg)
 {
     constexpr int NIT = INT8 ? 4 : 2; // key groups of 8 per warp and pass
     constexpr int kPart = kDh + 4;    // m, l, 2 pad, o[64]
@@ -263,9 +291,12 @@ __global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(con
     const bool active = gp < p.batch_size * H;
     const int b = active ? gp / H : 0, h = active ? gp - b * H : 0;
     const size_t esz = INT8 ? 1 : 2;
-    char* kc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 0) * H + h) * Smax * kDh * esz;
+    char* kc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 0) * H + h) * Smax * kDh * esz; // unused when PAGED
     char* vc = static_cast<char*>(p.kv_cache) + ((size_t) (b * 2 + 1) * H + h) * Smax * kDh * esz;
 
+    // keys past the end are fetched (and ignored) up to a cap: the whole linear buffer exists, but only the blocks up
+    // to the token being appended are guaranteed to be allocated in a paged cache
+    int paged_cap = 0;
     __half2 kw[NIT][8], vw[NIT][8];
     auto fetch = [&](int k0)
     {
@@ -273,9 +304,17 @@ __global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(con
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
         {
-            const int key = min(k0 + (2 * it + half) * 8 + kl, Smax - 1);
-            kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
-            vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
+            const int key = min(k0 + (2 * it + half) * 8 + kl, PAGED ? paged_cap : Smax - 1);
+            if constexpr (PAGED)
+            {
+                kreg[it].load(kv_row<true>(kc, pg, b, 0, h, key, esz), (size_t) chunk * 16);
+                vreg[it].load(kv_row<true>(vc, pg, b, 1, h, key, esz), (size_t) chunk * 16);
+            }
+            else
+            {
+                kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
+                vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
+            }
         }
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
@@ -287,6 +326,8 @@ __global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(con
     grid_dep_launch_dependents();
     if (!early_kv)
         grid_dep_wait();
+    if constexpr (PAGED)
+        paged_cap = min(p.sequence_lengths ? p.sequence_lengths[b] : p.past_kv_length, Smax - 1);
     fetch(0);
     int tlen = p.sequence_lengths ? p.sequence_lengths[b] : p.past_kv_length;
     tlen = min(tlen, Smax - 1);
@@ -321,10 +362,20 @@ __global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(con
     {
         if (active)
         {
-            if (kl == 0)
-                store16<INT8>(kc, (size_t) tlen * kDh + chunk * 16, s_oq, kh);
-            else if (kl == 1)
-                store16<INT8>(vc, (size_t) tlen * kDh + chunk * 16, s_oq, vh);
+            if constexpr (PAGED)
+            {
+                if (kl == 0)
+                    store16<INT8>(kv_row<true>(kc, pg, b, 0, h, tlen, esz), (size_t) chunk * 16, s_oq, kh);
+                else if (kl == 1)
+                    store16<INT8>(kv_row<true>(vc, pg, b, 1, h, tlen, esz), (size_t) chunk * 16, s_oq, vh);
+            }
+            else
+            {
+                if (kl == 0)
+                    store16<INT8>(kc, (size_t) tlen * kDh + chunk * 16, s_oq, kh);
+                else if (kl == 1)
+                    store16<INT8>(vc, (size_t) tlen * kDh + chunk * 16, s_oq, vh);
+            }
         }
         float sc0 = 0.f;
 #pragma unroll
@@ -464,10 +515,10 @@ __global__ void __launch_bounds__(kMmhaWarps * 32, 2) mmha_generation_kernel(con
 // [0, S) are written (int8-quantized when requested), and each warp handles query rows i = warp, warp+4, ...
 // causal: key j is visible to query i iff j <= i and j < input_length[b].
 // =====================================================================================================
-template <bool INT8>
+template <bool INT8, bool PAGED>
 __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __restrict__ qkv,
     const int* __restrict__ input_lengths, __half* __restrict__ out, void* __restrict__ kv_cache,
-    const float* __restrict__ kv_scale_orig_quant, int S, int H, int Smax, float q_scaling)
+    const float* __restrict__ kv_scale_orig_quant, int S, int H, int Smax, float q_scaling, const KvPaged pg)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __half* sK = reinterpret_cast<__half*>(s_raw);          // [S][64]
@@ -485,8 +536,8 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
     const float s_oq = INT8 ? kv_scale_orig_quant[0] : 1.f;
     const float inv_sqrt_dh = 1.f / (sqrtf((float) kDh) * q_scaling);
     const size_t esz = INT8 ? 1 : 2;
-    char* kc = static_cast<char*>(kv_cache) + ((size_t) (b * 2 + 0) * H + h) * Smax * kDh * esz;
-    char* vc = static_cast<char*>(kv_cache) + ((size_t) (b * 2 + 1) * H + h) * Smax * kDh * esz;
+    char* kc = PAGED ? nullptr : static_cast<char*>(kv_cache) + ((size_t) (b * 2 + 0) * H + h) * Smax * kDh * esz;
+    char* vc = PAGED ? nullptr : static_cast<char*>(kv_cache) + ((size_t) (b * 2 + 1) * H + h) * Smax * kDh * esz;
 
     // stage K, V; fill the cache.  The reference zeroes the padded rows of its K/V scratch before the transpose
     // (gptAttentionCommon.cpp:481), so padded cache rows hold quantized zeros.
@@ -510,8 +561,8 @@ __global__ void __launch_bounds__(128) attention_context_kernel(const __half* __
         *reinterpret_cast<uint4*>(&sK[t * kDh + c * 16 + 8]) = *reinterpret_cast<const uint4*>(&kh[8]);
         *reinterpret_cast<uint4*>(&sV[t * kDh + c * 16]) = *reinterpret_cast<const uint4*>(&vh[0]);
         *reinterpret_cast<uint4*>(&sV[t * kDh + c * 16 + 8]) = *reinterpret_cast<const uint4*>(&vh[8]);
-        store16<INT8>(kc, (size_t) t * kDh + c * 16, s_oq, kh);
-        store16<INT8>(vc, (size_t) t * kDh + c * 16, s_oq, vh);
+        store16<INT8>(kv_row<PAGED>(kc, pg, b, 0, h, t, esz), (size_t) c * 16, s_oq, kh);
+        store16<INT8>(kv_row<PAGED>(vc, pg, b, 1, h, t, esz), (size_t) c * 16, s_oq, vh);
     }
     __syncthreads();
 
@@ -1123,10 +1174,27 @@ __global__ void cross_kv_pack_kernel(const __half* __restrict__ k, const __half*
 
 using namespace b200;
 
-extern "C" int b200_mmha_generation(const b200_mmha_params* p, b200_stream_t stream)
+static int paged_view(const void* const* block_pointers, int max_blocks_per_seq, int tokens_per_block, int max_seq_len,
+    KvPaged* pg)
+{
+    B200_REQUIRE(block_pointers != nullptr, B200_ERR_INVALID_ARG, "null pointer (block_pointers)");
+    B200_REQUIRE(tokens_per_block > 0 && (tokens_per_block & (tokens_per_block - 1)) == 0, B200_ERR_INVALID_ARG,
+        "tokens_per_block %d must be a power of 2 (kvCacheUtils.h:45-46)", tokens_per_block);
+    B200_REQUIRE(max_blocks_per_seq > 0 && (long long) max_blocks_per_seq * tokens_per_block >= max_seq_len,
+        B200_ERR_INVALID_ARG, "%d blocks of %d tokens do not cover max_seq_len %d", max_blocks_per_seq, tokens_per_block,
+        max_seq_len);
+    pg->table = block_pointers;
+    pg->max_blocks_per_seq = max_blocks_per_seq;
+    pg->tokens_per_block_log2 = 0;
+    while ((1 << pg->tokens_per_block_log2) < tokens_per_block)
+        ++pg->tokens_per_block_log2;
+    return B200_OK;
+}
+
+static int mmha_generation_impl(const b200_mmha_params* p, const KvPaged* paged, b200_stream_t stream)
 {
     B200_REQUIRE(p != nullptr, B200_ERR_INVALID_ARG, "null params");
-    B200_REQUIRE(p->qkv && p->out && p->kv_cache, B200_ERR_INVALID_ARG, "null pointer (qkv/out/kv_cache)");
+    B200_REQUIRE(p->qkv && p->out && (p->kv_cache || paged), B200_ERR_INVALID_ARG, "null pointer (qkv/out/kv_cache)");
     B200_REQUIRE(p->head_size == kDh, B200_ERR_UNSUPPORTED, "head_size %d unsupported (only 64)", p->head_size);
     B200_REQUIRE(p->batch_size >= 0 && p->num_heads > 0 && p->max_seq_len > 0, B200_ERR_INVALID_ARG, "bad sizes");
     B200_REQUIRE(p->past_kv_length >= 0 && p->past_kv_length < p->max_seq_len, B200_ERR_INVALID_ARG,
@@ -1138,18 +1206,42 @@ extern "C" int b200_mmha_generation(const b200_mmha_params* p, b200_stream_t str
         return B200_OK;
     B200_REQUIRE_DEVICE();
     const dim3 grid((p->num_heads * p->batch_size + kMmhaWarps / 2 - 1) / (kMmhaWarps / 2));
-    if (p->int8_kv_cache)
-        B200_LAUNCH(mmha_generation_kernel<true>, grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, static_kv_hint() ? 1 : 0);
+    const int early = static_kv_hint() ? 1 : 0;
+    const KvPaged none{nullptr, 0, 0};
+    if (paged != nullptr)
+    {
+        if (p->int8_kv_cache)
+            B200_LAUNCH((mmha_generation_kernel<true, true>), grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, early, *paged);
+        else
+            B200_LAUNCH((mmha_generation_kernel<false, true>), grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, early, *paged);
+    }
+    else if (p->int8_kv_cache)
+        B200_LAUNCH((mmha_generation_kernel<true, false>), grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, early, none);
     else
-        B200_LAUNCH(mmha_generation_kernel<false>, grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, static_kv_hint() ? 1 : 0);
+        B200_LAUNCH((mmha_generation_kernel<false, false>), grid, dim3(kMmhaWarps * 32), 0, as_stream(stream), *p, early, none);
     return B200_OK;
 }
 
-extern "C" int b200_attention_context(const void* qkv, const int32_t* input_lengths, void* out, void* kv_cache,
-    const float* kv_scale_orig_quant, int batch_size, int seq_len, int num_heads, int head_size, int max_seq_len,
-    int int8_kv_cache, float q_scaling, b200_stream_t stream)
+extern "C" int b200_mmha_generation(const b200_mmha_params* p, b200_stream_t stream)
 {
-    B200_REQUIRE(qkv && out && kv_cache, B200_ERR_INVALID_ARG, "null pointer (qkv/out/kv_cache)");
+    return mmha_generation_impl(p, nullptr, stream);
+}
+
+extern "C" int b200_mmha_generation_paged(const b200_mmha_params* p, const void* const* block_pointers, int max_blocks_per_seq,
+    int tokens_per_block, b200_stream_t stream)
+{
+    B200_REQUIRE(p != nullptr, B200_ERR_INVALID_ARG, "null params");
+    KvPaged pg{};
+    if (int rc = paged_view(block_pointers, max_blocks_per_seq, tokens_per_block, p->max_seq_len, &pg))
+        return rc;
+    return mmha_generation_impl(p, &pg, stream);
+}
+
+static int attention_context_impl(const void* qkv, const int32_t* input_lengths, void* out, void* kv_cache,
+    const KvPaged* paged, const float* kv_scale_orig_quant, int batch_size, int seq_len, int num_heads, int head_size,
+    int max_seq_len, int int8_kv_cache, float q_scaling, b200_stream_t stream)
+{
+    B200_REQUIRE(qkv && out && (kv_cache || paged), B200_ERR_INVALID_ARG, "null pointer (qkv/out/kv_cache)");
     B200_REQUIRE(head_size == kDh, B200_ERR_UNSUPPORTED, "head_size %d unsupported (only 64)", head_size);
     B200_REQUIRE(batch_size >= 0 && seq_len >= 0 && num_heads > 0, B200_ERR_INVALID_ARG, "bad sizes");
     B200_REQUIRE(seq_len <= max_seq_len, B200_ERR_INVALID_ARG, "seq_len %d exceeds max_seq_len %d", seq_len, max_seq_len);
@@ -1161,21 +1253,52 @@ extern "C" int b200_attention_context(const void* qkv, const int32_t* input_leng
     const size_t smem = (size_t) seq_len * kDh * 2 * sizeof(__half) + sizeof(float) * 4 * seq_len;
     B200_REQUIRE(smem <= 200 * 1024, B200_ERR_UNSUPPORTED, "context length %d too large for the single-kernel path", seq_len);
     const dim3 grid(num_heads, batch_size);
-    if (int8_kv_cache)
+    const KvPaged pg = paged != nullptr ? *paged : KvPaged{nullptr, 0, 0};
+    const __half* q = static_cast<const __half*>(qkv);
+    __half* o = static_cast<__half*>(out);
+    cudaStream_t st = as_stream(stream);
+#define B200_CTX_LAUNCH(I8, PG)                                                                                        \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (smem > 48 * 1024)                                                                                          \
+            B200_CUDA(cudaFuncSetAttribute((attention_context_kernel<I8, PG>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                (int) smem));                                                                                          \
+        B200_LAUNCH((attention_context_kernel<I8, PG>), grid, dim3(128), smem, st, q, input_lengths, o, kv_cache,       \
+            kv_scale_orig_quant, seq_len, num_heads, max_seq_len, q_scaling, pg);                                      \
+    } while (0)
+    if (paged != nullptr)
     {
-        if (smem > 48 * 1024)
-            B200_CUDA(cudaFuncSetAttribute(attention_context_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        B200_LAUNCH(attention_context_kernel<true>, grid, dim3(128), smem, as_stream(stream), static_cast<const __half*>(qkv),
-            input_lengths, static_cast<__half*>(out), kv_cache, kv_scale_orig_quant, seq_len, num_heads, max_seq_len, q_scaling);
+        if (int8_kv_cache)
+            B200_CTX_LAUNCH(true, true);
+        else
+            B200_CTX_LAUNCH(false, true);
     }
+    else if (int8_kv_cache)
+        B200_CTX_LAUNCH(true, false);
     else
-    {
-        if (smem > 48 * 1024)
-            B200_CUDA(cudaFuncSetAttribute(attention_context_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        B200_LAUNCH(attention_context_kernel<false>, grid, dim3(128), smem, as_stream(stream), static_cast<const __half*>(qkv),
-            input_lengths, static_cast<__half*>(out), kv_cache, kv_scale_orig_quant, seq_len, num_heads, max_seq_len, q_scaling);
-    }
+        B200_CTX_LAUNCH(false, false);
+#undef B200_CTX_LAUNCH
     return B200_OK;
+}
+
+extern "C" int b200_attention_context(const void* qkv, const int32_t* input_lengths, void* out, void* kv_cache,
+    const float* kv_scale_orig_quant, int batch_size, int seq_len, int num_heads, int head_size, int max_seq_len,
+    int int8_kv_cache, float q_scaling, b200_stream_t stream)
+{
+    return attention_context_impl(qkv, input_lengths, out, kv_cache, nullptr, kv_scale_orig_quant, batch_size, seq_len,
+        num_heads, head_size, max_seq_len, int8_kv_cache, q_scaling, stream);
+}
+
+extern "C" int b200_attention_context_paged(const void* qkv, const int32_t* input_lengths, void* out,
+    const void* const* block_pointers, int max_blocks_per_seq, int tokens_per_block, const float* kv_scale_orig_quant,
+    int batch_size, int seq_len, int num_heads, int head_size, int max_seq_len, int int8_kv_cache, float q_scaling,
+    b200_stream_t stream)
+{
+    KvPaged pg{};
+    if (int rc = paged_view(block_pointers, max_blocks_per_seq, tokens_per_block, max_seq_len, &pg))
+        return rc;
+    return attention_context_impl(qkv, input_lengths, out, nullptr, &pg, kv_scale_orig_quant, batch_size, seq_len, num_heads,
+        head_size, max_seq_len, int8_kv_cache, q_scaling, stream);
 }
 
 namespace b200

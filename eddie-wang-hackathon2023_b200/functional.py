@@ -25,7 +25,8 @@ def gpt_attention(tensor, past_key_value, sequence_length, past_key_value_length
     updated in place, T/tests/attention/test_gpt_attention.py:245-248).
 
     tensor                 [B, S, 3*H*Dh] fp16 (S == 1 in the generation phase)
-    past_key_value         [B, 2, H, Smax, Dh] int8 (use_int8_kv_cache) or fp16
+    past_key_value         [B, 2, H, Smax, Dh] int8 (use_int8_kv_cache) or fp16; with kv_cache_block_pointers: the
+                           block pool [blocks, 2, H, tokens_per_block, Dh]
     sequence_length        [B] int32 CUDA: tokens already cached per sequence in the generation phase
     past_key_value_length  [2] int32 *host* tensor: [past_len, is_context]  (gptAttentionPlugin.cpp:261-278)
     masked_tokens          [B, Smax] int32 CUDA, 1 = padding between the prompt and the generated tokens
@@ -35,8 +36,8 @@ def gpt_attention(tensor, past_key_value, sequence_length, past_key_value_length
     """
     if rotary_embedding_dim != 0 or neox_rotary_style:
         raise NotImplementedError("rotary embeddings are not on the Whisper hot path")
-    if multi_query_mode or use_fp8_kv_cache or kv_cache_block_pointers is not None or host_request_types is not None:
-        raise NotImplementedError("multi-query / fp8 / paged KV / in-flight batching are not on the Whisper hot path")
+    if multi_query_mode or use_fp8_kv_cache or host_request_types is not None:
+        raise NotImplementedError("multi-query / fp8 KV / in-flight batching are not on the Whisper hot path")
     if cache_indirection is not None and cache_indirection.dim() == 3 and cache_indirection.shape[1] != 1:
         raise NotImplementedError("beam search is not on the Whisper hot path (beam width 1)")
     if past_key_value_length.is_cuda:
@@ -50,13 +51,39 @@ def gpt_attention(tensor, past_key_value, sequence_length, past_key_value_length
     hidden = num_heads * head_size
     assert three_hidden == 3 * hidden, "qkv last dim must be 3 * num_heads * head_size"
     past_len, is_context = int(past_key_value_length[0]), bool(int(past_key_value_length[1]))
-    max_seq_len = cache_indirection.shape[-1] if cache_indirection is not None else past_key_value.shape[3]
-    assert tuple(past_key_value.shape) == (B, 2, num_heads, max_seq_len, head_size)
+    paged = kv_cache_block_pointers is not None
+    if paged:
+        # paged KV cache (gptAttentionPlugin.cpp:314-326): past_key_value is the block POOL
+        # [blocks, 2, H, tokens_per_block, Dh]; kv_cache_block_pointers [B, beam = 1, 2, max_blocks_per_seq] int64 (or the
+        # reference's int32 view with twice the last dim) holds device addresses of [H, tokens_per_block, Dh] blocks
+        if cache_indirection is None:
+            raise ValueError("paged KV cache: max_seq_len is read from cache_indirection's last dim")
+        bp = kv_cache_block_pointers
+        if bp.dtype == torch.int32:
+            bp = bp.contiguous().view(torch.int64)
+        assert bp.is_cuda and bp.dtype == torch.int64
+        bp = bp.reshape(B, -1, 2, bp.shape[-1])
+        if bp.shape[1] != 1:
+            raise NotImplementedError("beam search is not on the Whisper hot path (beam width 1)")
+        bp = bp[:, 0].contiguous()
+        max_blocks, tokens_per_block = bp.shape[-1], past_key_value.shape[3]
+        max_seq_len = cache_indirection.shape[-1]
+        assert tuple(past_key_value.shape[1:]) == (2, num_heads, tokens_per_block, head_size)
+    else:
+        max_seq_len = cache_indirection.shape[-1] if cache_indirection is not None else past_key_value.shape[3]
+        assert tuple(past_key_value.shape) == (B, 2, num_heads, max_seq_len, head_size)
     assert past_key_value.dtype == (torch.int8 if use_int8_kv_cache else torch.float16)
     x = tensor.contiguous()
     out = torch.empty((B, S, hidden), dtype=torch.float16, device=tensor.device)
     st = _lib.stream_ptr()
-    if is_context:
+    if is_context and paged:
+        rc = lib.b200_attention_context_paged(_lib.ptr(x), _lib.ptr(input_lengths), _lib.ptr(out), _lib.ptr(bp), max_blocks,
+                                              tokens_per_block,
+                                              _lib.ptr(kv_orig_quant_scale) if use_int8_kv_cache else None, B, S,
+                                              num_heads, head_size, max_seq_len, int(use_int8_kv_cache),
+                                              float(q_scaling), st)
+        _lib.check(rc, "gpt_attention (context, paged)")
+    elif is_context:
         rc = lib.b200_attention_context(_lib.ptr(x), _lib.ptr(input_lengths), _lib.ptr(out), _lib.ptr(past_key_value),
                                         _lib.ptr(kv_orig_quant_scale) if use_int8_kv_cache else None, B, S, num_heads,
                                         head_size, max_seq_len, int(use_int8_kv_cache), float(q_scaling), st)
@@ -76,7 +103,10 @@ def gpt_attention(tensor, past_key_value, sequence_length, past_key_value_length
         p.max_seq_len, p.past_kv_length = max_seq_len, past_len
         p.int8_kv_cache = int(use_int8_kv_cache)
         p.q_scaling = float(q_scaling)
-        rc = lib.b200_mmha_generation(ctypes.byref(p), st)
+        if paged:
+            rc = lib.b200_mmha_generation_paged(ctypes.byref(p), _lib.ptr(bp), max_blocks, tokens_per_block, st)
+        else:
+            rc = lib.b200_mmha_generation(ctypes.byref(p), st)
         _lib.check(rc, "gpt_attention (generation)")
     return out, past_key_value
 

@@ -112,6 +112,8 @@ bool GPTAttentionPlugin::supportsFormatCombination(
         return inOut[pos].type == nvinfer1::DataType::kINT32;
     if ((mInt8KVCache || mFp8KVCache) && (pos == kKV_QUANT_SCALE || pos == kKV_DEQUANT_SCALE))
         return inOut[pos].type == nvinfer1::DataType::kFLOAT;
+    if (mPagedKVCache && pos == blockPointersIdx())
+        return inOut[pos].type == nvinfer1::DataType::kINT32; // pointers as pairs of int32 (gptAttentionPlugin.cpp:106-110)
     if (mInt8KVCache && (pos == kPAST_KV || pos == nbInputs + 1))
         return inOut[pos].type == nvinfer1::DataType::kINT8;
     return inOut[pos].type == mType;
@@ -134,8 +136,8 @@ const char* GPTAttentionPlugin::unsupportedReason() const
         return "GPTAttention on B200: only head_size 64 is implemented";
     if (mRotaryEmbeddingDim != 0)
         return "GPTAttention on B200: rotary embeddings are not on the Whisper hot path";
-    if (mMultiQueryMode || mFp8KVCache || mPagedKVCache || mInFlightBatching || mRemovePadding)
-        return "GPTAttention on B200: multi-query / fp8 KV / paged KV / in-flight batching / packed input are not on the "
+    if (mMultiQueryMode || mFp8KVCache || mInFlightBatching || mRemovePadding)
+        return "GPTAttention on B200: multi-query / fp8 KV / in-flight batching / packed input are not on the "
                "Whisper hot path";
     if (mMaskType != 1 || !mUnidirectional)
         return "GPTAttention on B200: only the causal mask is implemented";
@@ -167,8 +169,29 @@ int GPTAttentionPlugin::enqueue(const PluginTensorDesc* inputDesc, const PluginT
     }
     void* key_value_cache = outputs[1]; // present == past buffer by convention (test_gpt_attention.py:245-248)
     (void) outputDesc;
+    // paged KV cache (gptAttentionPlugin.cpp:314-326): input 1 is the block pool [blocks, 2, H, tokens_per_block, Dh], the
+    // block-pointer input [B, beam, 2, 2 * max_blocks_per_seq] holds 64-bit device addresses as pairs of int32
+    const void* const* block_pointers = nullptr;
+    int max_blocks_per_seq = 0, tokens_per_block = 0;
+    if (mPagedKVCache)
+    {
+        max_blocks_per_seq = inputDesc[blockPointersIdx()].dims.d[3] / 2;
+        tokens_per_block = inputDesc[kPAST_KV].dims.d[3];
+        block_pointers = static_cast<const void* const*>(inputs[blockPointersIdx()]);
+        if (beam_width != 1)
+        {
+            b200::plugin::logError("GPTAttention on B200: beam search is not on the Whisper hot path (beam width 1)");
+            return B200_ERR_UNSUPPORTED;
+        }
+    }
     int rc;
-    if (is_context)
+    if (is_context && mPagedKVCache)
+    {
+        rc = b200_attention_context_paged(inputs[kQKV], static_cast<const int32_t*>(inputs[kINPUT_LENGTHS]), outputs[0],
+            block_pointers, max_blocks_per_seq, tokens_per_block, kv_scale_orig_quant, nbSeq, max_input_len, mNumHeads,
+            mHeadSize, max_seq_len, mInt8KVCache ? 1 : 0, mQScaling, reinterpret_cast<b200_stream_t>(stream));
+    }
+    else if (is_context)
     {
         rc = b200_attention_context(inputs[kQKV], static_cast<const int32_t*>(inputs[kINPUT_LENGTHS]), outputs[0],
             key_value_cache, kv_scale_orig_quant, nbSeq, max_input_len, mNumHeads, mHeadSize, max_seq_len,
@@ -197,7 +220,9 @@ int GPTAttentionPlugin::enqueue(const PluginTensorDesc* inputDesc, const PluginT
         p.past_kv_length = past_kv_len;
         p.int8_kv_cache = mInt8KVCache ? 1 : 0;
         p.q_scaling = mQScaling;
-        rc = b200_mmha_generation(&p, reinterpret_cast<b200_stream_t>(stream));
+        rc = mPagedKVCache ? b200_mmha_generation_paged(&p, block_pointers, max_blocks_per_seq, tokens_per_block,
+                                 reinterpret_cast<b200_stream_t>(stream))
+                           : b200_mmha_generation(&p, reinterpret_cast<b200_stream_t>(stream));
     }
     if (rc != B200_OK)
         b200::plugin::logError(b200_last_error());

@@ -7,11 +7,13 @@
 //     fp8_kv_cache remove_input_padding mask_type paged_kv_cache type_id in_flight_batching;
 //   inputs by index (gptAttentionPlugin.h:105-168): 0 qkv, 1 past_key_value, 2 sequence_length, 3 past_key_value_length
 //     (HOST [past_len, is_context]), 4 masked_tokens, 5 input_lengths, 6 max_input_length (shape only),
-//     7 cache_indirection (Smax = dims[2]), 8 kv_orig_quant_scale, 9 kv_quant_orig_scale (int8/fp8 KV only);
+//     7 cache_indirection (Smax = dims[2]), 8 kv_orig_quant_scale, 9 kv_quant_orig_scale (int8/fp8 KV only), then
+//     kv_cache_block_pointers [B, beam, 2, 2 * max_blocks_per_seq] int32 pairs when paged_kv_cache (input 1 is then the
+//     block pool [blocks, 2, H, tokens_per_block, Dh]);
 //   outputs: 0 context [B, S, H*Dh], 1 present_key_value (same buffer as input 1);
 //   serialization: the 37-byte common block (gptAttentionCommon.cpp:862-890) || bool inFlightBatching = 38 bytes.
-// Only the Whisper hot-path configuration executes on B200 (fp16 I/O, contiguous int8 or fp16 KV cache, beam 1, no
-// rotary / multi-query / paged / in-flight batching); other configurations are constructible and serializable (so
+// Only the Whisper hot-path configuration executes on B200 (fp16 I/O, contiguous or paged int8 / fp16 KV cache, beam 1, no
+// rotary / multi-query / in-flight batching); other configurations are constructible and serializable (so
 // engines round-trip) but enqueue reports an error instead of computing something else.
 #pragma once
 
@@ -79,6 +81,10 @@ private:
     };
 
     const char* unsupportedReason() const;
+    int blockPointersIdx() const // getKVCacheBlockPointersIdx, gptAttentionPlugin.h:150-153
+    {
+        return mInt8KVCache ? 10 : 8;
+    }
 
     std::string mNamespace;
     int mNumHeads, mHeadSize, mUnidirectional;

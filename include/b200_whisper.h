@@ -188,6 +188,19 @@ int b200_attention_context(const void* qkv, const int32_t* input_lengths, void* 
     const float* kv_scale_orig_quant, int batch_size, int seq_len, int num_heads, int head_size, int max_seq_len,
     int int8_kv_cache, float q_scaling, b200_stream_t stream);
 
+/* The same two operators over a PAGED KV cache (KVBlockArray, T/cpp/tensorrt_llm/kernels/kvCacheUtils.h:34-112; plugin
+ * inputs: gptAttentionPlugin.cpp:314-326): block_pointers is a device array [B, 2, max_blocks_per_seq] of device pointers
+ * (K table then V table per sequence, beam width 1), every block laid out [num_heads, tokens_per_block, head_size] in the
+ * cache dtype; tokens_per_block is a power of 2 and max_blocks_per_seq * tokens_per_block >= max_seq_len.  Only the
+ * blocks up to the token being written have to be allocated.  p->kv_cache is ignored.  Results and cache bytes are
+ * identical with the linear-buffer entry points. */
+int b200_mmha_generation_paged(const b200_mmha_params* p, const void* const* block_pointers, int max_blocks_per_seq,
+    int tokens_per_block, b200_stream_t stream);
+int b200_attention_context_paged(const void* qkv, const int32_t* input_lengths, void* out,
+    const void* const* block_pointers, int max_blocks_per_seq, int tokens_per_block, const float* kv_scale_orig_quant,
+    int batch_size, int seq_len, int num_heads, int head_size, int max_seq_len, int int8_kv_cache, float q_scaling,
+    b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Cached cross-attention over the encoder frames with an int8 (or fp16) cross-KV cache
  * [B, 2, H, S_enc, Dh] produced once per utterance by the cross_kv_cache_warping model.

@@ -71,6 +71,19 @@ def test_argument_validation_without_gpu(lib):
     assert lib.b200_attention_bidirectional_fp16(None, None, 1, 1500, 20, 64, None) == 1
     assert lib.b200_whisper_filtered_argmax(None, 1, 51865, None, 50257, 50363, 50364, 220, -1, None, None, None, None) == 1
     assert lib.b200_transpose_add_pos_fp16(None, None, None, 1, 1280, 1500, None) == 1
+    # paged KV cache entry points (kvCacheUtils.h:34-112): the block geometry is validated before any device work
+    from b200_whisper._lib import MmhaParams
+    import ctypes as ct
+    mp = MmhaParams()
+    t8 = torch.zeros(8)
+    mp.qkv = mp.out = t8.data_ptr()
+    mp.batch_size, mp.num_heads, mp.head_size, mp.max_seq_len, mp.past_kv_length, mp.q_scaling = 1, 4, 64, 448, 3, 1.0
+    assert lib.b200_mmha_generation_paged(ct.byref(mp), None, 7, 64, None) == 1                      # no table
+    assert lib.b200_mmha_generation_paged(ct.byref(mp), t8.data_ptr(), 7, 48, None) == 1            # not a power of 2
+    assert b"power of 2" in lib.b200_last_error()
+    assert lib.b200_mmha_generation_paged(ct.byref(mp), t8.data_ptr(), 6, 64, None) == 1            # 384 < 448 tokens
+    assert lib.b200_attention_context_paged(t8.data_ptr(), None, t8.data_ptr(), t8.data_ptr(), 7, 64, None, 1, 4, 4, 32, 448,
+                                            0, 1.0, None) == 2                                      # head size 32
     x = torch.zeros(8)
     assert lib.b200_logits_range_softmax(None, 1, 51865, 50259, 50358, 50362, None, None, None, None) == 1
     assert lib.b200_logits_range_softmax(x.data_ptr(), 1, 8, 5, 3, 0, x.data_ptr(), None, None, None) == 1   # empty range

@@ -202,3 +202,73 @@ def test_bidirectional_attention(B, S, H):
     ref = (w @ v).permute(0, 2, 1, 3).reshape(B, S, H * D)
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"bidirectional attention err {err}"
+
+
+@pytest.mark.parametrize("int8", [True, False])
+@pytest.mark.parametrize("in_len,tokens_per_block", [(4, 16), (100, 64), (37, 8)])
+def test_paged_kv_cache_equals_linear(int8, in_len, tokens_per_block):
+    """Paged KV cache (KVBlockArray, K/kvCacheUtils.h:34-112; kv_cache_block_pointers of gpt_attention): a context step and 9
+    generation steps over a block pool in shuffled order give bit-identical outputs and, gathered back through the block
+    table, a bit-identical cache compared with the contiguous KVLinearBuffer path.  Blocks a sequence has not reached
+    yet all point at one poisoned guard block that must stay untouched."""
+    from b200_whisper.functional import gpt_attention
+    torch.manual_seed(7 + in_len)
+    B, H, D = 3, 4, 64
+    hidden = H * D
+    n_gen = 9
+    max_seq = in_len + 24
+    dev = "cuda"
+    dt = torch.int8 if int8 else torch.float16
+    kv_dequant = torch.tensor([0.05], dtype=torch.float32, device=dev)
+    kv_quant = 1.0 / kv_dequant
+    max_blocks = (max_seq + tokens_per_block - 1) // tokens_per_block
+    used_blocks = (in_len + n_gen + tokens_per_block - 1) // tokens_per_block      # blocks a sequence ever writes
+    n_pool = B * 2 * used_blocks + 1
+    pool = torch.zeros((n_pool, 2, H, tokens_per_block, D), dtype=dt, device=dev)   # [blocks, 2, H, tpb, Dh]
+    guard = n_pool - 1
+    pool[guard] = 77
+    esz = pool.element_size()
+    block_bytes = 2 * H * tokens_per_block * D * esz
+    perm = torch.randperm(n_pool - 1).tolist()
+    table = torch.full((B, 1, 2, max_blocks), guard, dtype=torch.int64)
+    it = iter(perm)
+    for b in range(B):
+        for kv in range(2):
+            for j in range(used_blocks):
+                table[b, 0, kv, j] = next(it)
+    block_id = table.clone()
+    pointers = (pool.data_ptr() + block_id * block_bytes).to(dev)
+    linear = torch.zeros((B, 2, H, max_seq, D), dtype=dt, device=dev)
+    input_lengths = torch.full((B,), in_len, dtype=torch.int32, device=dev)
+    masked_tokens = torch.zeros((B, max_seq), dtype=torch.int32, device=dev)
+    cache_ind = torch.zeros((B, 1, max_seq), dtype=torch.int32, device=dev)
+    max_in = torch.zeros((in_len,), dtype=torch.int32, device=dev)
+
+    def both(qkv, seq_len, host):
+        a, _ = gpt_attention(qkv, linear, seq_len, host, masked_tokens, input_lengths, max_in, cache_ind, H, D, 1.0, 0,
+                             False, False, False, kv_quant, kv_dequant, int8)
+        b, _ = gpt_attention(qkv, pool, seq_len, host, masked_tokens, input_lengths, max_in, cache_ind, H, D, 1.0, 0,
+                             False, False, False, kv_quant, kv_dequant, int8, kv_cache_block_pointers=pointers)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+
+    def gathered(n_tokens):
+        out = torch.zeros((B, 2, H, n_tokens, D), dtype=dt, device=dev)
+        for b in range(B):
+            for kv in range(2):
+                for t in range(n_tokens):
+                    blk = int(block_id[b, 0, kv, t // tokens_per_block])
+                    out[b, kv, :, t] = pool[blk, 0, :, t % tokens_per_block]
+        return out
+
+    qkv = torch.randn((B, in_len, 3 * hidden), device=dev).half()
+    both(qkv, torch.full((B,), in_len, dtype=torch.int32, device=dev), torch.tensor([0, 1], dtype=torch.int32))
+    assert torch.equal(gathered(in_len), linear[:, :, :, :in_len])
+    for step in range(n_gen):
+        past_len = in_len + step
+        qkv1 = torch.randn((B, 1, 3 * hidden), device=dev).half()
+        both(qkv1, torch.full((B,), past_len, dtype=torch.int32, device=dev), torch.tensor([past_len, 0], dtype=torch.int32))
+    n = in_len + n_gen
+    assert torch.equal(gathered(n), linear[:, :, :, :n])
+    assert (pool[guard] == 77).all()                     # nothing was written through the not-yet-allocated entries
+    assert (pool[:guard, 1] == 0).all()                  # the tables point at the first half of every pool slot only
