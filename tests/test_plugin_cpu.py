@@ -112,6 +112,18 @@ def test_gpt_attention_plugin_contract():
     bad[8] = ((1,), "float16")  # KV scales are kFLOAT
     assert not p.supports_format(8, bad, len(ins))
     assert p.output_dtype(1, ["float16", "int8"] + ["int32"] * 6 + ["float32"] * 2) == 2
+    # paged KV cache: input 1 is the block pool, the block pointers arrive as int32 pairs in slot 10 (8 without int8 KV)
+    pg = TrtPlugin.create("GPTAttention", attn_fields(paged_kv_cache=1))
+    assert pg.serialize()[32] == 1
+    pins = list(ins)
+    pins[1] = ((64, 2, 20, 64, 64), "int8")
+    pins.append(((B, 1, 2, 2 * 7), "int32"))
+    pio = pins + [((B, S, 1280), "float16"), ((64, 2, 20, 64, 64), "int8")]
+    assert all(pg.supports_format(pos, pio, len(pins)) for pos in range(len(pio)))
+    bad = list(pio)
+    bad[10] = ((B, 1, 2, 2 * 7), "float16")
+    assert not pg.supports_format(10, bad, len(pins))
+    assert pg.output_dims(1, pins) == (64, 2, 20, 64, 64)
     # context FMHA flags round-trip through the byte layout (type 2 -> enable + force fp32 acc)
     r = TrtPlugin.create("GPTAttention", attn_fields(context_fmha_type=2, int8_kv_cache=0))
     b2 = r.serialize()

@@ -103,3 +103,65 @@ def test_gpt_attention_through_plugin():
         past_k = torch.cat([past_k, (cache[:, 0, :, past_len].float() * deq).half().float()[:, :, None]], 2)
         past_v = torch.cat([past_v, (cache[:, 1, :, past_len].float() * deq).half().float()[:, :, None]], 2)
     plug.destroy()
+
+
+def test_gpt_attention_paged_kv_through_plugin():
+    """paged_kv_cache = 1 (gptAttentionPlugin.cpp:314-326): input 1 is the block pool, input 10 the block pointers as pairs
+    of int32; the plugin must produce the same bits as the contiguous-cache plugin."""
+    torch.manual_seed(3)
+    B, H, D, in_len = 2, 4, 64, 8
+    hidden, max_seq, tpb = H * D, 32, 8
+    max_blocks = max_seq // tpb
+    dev = "cuda"
+    lin = TrtPlugin.create("GPTAttention", attn_fields(num_heads=H, head_size=D))
+    pag = TrtPlugin.create("GPTAttention", attn_fields(num_heads=H, head_size=D, paged_kv_cache=1))
+    pag = TrtPlugin.deserialize("GPTAttention", pag.serialize())
+    deq = torch.tensor([0.05], dtype=torch.float32, device=dev)
+    qnt = 1.0 / deq
+    cache = torch.zeros((B, 2, H, max_seq, D), dtype=torch.int8, device=dev)
+    n_pool = B * 2 * max_blocks
+    pool = torch.zeros((n_pool, 2, H, tpb, D), dtype=torch.int8, device=dev)
+    ids = torch.randperm(n_pool).view(B, 1, 2, max_blocks)
+    ptrs64 = (pool.data_ptr() + ids * (2 * H * tpb * D)).to(dev)               # each table entry -> pool[id, 0]
+    ptrs32 = ptrs64.view(torch.int32)                                          # [B, 1, 2, 2 * max_blocks]
+    assert tuple(ptrs32.shape) == (B, 1, 2, 2 * max_blocks)
+    input_lengths = torch.full((B,), in_len, dtype=torch.int32, device=dev)
+    masked = torch.zeros((B, max_seq), dtype=torch.int32, device=dev)
+    cache_ind = torch.zeros((B, 1, max_seq), dtype=torch.int32, device=dev)
+    max_in = torch.zeros((in_len,), dtype=torch.int32, device=dev)
+
+    def run(plug, kv, qkv, seq_len, host_scalars, paged):
+        S = qkv.shape[1]
+        out = torch.empty((B, S, hidden), dtype=torch.float16, device=dev)
+        ins = [(tuple(qkv.shape), "float16"), (tuple(kv.shape), "int8"), ((B,), "int32"), ((2,), "int32"),
+               ((B, max_seq), "int32"), ((B,), "int32"), ((in_len,), "int32"), ((B, 1, max_seq), "int32"),
+               ((1,), "float32"), ((1,), "float32")]
+        ptr_list = [qkv.data_ptr(), kv.data_ptr(), seq_len.data_ptr(), None, masked.data_ptr(), input_lengths.data_ptr(),
+                    max_in.data_ptr(), cache_ind.data_ptr(), qnt.data_ptr(), deq.data_ptr()]
+        if paged:
+            ins.append((tuple(ptrs32.shape), "int32"))
+            ptr_list.append(ptrs32.data_ptr())
+        outs = [(tuple(out.shape), "float16"), (tuple(kv.shape), "int8")]
+        host = np.array(host_scalars, np.int32)
+        ptr_list[3] = host.ctypes.data
+        rc = plug.enqueue(ins, outs, ptr_list, [out.data_ptr(), kv.data_ptr()], None, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert rc == 0
+        return out
+
+    steps = [(torch.randn((B, in_len, 3 * hidden), device=dev).half(), in_len, [0, 1])]
+    for step in range(4):
+        steps.append((torch.randn((B, 1, 3 * hidden), device=dev).half(), in_len + step, [in_len + step, 0]))
+    for qkv, n, host in steps:
+        seq_len = torch.full((B,), n, dtype=torch.int32, device=dev)
+        a = run(lin, cache, qkv, seq_len, host, False)
+        b = run(pag, pool, qkv, seq_len, host, True)
+        assert torch.equal(a, b)
+    n = in_len + 4
+    for bi in range(B):
+        for kv in range(2):
+            for t in range(n):
+                blk = int(ids[bi, 0, kv, t // tpb])
+                assert torch.equal(pool[blk, 0, :, t % tpb], cache[bi, kv, :, t])
+    lin.destroy()
+    pag.destroy()
