@@ -12,7 +12,7 @@ echo "=== smoke" | tee -a gpurun_out/summary.txt
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit $?" >> gpurun_out/smoke.log
 tail -n 3 gpurun_out/smoke.log | tee -a gpurun_out/summary.txt
 echo "=== bench" | tee -a gpurun_out/summary.txt
-timeout 900 python bench.py > gpurun_out/bench.log 2>&1; echo "exit $?" >> gpurun_out/bench.log
+timeout 900 python bench.py $BENCH_ARGS > gpurun_out/bench.log 2>&1; echo "exit $?" >> gpurun_out/bench.log
 tail -n 3 gpurun_out/bench.log | cut -c1-6000 | tee -a gpurun_out/summary.txt
 if [ "$1" != "noncu" ]; then
 echo "=== ncu" | tee -a gpurun_out/summary.txt
