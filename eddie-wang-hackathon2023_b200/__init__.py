@@ -12,6 +12,7 @@ ctypes to the C ABI in include/b200_whisper.h.  Import as ``b200_whisper`` (see 
     whisper_utils.log_mel_spectrogram / pad_or_trim      <- examples/whisper/whisper_utils.py:56-145 (GPU log-Mel front end)
     tokenizer.get_tokenizer / Tokenizer                  <- examples/whisper/tokenizer.py:125-265, decoding.py:423-486
     runtime.WhisperPipeline, load_checkpoint, *_kv_scales <- examples/whisper/run.py:33-66, build.py:146-154, weight.py:236-243
+    summarize.evaluate / word_error_rate / load_dataset  <- examples/whisper/summarize.py:56-185 (WER harness)
 """
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401
@@ -21,8 +22,9 @@ from .quantization import QuantMode  # noqa: F401
 from . import runtime  # noqa: F401
 from . import whisper_utils  # noqa: F401
 from . import tokenizer  # noqa: F401
+from . import summarize  # noqa: F401
 
-__all__ = ["ops", "functional", "quantization", "QuantMode", "whisper_utils", "tokenizer", "load", "launch_count"]
+__all__ = ["ops", "functional", "quantization", "QuantMode", "whisper_utils", "tokenizer", "summarize", "load", "launch_count"]
 
 
 def load():
