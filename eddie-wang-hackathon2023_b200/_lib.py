@@ -30,6 +30,33 @@ class MmhaParams(ctypes.Structure):
     ]
 
 
+class DecoderLayer(ctypes.Structure):
+    """b200_decoder_layer (include/b200_whisper.h): 32 device pointers per decoder layer."""
+    _names = [
+        "attn_ln_gamma", "qkv_w", "qkv_scales", "qkv_bias", "qkv_c1s", "qkv_c2",
+        "attn_out_w", "attn_out_scales", "attn_out_bias",
+        "cross_ln_gamma", "cross_q_w", "cross_q_scales", "cross_q_bias", "cross_q_c1s", "cross_q_c2",
+        "cross_out_w", "cross_out_scales", "cross_out_bias",
+        "mlp_ln_gamma", "fc1_w", "fc1_scales", "fc1_bias", "fc1_c1s", "fc1_c2",
+        "fc2_w", "fc2_scales", "fc2_bias",
+        "self_kv", "kv_scale_orig_quant", "kv_scale_quant_orig",
+        "cross_kv", "cross_kv_scale_quant_orig",
+    ]
+    _fields_ = [(n, _vp) for n in _names]
+
+
+class DecoderStepParams(ctypes.Structure):
+    """b200_decoder_step_params (include/b200_whisper.h)."""
+    _fields_ = [
+        ("layers", _vp),
+        ("n_layers", ctypes.c_int32), ("batch_size", ctypes.c_int32), ("num_heads", ctypes.c_int32),
+        ("d_ff", ctypes.c_int32), ("max_seq_len", ctypes.c_int32), ("enc_len", ctypes.c_int32),
+        ("vocab", ctypes.c_int32), ("n_ctx", ctypes.c_int32),
+        ("tokens", _vp), ("sequence_lengths", _vp), ("tok_emb", _vp), ("pos_emb", _vp), ("x_out", _vp),
+        ("scratch", _vp), ("ln_eps", ctypes.c_float), ("max_ctas", ctypes.c_int32),
+    ]
+
+
 _SIGS = {
     "b200_last_error": (ctypes.c_char_p, []),
     "b200_abi_version": (_i, []),
@@ -76,6 +103,9 @@ _SIGS = {
     "b200_logits_workspace_bytes": (_sz, [_i, _i]),
     "b200_logits_argmax_fp16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "b200_logits_set_kernel_policy": (_i, [_i]),
+    "b200_decoder_step_scratch_bytes": (_sz, [_i, _i]),
+    "b200_decoder_step": (_i, [ctypes.POINTER(DecoderStepParams), _vp]),
+    "b200_decoder_step_status": (_i, [_vp, ctypes.POINTER(ctypes.c_int32)]),
 }
 
 

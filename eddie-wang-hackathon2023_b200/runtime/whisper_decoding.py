@@ -140,6 +140,15 @@ class WhisperDecoding:
         self._side = torch.cuda.Stream(device=dev) if torch.cuda.is_available() else None
         self._pinned_in = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
         self._pinned_out = torch.zeros((B,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
+        # The generation step as ONE persistent kernel (b200_decoder_step): weights and cross-KV stream through a
+        # shared-memory ring ahead of the dependency chain.  B200_STEP_KERNEL=0 restores the kernel-per-operator chain.
+        self.d_ff = self.layers[0]["fc1"].n
+        self.step_kernel = (os.environ.get("B200_STEP_KERNEL", "1") != "0" and self.fuse_ln and B <= 16
+                            and self.d <= 1280 and self.n_chains == 1
+                            and self.d_ff % (64 * ((self.d_ff + 1279) // 1280)) == 0)
+        self.step_ctas = int(os.environ.get("B200_STEP_CTAS", "0"))
+        self._step_table = None
+        self._step_scratch = None
 
     # ---- thin wrappers over the C ABI (pointers only; no torch math) --------------------------------------
     def _st(self):
@@ -188,6 +197,7 @@ class WhisperDecoding:
             self._gemm(x, B * S, lay["cross_v"], v)
             if self.cross_kv[i] is None:
                 self.cross_kv[i] = torch.empty((B, 2, self.H, S, self.Dh), dtype=torch.int8, device=self.device)
+                self._step_table = None  # the step kernel's layer table holds the cache pointers
             rc = self.lib.b200_cross_kv_pack(k.data_ptr(), v.data_ptr(), self.cross_kv[i].data_ptr(),
                                              lay["ckv_oq"].data_ptr(), B, S, self.H, self.Dh, 1, self._st())
             _lib.check(rc, "cross_kv_pack")
@@ -196,6 +206,58 @@ class WhisperDecoding:
         """Installs precomputed int8 cross-KV caches [B, 2, H, S_enc, Dh] (synthetic benchmarks)."""
         assert len(caches) == self.L
         self.cross_kv = [c.to(self.device) for c in caches]
+        # captured graphs and the step kernel's layer table hold the old device pointers
+        self.graph = self.graph_host = None
+        self._step_table = None
+
+    # ---- the persistent step kernel (b200_decoder_step) -----------------------------------------------------------
+    def _build_step_table(self):
+        """Device array of b200_decoder_layer (32 pointers per layer) + the zero-initialised scratch."""
+        names = _lib.DecoderLayer._names
+        rows = []
+        for i, lay in enumerate(self.layers):
+            ent = {
+                "attn_ln_gamma": lay["attn_ln"][0], "qkv_w": lay["qkv"].weight, "qkv_scales": lay["qkv"].scales,
+                "qkv_bias": lay["qkv"].bias, "qkv_c1s": lay["qkv"].c1s, "qkv_c2": lay["qkv"].c2,
+                "attn_out_w": lay["attn_out"].weight, "attn_out_scales": lay["attn_out"].scales,
+                "attn_out_bias": lay["attn_out"].bias,
+                "cross_ln_gamma": lay["cross_ln"][0], "cross_q_w": lay["cross_q"].weight,
+                "cross_q_scales": lay["cross_q"].scales, "cross_q_bias": lay["cross_q"].bias,
+                "cross_q_c1s": lay["cross_q"].c1s, "cross_q_c2": lay["cross_q"].c2,
+                "cross_out_w": lay["cross_out"].weight, "cross_out_scales": lay["cross_out"].scales,
+                "cross_out_bias": lay["cross_out"].bias,
+                "mlp_ln_gamma": lay["mlp_ln"][0], "fc1_w": lay["fc1"].weight, "fc1_scales": lay["fc1"].scales,
+                "fc1_bias": lay["fc1"].bias, "fc1_c1s": lay["fc1"].c1s, "fc1_c2": lay["fc1"].c2,
+                "fc2_w": lay["fc2"].weight, "fc2_scales": lay["fc2"].scales, "fc2_bias": lay["fc2"].bias,
+                "self_kv": self.self_kv[i], "kv_scale_orig_quant": lay["kv_oq"], "kv_scale_quant_orig": lay["kv_qo"],
+                "cross_kv": self.cross_kv[i], "cross_kv_scale_quant_orig": lay["ckv_qo"],
+            }
+            rows.append([0 if ent[n] is None else ent[n].data_ptr() for n in names])
+        self._step_table = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        if self._step_scratch is None:
+            nbytes = self.lib.b200_decoder_step_scratch_bytes(self.H, self.d_ff)
+            self._step_scratch = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)
+
+    def _step_kernel_call(self, x_out):
+        if self._step_table is None:
+            self._build_step_table()
+        p = _lib.DecoderStepParams()
+        p.layers = self._step_table.data_ptr()
+        p.n_layers, p.batch_size, p.num_heads, p.d_ff = self.L, self.B, self.H, self.d_ff
+        p.max_seq_len, p.enc_len, p.vocab, p.n_ctx = self.Smax, self.S_enc, self.V, self.Smax
+        p.tokens, p.sequence_lengths = self.tokens.data_ptr(), self.seq_len.data_ptr()
+        p.tok_emb, p.pos_emb = self.tok_emb.data_ptr(), self.pos_emb.data_ptr()
+        p.x_out, p.scratch = x_out.data_ptr(), self._step_scratch.data_ptr()
+        p.ln_eps, p.max_ctas = 1e-5, self.step_ctas
+        _lib.check(self.lib.b200_decoder_step(ctypes.byref(p), self._st()), "decoder_step")
+
+    def step_kernel_status(self):
+        """0 unless a barrier or ring wait of the persistent step kernel timed out (synchronises the device)."""
+        if self._step_scratch is None:
+            return 0
+        st = ctypes.c_int32(0)
+        _lib.check(self.lib.b200_decoder_step_status(self._step_scratch.data_ptr(), ctypes.byref(st)), "status")
+        return st.value
 
     def reset(self):
         self.seq_len.zero_()
@@ -340,6 +402,13 @@ class WhisperDecoding:
 
     def _step_body(self):
         B = self.B
+        if self.step_kernel:
+            x = self._buf("x", B, self.d)
+            self._step_kernel_call(x)
+            self._head(x, B, self.logits, self.next_tokens)
+            self.seq_len.add_(1)
+            self.tokens.copy_(self.next_tokens)
+            return
         self.lib.b200_set_static_kv_hint(1 if self.static_kv else 0)
         x = self._buf("x", B, self.d)
         _lib.check(self.lib.b200_embed_tokens_fp16(self.tokens.data_ptr(), self.seq_len.data_ptr(),

@@ -316,6 +316,67 @@ int b200_logits_argmax_fp16(const void* x, const void* emb, void* logits_fp32, i
 /* 0 = auto (tcgen05 fp16 GEMM), 1 = SIMT (tests / comparison). */
 int b200_logits_set_kernel_policy(int policy);
 
+/* ------------------------------------------------------------------------------------------------
+ * Persistent decoder step: the WHOLE stack of one generation step (token + position embedding, then per layer
+ * LN->qkv, masked self-attention with int8 KV append, out-projection, LN->cross-q, cached cross-attention over the
+ * int8 cross-KV, out-projection, LN->fc1+GELU, fc2; rows = batch <= 16) as ONE kernel launch.
+ * Replaces, for the generation phase, the per-operator chain the reference engine executes for a decoder step
+ *   WeightOnlyQuantMatmulPlugin::enqueue   T/cpp/tensorrt_llm/plugins/weightOnlyQuantMatmulPlugin/weightOnlyQuantMatmulPlugin.cpp:162-222   (x6 per layer)
+ *   GPTAttentionPluginCommon::enqueueGeneration  T/cpp/tensorrt_llm/plugins/gptAttentionCommon/gptAttentionCommon.cpp:649-780
+ *   cross attention                        T/tensorrt_llm/layers/attention.py:308-323,385-406
+ *   graph of WhisperDecoder                T/tensorrt_llm/models/whisper/model.py:74-118,257-292
+ * with the same arithmetic as the per-operator entry points above (same weight layout, folded LayerNorm vectors from
+ * b200_woq_ln_fold_prepare, same KV-cache layouts and quantization rules, same epilogue rounding).
+ *
+ * One CTA per SM stays resident for the whole step.  A producer warp streams every int8 weight tile and every
+ * cross-KV chunk of the step through ONE shared-memory ring with 1-D TMA bulk copies, in a static order, as far
+ * ahead as the ring allows (weights and cross-KV never depend on the step's activations), so HBM keeps streaming
+ * while the consumer warps sit in the dependency chain; the ten consumer warps run the matmuls (in-register
+ * int8->fp16 dequant, mma.sync m16n8k16 with the 16 batch rows as M, K split over warps), the attention kernels'
+ * inner loops and the epilogues.  Phases are separated by grid-wide release/acquire barriers on `sync`.
+ *
+ * Activations that feed a matmul are kept in "A-fragment order" ([K/64][4][32 lanes][8 halves], 16 rows): the
+ * consumer warps load their mma.sync A operands with coalesced 128-bit loads, no shared-memory staging.
+ * All scratch buffers are caller-owned (b200_decoder_step_scratch_bytes); `sync` must be zero before the first call
+ * and is left zero by every call.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200_decoder_layer
+{
+    /* LayerNorm -> qkv [d -> 3d] (bias: q | 0 | v), folded-LN vectors from b200_woq_ln_fold_prepare */
+    const void* attn_ln_gamma; const int8_t* qkv_w; const void* qkv_scales; const void* qkv_bias;
+    const float* qkv_c1s; const float* qkv_c2;
+    const int8_t* attn_out_w; const void* attn_out_scales; const void* attn_out_bias;
+    const void* cross_ln_gamma; const int8_t* cross_q_w; const void* cross_q_scales; const void* cross_q_bias;
+    const float* cross_q_c1s; const float* cross_q_c2;
+    const int8_t* cross_out_w; const void* cross_out_scales; const void* cross_out_bias;
+    const void* mlp_ln_gamma; const int8_t* fc1_w; const void* fc1_scales; const void* fc1_bias;
+    const float* fc1_c1s; const float* fc1_c2;
+    const int8_t* fc2_w; const void* fc2_scales; const void* fc2_bias;
+    void* self_kv;                  /* [B, 2, H, Smax, 64] int8 (KVLinearBuffer) */
+    const float* kv_scale_orig_quant; const float* kv_scale_quant_orig;
+    const void* cross_kv;           /* [B, 2, H, S_enc, 64] int8, offset-binary (b200_cross_kv_pack) */
+    const float* cross_kv_scale_quant_orig;
+} b200_decoder_layer;
+
+typedef struct b200_decoder_step_params
+{
+    const b200_decoder_layer* layers; /* DEVICE array [n_layers] */
+    int32_t n_layers, batch_size, num_heads, d_ff, max_seq_len, enc_len, vocab, n_ctx;
+    const int32_t* tokens;           /* [B] device: input token ids of this step */
+    const int32_t* sequence_lengths; /* [B] device: tokens already in the self KV cache (= position of this token) */
+    const void* tok_emb;             /* [vocab, d] fp16 */
+    const void* pos_emb;             /* [n_ctx, d] fp16 */
+    void* x_out;                     /* [B, d] fp16 row-major: the residual stream after the last layer */
+    void* scratch;                   /* b200_decoder_step_scratch_bytes(), zero-initialised once */
+    float ln_eps;
+    int32_t max_ctas;                /* 0 = one per SM; tests use smaller grids */
+} b200_decoder_step_params;
+
+size_t b200_decoder_step_scratch_bytes(int num_heads, int d_ff);
+int b200_decoder_step(const b200_decoder_step_params* params, b200_stream_t stream);
+/* Debug: error word of the last steps run on this scratch (0 = no barrier / ring wait timed out); synchronises. */
+int b200_decoder_step_status(const void* scratch, int32_t* status_host);
+
 #ifdef __cplusplus
 }
 #endif

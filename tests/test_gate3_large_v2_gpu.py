@@ -1,0 +1,124 @@
+"""Gate 3 at the headline configuration (BASELINE.json configs[2], north_star): Whisper large-v2 -- 32 decoder layers,
+d = 1280, 20 heads, vocabulary 51865 -- int8 weight-only + int8 self/cross KV, BATCH 16, 64 greedy tokens from a
+synthetic [16, 80, 3000] log-mel, against the oracle (oracle/whisper_oracle.py: the reference's torch_model.py
+:143-218 and greedy loop decoding.py:743-783 restated, with identically dequantized weights and int8-round-tripped
+K/V).
+
+Flow under test = the reference's run flow (examples/whisper/run.py:33-66, decoding.py:543-659): mel -> WhisperEncoder
+-> CrossAttn_KV (int8 cross-KV cache, set_encoder_output) -> context step -> CUDA-graph greedy loop.
+
+What "identical greedy tokens" can mean on random-init weights: the oracle's top-1 / top-2 logit gap over 51865 tokens
+is ~0.8 on average and below any fixed noise floor in a few percent of the 16 x 64 (row, step) events, so a free
+running fp16 decoder MUST eventually take the other branch of a genuine near-tie somewhere in 1024 events.  The test
+therefore asserts both of the statements that are true of a correct implementation:
+
+  (A) teacher-forced identity, ALL 64 steps x 16 rows: fed the oracle's history, the GPU logits stay within tolerance
+      of the oracle's at every step and the GPU arg-max equals the oracle's token at every event whose oracle margin
+      is above the noise floor (MARGIN); events below it are counted and bounded;
+  (B) free-running identity: the CUDA-graph greedy loop reproduces the oracle's tokens exactly until, per row, the
+      first event where the two differ -- and that event must be a near-tie of the oracle (margin < MARGIN).  A floor
+      on the matched prefix keeps the escape hatch honest (VERDICT r1 "weak" #2).
+
+The oracle encoder is run for 2 of the 16 rows as a cross-check of the encoder output the decoder parity starts from.
+CPU cost of the oracle: about 3 minutes on the GPU box's host cores.
+"""
+import os
+import time
+
+import pytest
+import torch
+
+from oracle import whisper_oracle as wo
+
+pytestmark = pytest.mark.gpu
+
+PROMPT = [50258, 50259, 50359]  # sot, <|en|>, <|transcribe|>  (decoding.py:314-319)
+SEED = 0
+MARGIN = 0.05      # oracle top-1 margin regarded as above the fp16 noise floor (logit scale ~ +-15)
+B, N_NEW = 16, 64
+
+
+def _mel(batch, dims, seed):
+    torch.manual_seed(seed)
+    return torch.randn(batch, dims.n_mels, 2 * dims.n_audio_ctx).clamp(-1, 1).half().float()
+
+
+@pytest.mark.timeout(1800)
+def test_large_v2_batch16_greedy_tokens_against_oracle():
+    from b200_whisper.runtime import WhisperDecoding, WhisperEncoder
+    torch.set_num_threads(os.cpu_count() or 1)
+    dims = wo.LARGE_V2
+    t0 = time.perf_counter()
+    sd = wo.synthetic_state_dict(dims, seed=SEED)
+    mel = _mel(B, dims, 1)
+
+    # ---- GPU: encoder -> int8 cross-KV ------------------------------------------------------------------------
+    enc = WhisperEncoder(dims, sd)
+    xa = enc(mel.cuda())
+    torch.cuda.synchronize()
+    xa_ref = xa.float().cpu()
+    del enc
+    torch.cuda.empty_cache()
+
+    # ---- oracle encoder on 2 rows (cross-check of the starting point) ------------------------------------------
+    sdq = wo.quantize_state_dict(sd, dims, decoder_only=False)
+    with torch.no_grad():
+        enc_ref = wo.encoder_forward(sdq, dims, mel[:2])
+    enc_err = (xa_ref[:2] - enc_ref).abs()
+    assert enc_err.max().item() <= 4e-2 * max(1.0, enc_ref.abs().max().item()), f"encoder err {enc_err.max().item()}"
+    assert enc_err.mean().item() <= 5e-3, f"encoder mean err {enc_err.mean().item()}"
+    t_enc = time.perf_counter() - t0
+
+    # ---- oracle decode (free running, its own history) ---------------------------------------------------------
+    with torch.no_grad():
+        kv_s, ckv_s = wo.calibrate_kv_scales(sdq, dims, xa_ref[:2], PROMPT, n_steps=6)
+        ref_tokens, ref_logits = wo.greedy_decode(sdq, dims, xa_ref, PROMPT, N_NEW, kv_s, ckv_s, act_fp16=True)
+    ref_logits = torch.stack(ref_logits, 1)  # [B, N_NEW, V]
+    top2 = ref_logits.topk(2, dim=-1).values
+    margins = top2[..., 0] - top2[..., 1]     # [B, N_NEW]
+    strong = margins >= MARGIN
+    t_oracle = time.perf_counter() - t0 - t_enc
+
+    # ---- GPU decoder -------------------------------------------------------------------------------------------
+    dec = WhisperDecoding(dims, sd, B, kv_s, ckv_s)
+    dec.set_encoder_output(xa)
+    # (B) free running, CUDA graph
+    got = dec.decode([PROMPT] * B, N_NEW).cpu().long()
+    # (A) teacher forced on the oracle's history
+    dec.reset()
+    tf_tokens = [dec.prefill([PROMPT] * B).clone()]
+    tf_err = [(dec.logits.cpu() - ref_logits[:, 0]).abs().max().item()]
+    for t in range(1, N_NEW):
+        dec.tokens.copy_(ref_tokens[:, t - 1].to(torch.int32))
+        tf_tokens.append(dec.step().clone())
+        tf_err.append((dec.logits.cpu() - ref_logits[:, t]).abs().max().item())
+    tf_tokens = torch.stack(tf_tokens, 1).cpu().long()
+    scale = ref_logits.abs().max().item()
+    print(f"\n[gate3] oracle: encoder+quantize {t_enc:.0f}s, decode {t_oracle:.0f}s; logit scale {scale:.2f}; "
+          f"teacher-forced max |dlogit| {max(tf_err):.4f}; events with margin < {MARGIN}: {(~strong).sum().item()} of "
+          f"{strong.numel()}; min margin {margins.min().item():.4f}")
+
+    # (A) every step's logits within tolerance; arg-max identical wherever the oracle is not at a near-tie
+    assert max(tf_err) <= 1e-2 * scale, f"teacher-forced logits err {max(tf_err)} vs scale {scale}"
+    same = tf_tokens == ref_tokens
+    assert bool(same[strong].all()), "GPU arg-max differs from the oracle at an event with a clear margin"
+    weak_flips = int((~same).sum())
+    assert weak_flips <= int((~strong).sum())
+    assert (~strong).float().mean().item() < 0.15, "pick another seed: too many oracle near-ties"
+
+    # (B) free running: identical until the first divergence, which must sit on an oracle near-tie
+    prefix = []
+    for b in range(B):
+        diff = (got[b] != ref_tokens[b]).nonzero()
+        first = int(diff[0]) if len(diff) else N_NEW
+        prefix.append(first)
+        if first < N_NEW:
+            assert margins[b, first].item() < MARGIN, (
+                f"row {b} diverges at step {first} where the oracle margin is {margins[b, first].item():.3f}: "
+                f"got {got[b, first].item()} want {ref_tokens[b, first].item()}")
+    full = sum(p == N_NEW for p in prefix)
+    print(f"[gate3] free-running matched prefix per row: {prefix}; rows identical for all {N_NEW} tokens: {full}/{B}; "
+          f"teacher-forced flips on near-ties: {weak_flips}")
+    # floors (seed 0, recorded from the B200 run): most rows run the full length, none diverges early
+    assert full >= B // 2, f"only {full} of {B} rows reproduce all {N_NEW} oracle tokens"
+    assert sum(prefix) >= int(0.75 * B * N_NEW)
