@@ -172,10 +172,66 @@ def cpu_baseline(steps, seconds_budget=25.0):
             "ms_per_step": 1e3 * dt / max(done, 1)}
 
 
+REF_WHISPER = "/root/reference/tensorrt_llm_july-release-v1/examples/whisper"
+
+
+def reference_cpu_baseline(steps, seconds_budget=25.0):
+    """The UNMODIFIED reference PyTorch model (examples/whisper/torch_model.py: Whisper, TextDecoder.forward :196-218,
+    install_kv_cache_hooks :270-301 -- what `summarize.py --test_torch` drives through decoding.py:743-783) on the host
+    cores, fp32, large-v2 decoder, batch 16, same synthetic weights as the oracle port.  Only available where
+    /root/reference exists (the build container); returns None elsewhere."""
+    if not os.path.exists(os.path.join(REF_WHISPER, "torch_model.py")):
+        return None
+    import torch
+    sys.dont_write_bytecode = True  # the reference tree is read-only
+    sys.path.insert(0, REF_WHISPER)
+    try:
+        from torch_model import ModelDimensions, Whisper
+    except Exception:
+        return None
+    finally:
+        sys.path.pop(0)
+    from oracle import whisper_oracle as wo
+    torch.set_num_threads(os.cpu_count() or 1)
+    d = wo.LARGE_V2
+    # the encoder is not on the timed path: keep it at one layer so the model fits comfortably in host memory
+    dims = ModelDimensions(d.n_mels, d.n_audio_ctx, d.n_audio_state, d.n_audio_head, 1, d.n_vocab, d.n_text_ctx,
+                           d.n_text_state, d.n_text_head, d.n_text_layer)
+    t0 = time.perf_counter()
+    model = Whisper(dims).float().eval()
+    sd = wo.synthetic_state_dict(d, seed=0, decoder_only=True)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("encoder.") for k in missing), (missing[:3], unexpected[:3])
+    build_s = time.perf_counter() - t0
+    B = BATCH
+    g = torch.Generator().manual_seed(1)
+    xa = torch.randn(B, d.n_audio_ctx, d.n_text_state, generator=g)
+    cache, hooks = model.install_kv_cache_hooks()
+    tokens = torch.tensor([PROMPT] * B)
+    with torch.no_grad():
+        logits = model.decoder(tokens, xa, kv_cache=cache)  # context step + cross K/V projection, untimed
+        cur = logits[:, -1].argmax(-1)[:, None]
+        done = 0
+        t0 = time.perf_counter()
+        while done < steps and (time.perf_counter() - t0) < seconds_budget:
+            logits = model.decoder(cur, xa, kv_cache=cache)
+            cur = logits[:, -1].argmax(-1)[:, None]
+            done += 1
+        dt = time.perf_counter() - t0
+    for h in hooks:
+        h.remove()
+    return {"value": B * done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{done} greedy decoder steps, batch {B}, large-v2 decoder fp32: the reference's own "
+                      f"examples/whisper/torch_model.py (TextDecoder + install_kv_cache_hooks) imported from "
+                      f"/root/reference; model built in {build_s:.1f}s",
+            "ms_per_step": 1e3 * dt / max(done, 1)}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cb = cpu_baseline(max(args.steps, 1), seconds_budget=60.0)
+    # the reference's own module when its tree is present (this container), the oracle port of it otherwise (GPU box)
+    cb = reference_cpu_baseline(max(args.steps, 1), seconds_budget=60.0) or cpu_baseline(max(args.steps, 1), seconds_budget=60.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -25,9 +25,15 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I" + os.pat
           "-I" + PLUG]
 # B200_TC_DEBUG=1: compile the clock64 / %globaltimer stamps into the tcgen05 GEMM (tools/tc_timing*.py,
 # tools/gemm_timeline.py).  Off by default: the stamps cost about 1 % of the decoder step even when unused.
-DEBUG_STAMPS = os.environ.get("B200_TC_DEBUG", "0") == "1"
-if DEBUG_STAMPS:
+TC_DEBUG = os.environ.get("B200_TC_DEBUG", "0") == "1"
+# B200_DS_DEBUG=1: compile the per-phase %globaltimer / clock64 stamps into the persistent decoder-step kernel
+# (tools/step_phases.py).
+DS_DEBUG = os.environ.get("B200_DS_DEBUG", "0") == "1"
+DEBUG_STAMPS = TC_DEBUG or DS_DEBUG
+if TC_DEBUG:
     COMMON = COMMON + ["-DB200_TC_DEBUG=1"]
+if DS_DEBUG:
+    COMMON = COMMON + ["-DB200_DS_DEBUG=1"]
 
 
 def _sources():
@@ -57,7 +63,7 @@ def _headers_stamp():
 
 def _compile(src, stamp, verbose):
     rel = os.path.relpath(src, PKG).replace(os.sep, "_")
-    obj = os.path.join(OBJDIR, f"{rel}.{stamp}{'.dbg' if DEBUG_STAMPS else ''}.o")
+    obj = os.path.join(OBJDIR, f"{rel}.{stamp}{'.tcdbg' if TC_DEBUG else ''}{'.dsdbg' if DS_DEBUG else ''}.o")
     if os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(src):
         return obj
     cmd = [NVCC] + ARCH + COMMON + (["-x", "cu"] if src.endswith(".cpp") else []) + ["-c", src, "-o", obj]
@@ -81,7 +87,7 @@ def build(verbose=False, force=False):
         objs = list(ex.map(lambda s: _compile(s, stamp, verbose), srcs))
     out = os.path.join(LIBDIR, LIBNAME)
     flavour = os.path.join(LIBDIR, ".flavour")
-    want = "debug-stamps" if DEBUG_STAMPS else "release"
+    want = ("tc-debug " if TC_DEBUG else "") + ("ds-debug" if DS_DEBUG else "") if DEBUG_STAMPS else "release"
     have = open(flavour).read().strip() if os.path.exists(flavour) else ""
     if (not os.path.exists(out)) or have != want or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-Xlinker", "--version-script=" + os.path.join(PKG, "exports.map")]

@@ -106,6 +106,7 @@ _SIGS = {
     "b200_decoder_step_scratch_bytes": (_sz, [_i, _i]),
     "b200_decoder_step": (_i, [ctypes.POINTER(DecoderStepParams), _vp]),
     "b200_decoder_step_status": (_i, [_vp, ctypes.POINTER(ctypes.c_int32)]),
+    "b200_debug_decoder_step_timeline": (_i, [_vp]),
 }
 
 

@@ -41,7 +41,7 @@ namespace b200
 
 constexpr int kDsCW = 10;                 // consumer warps
 constexpr int kDsConsumers = kDsCW * 32;  // 320 threads
-constexpr int kDsThreads = kDsConsumers + 32;
+constexpr int kDsThreads = kDsConsumers + 32; // + the ring producer warp
 constexpr int kDsSlots = 19;
 constexpr int kDsSlotBytes = 10240;
 constexpr int kDsUnitK = 1280;            // k extent of a weight unit (8 columns x 1280 k = one slot)
@@ -51,7 +51,7 @@ constexpr int kDsScratchFloats = kDsCW * kDsRoundTiles * 16 * 8; // 25600 B: k-p
 constexpr int kDsStatFloats = kDsCW * 16 * 3;                    // per (warp, row): count, mean, M2
 constexpr int kDsPart = kDh + 4;          // attention partial: m, l, 2 pad, o[64]
 constexpr size_t kDsSmemBytes = (size_t) kDsSlots * kDsSlotBytes + sizeof(float) * (kDsScratchFloats + kDsStatFloats)
-    + sizeof(uint64_t) * 2 * kDsSlots + 64;
+    + sizeof(uint64_t) * 2 * kDsSlots + 64 + 2 * 32 * sizeof(uint64_t);
 constexpr long long kDsWaitCycles = 3000000000ll; // SM cycles before a wait gives up (~1.5 s; a step takes ~1 ms)
 constexpr int kDsMmhaWarpsPerPair = 3;
 constexpr int kDsMaxPairsPerCta = kDsCW / kDsMmhaWarpsPerPair;
@@ -102,18 +102,39 @@ struct DsShared
     float* stats;
     uint64_t* full;
     uint64_t* empty;
-    volatile int* dead; // CTA-local: a wait timed out, stop waiting
+    uint32_t dead;     // shared-space address of the CTA-local "a wait timed out, stop waiting" flag
+    uint32_t progress; // shared-space address of the ring producer's item count (read by the L2 prefetch lane)
 };
 
 struct DsCtx
 {
     DsShared sm;
     unsigned* sync;    // [0] arrivals, [1] exits, [2] status
+    long long* dbg;    // optional %globaltimer stamps [CTA][phase][2] (wait returned, work done); tools/step_phases.py
     unsigned phase;    // grid barriers passed so far
     unsigned item;     // ring items consumed so far by this CTA
     int c, G;          // CTA index, number of CTAs
     int tid, warp, lane;
 };
+
+__device__ __forceinline__ int ds_dead(const DsShared& sm)
+{
+    int v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(sm.dead) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void ds_set_dead(const DsShared& sm)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sm.dead), "r"(1) : "memory");
+}
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // bounded mbarrier wait (a lost TMA completion or a schedule mismatch must not hang the GPU)
 __device__ __forceinline__ void ds_mbar_wait(DsCtx& cx, uint64_t* bar, uint32_t parity, int code)
@@ -123,11 +144,11 @@ __device__ __forceinline__ void ds_mbar_wait(DsCtx& cx, uint64_t* bar, uint32_t 
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity))
     {
-        if (*cx.sm.dead || clock64() - t0 > kDsWaitCycles)
+        if (ds_dead(cx.sm) || clock64() - t0 > kDsWaitCycles)
         {
-            if (!*cx.sm.dead)
+            if (!ds_dead(cx.sm))
             {
-                *cx.sm.dead = 1;
+                ds_set_dead(cx.sm);
                 atomicCAS(cx.sync + 2, 0u, (unsigned) code | ((unsigned) cx.c << 8) | (cx.phase << 16));
             }
             return;
@@ -137,40 +158,74 @@ __device__ __forceinline__ void ds_mbar_wait(DsCtx& cx, uint64_t* bar, uint32_t 
 
 // ---- grid barrier --------------------------------------------------------------------------------------------
 // arrive: every consumer thread's global stores of the phase are ordered before the CTA's release increment
+__device__ __forceinline__ long long ds_globaltimer()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+[[maybe_unused]] constexpr int kDsDbgPhases = 512; // stamps per CTA in the debug buffer
+
+// fine-grained stamps of CTA 0 inside a phase (debug buffer region after the per-CTA barrier stamps)
+__device__ __forceinline__ void ds_stamp(DsCtx& cx, int slot)
+{
+#if defined(B200_DS_DEBUG)
+    if (cx.dbg != nullptr && cx.c == 0 && cx.tid == 0 && cx.phase < kDsDbgPhases)
+        cx.dbg[(size_t) cx.G * kDsDbgPhases * 2 + (size_t) cx.phase * 16 + slot] = clock64(); // SM cycles: fine resolution
+#endif
+}
+
 __device__ __forceinline__ void ds_grid_arrive(DsCtx& cx)
 {
+    ds_stamp(cx, 8);
+#if defined(B200_DS_DEBUG)
+    if (cx.dbg != nullptr && cx.tid == 0 && cx.phase < kDsDbgPhases)
+        cx.dbg[((size_t) cx.c * kDsDbgPhases + cx.phase) * 2 + 1] = ds_globaltimer();
+#endif
+    // bar.sync orders every consumer thread's stores before thread 0's release (cumulativity); the release itself is
+    // the only GPU-scope fence on this side (MEMBAR.ALL.GPU + RED, no sequentially-consistent fence)
     consumer_sync();
     if (cx.tid == 0)
-    {
-        __threadfence();
         red_release_add_u32(cx.sync, 1u);
-    }
+    ds_stamp(cx, 9);
     ++cx.phase;
 }
 
-// wait until all G CTAs have arrived `phase` times
+// wait until all G CTAs have arrived `phase` times: one thread polls with relaxed GPU-scope loads, then bar.sync.
+// The writers release (MEMBAR.GPU + RED) after their data stores, so the data is in L2 before the count moves; every
+// load of data written by another CTA is an L1-bypassing GPU-scope load (ld.global.cg) issued after the bar.sync,
+// i.e. served by L2 after the count was observed there.  An acquire on this side (ld.acquire.gpu / fence) costs a
+// CCTL.IVALL per poll -- the L1 invalidation turns the kernel's few register spills into L2 round trips on the critical
+// path (measured: +1.1 us per barrier) -- and protects nothing that is read through L1.
 __device__ __forceinline__ void ds_grid_wait(DsCtx& cx)
 {
-    if (cx.tid == 0 && !*cx.sm.dead)
+    if (cx.tid == 0 && !ds_dead(cx.sm))
     {
         const unsigned target = cx.phase * (unsigned) cx.G;
         unsigned spins = 0;
-        const long long t0 = clock64();
-        while (ld_acquire_u32(cx.sync) < target)
+        long long t0 = 0;
+        while (ld_relaxed_u32(cx.sync) < target)
         {
             if ((++spins & 255u) == 0u)
             {
-                if (clock64() - t0 > kDsWaitCycles || ld_acquire_u32(cx.sync + 2) != 0u)
+                if (t0 == 0)
+                    t0 = clock64();
+                if (clock64() - t0 > kDsWaitCycles || ld_relaxed_u32(cx.sync + 2) != 0u)
                 {
-                    *cx.sm.dead = 1;
+                    ds_set_dead(cx.sm);
                     atomicCAS(cx.sync + 2, 0u, (unsigned) DS_ERR_GRID_BARRIER | ((unsigned) cx.c << 8) | (cx.phase << 16));
                     break;
                 }
             }
         }
-        __threadfence();
+        ds_stamp(cx, 7);
     }
     consumer_sync();
+#if defined(B200_DS_DEBUG)
+    if (cx.dbg != nullptr && cx.tid == 0 && cx.phase < kDsDbgPhases)
+        cx.dbg[((size_t) cx.c * kDsDbgPhases + cx.phase) * 2] = ds_globaltimer();
+#endif
 }
 
 // ---- static schedule helpers (shared by the producer and the consumers) ------------------------------------------
@@ -200,21 +255,54 @@ struct DsModel
     int L, B, H, d, dff, Smax, S, nch;
 };
 
-// ---- producer: one lane walks the whole step's schedule ---------------------------------------------------------
-__device__ void ds_producer(const DsModel& m, DsCtx& cx)
+// ---- producers: one lane each, both walk the whole step's static schedule -------------------------------------------
+//   PF = false  warp 10: fills the shared-memory ring (cp.async.bulk + mbarrier), at most kDsSlots items ahead
+//   PF = true   warp 11: the same walk, `l2_ahead` items ahead of the ring producer, issuing cp.async.bulk.prefetch.L2
+//               only: HBM latency is paid into L2 (tens of MB in flight chip-wide), the ring then fills at L2 latency
+__device__ __forceinline__ void ds_l2_prefetch(const void* p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <bool PF>
+__device__ __forceinline__ void ds_producer(const DsModel& m, DsCtx& cx, unsigned l2_ahead)
 {
     const uint64_t pol = policy_evict_first();
     unsigned it = 0;
-    auto acquire = [&](uint32_t bytes) -> uint8_t*
+    // returns false when the kernel is draining after a timed-out wait
+    auto begin_item = [&](uint32_t bytes, uint8_t*& dst, uint64_t*& bar) -> bool
     {
-        const unsigned s = it % kDsSlots, use = it / kDsSlots;
-        if (use > 0)
-            ds_mbar_wait(cx, &cx.sm.empty[s], (use - 1) & 1, DS_ERR_RING_EMPTY_WAIT);
-        mbar_arrive_expect_tx(&cx.sm.full[s], bytes);
-        ++it;
-        return cx.sm.ring + (size_t) s * kDsSlotBytes;
+        if constexpr (PF)
+        {
+            unsigned prog;
+            for (;;)
+            {
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(prog) : "r"(cx.sm.progress) : "memory");
+                if (it < prog + l2_ahead)
+                    break;
+                if (ds_dead(cx.sm))
+                    return false;
+                __nanosleep(64);
+            }
+            dst = nullptr, bar = nullptr;
+            ++it;
+            return true;
+        }
+        else
+        {
+            const unsigned s = it % kDsSlots, use = it / kDsSlots;
+            if (use > 0)
+                ds_mbar_wait(cx, &cx.sm.empty[s], (use - 1) & 1, DS_ERR_RING_EMPTY_WAIT);
+            if (ds_dead(cx.sm))
+                return false;
+            mbar_arrive_expect_tx(&cx.sm.full[s], bytes);
+            ++it;
+            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(cx.sm.progress), "r"(it) : "memory");
+            dst = cx.sm.ring + (size_t) s * kDsSlotBytes, bar = &cx.sm.full[s];
+            return true;
+        }
     };
-    auto gemm = [&](const int8_t* W, int K, int N, int which)
+    auto gemm = [&](const int8_t* W, int K, int N, int which) -> bool
     {
         const DsGemmShape g{K, N, ds_rot(which, cx.G)};
         const int nq = g.nq(), KU = K / nq, first = g.first_tile(cx.c, cx.G), nt = g.ntiles(cx.c, cx.G);
@@ -224,24 +312,29 @@ __device__ void ds_producer(const DsModel& m, DsCtx& cx)
             const int tile = first + j * cx.G;
             for (int q = 0; q < nq; ++q)
             {
-                const unsigned s = it % kDsSlots;
-                uint8_t* dst = acquire((uint32_t) 8 * KU);
-                if (*cx.sm.dead)
-                    return;
+                uint8_t* dst;
+                uint64_t* bar;
+                if (!begin_item((uint32_t) 8 * KU, dst, bar))
+                    return false;
 #pragma unroll
                 for (int rp = 0; rp < 4; ++rp)
-                    bulk_g2s_hint(dst + (size_t) rp * 2 * KU, base + (size_t) (4 * tile + rp) * 2 * K + (size_t) q * 2 * KU,
-                        (uint32_t) 2 * KU, &cx.sm.full[s], pol);
+                {
+                    const uint8_t* src = base + (size_t) (4 * tile + rp) * 2 * K + (size_t) q * 2 * KU;
+                    if constexpr (PF)
+                        ds_l2_prefetch(src, (uint32_t) 2 * KU);
+                    else
+                        bulk_g2s_hint(dst + (size_t) rp * 2 * KU, src, (uint32_t) 2 * KU, bar, pol);
+                }
             }
         }
+        return true;
     };
     const int pairs = m.B * m.H;
     for (int l = 0; l < m.L; ++l)
     {
         const b200_decoder_layer& ly = m.layers[l];
-        gemm(ly.qkv_w, m.d, 3 * m.d, 0);
-        gemm(ly.attn_out_w, m.d, m.d, 1);
-        gemm(ly.cross_q_w, m.d, m.d, 2);
+        if (!gemm(ly.qkv_w, m.d, 3 * m.d, 0) || !gemm(ly.attn_out_w, m.d, m.d, 1) || !gemm(ly.cross_q_w, m.d, m.d, 2))
+            return;
         for (int p = cx.c; p < pairs; p += cx.G)
         {
             const int b = p / m.H, h = p - b * m.H;
@@ -251,17 +344,24 @@ __device__ void ds_producer(const DsModel& m, DsCtx& cx)
             {
                 const int key0 = ch * kDsChunkKeys;
                 const uint32_t bytes = (uint32_t) min(kDsChunkKeys, m.S - key0) * kDh;
-                const unsigned s = it % kDsSlots;
-                uint8_t* dst = acquire(2 * bytes);
-                if (*cx.sm.dead)
+                uint8_t* dst;
+                uint64_t* bar;
+                if (!begin_item(2 * bytes, dst, bar))
                     return;
-                bulk_g2s_hint(dst, kb + (size_t) key0 * kDh, bytes, &cx.sm.full[s], pol);
-                bulk_g2s_hint(dst + kDsSlotBytes / 2, vb + (size_t) key0 * kDh, bytes, &cx.sm.full[s], pol);
+                if constexpr (PF)
+                {
+                    ds_l2_prefetch(kb + (size_t) key0 * kDh, bytes);
+                    ds_l2_prefetch(vb + (size_t) key0 * kDh, bytes);
+                }
+                else
+                {
+                    bulk_g2s_hint(dst, kb + (size_t) key0 * kDh, bytes, bar, pol);
+                    bulk_g2s_hint(dst + kDsSlotBytes / 2, vb + (size_t) key0 * kDh, bytes, bar, pol);
+                }
             }
         }
-        gemm(ly.cross_out_w, m.d, m.d, 3);
-        gemm(ly.fc1_w, m.d, m.dff, 4);
-        gemm(ly.fc2_w, m.dff, m.d, 5);
+        if (!gemm(ly.cross_out_w, m.d, m.d, 3) || !gemm(ly.fc1_w, m.d, m.dff, 4) || !gemm(ly.fc2_w, m.dff, m.d, 5))
+            return;
     }
 }
 
@@ -289,29 +389,161 @@ __device__ __forceinline__ __half ds_finish(float acc, bool has_bias, float bias
         o = __float2half_rn(__half2float(o) + biasv);
     if (activation == B200_ACT_GELU_ERF)
         o = __float2half_rn(gelu_erf(__half2float(o)));
-    else if (activation == B200_ACT_GELU_TANH)
-        o = __float2half_rn(gelu_tanh(__half2float(o)));
     if (has_res)
         o = __float2half_rn(__half2float(o) + res);
     return o;
 }
 
-__device__ __noinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m, DsCtx& cx)
+// A fragments (4 MMAs' worth: 16 registers) of k-block `kb` of the activation matrix, this lane's share
+__device__ __forceinline__ void ds_load_a(const __half* A, int kb, int lane, uint4 (&dst)[4])
+{
+    const __half* ap = A + ((size_t) (kb * 4) * 32 + lane) * 8;
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+        dst[w] = ldcg_u4(ap + (size_t) w * 32 * 8);
+}
+
+__device__ __forceinline__ uint32_t ds_sel4(const uint4& v, int w) // w is a compile-time constant after unrolling
+{
+    return w == 0 ? v.x : (w == 1 ? v.y : (w == 2 ? v.z : v.w));
+}
+
+__device__ __forceinline__ __half2 ds_u2h2(uint32_t u)
+{
+    return *reinterpret_cast<__half2*>(&u);
+}
+
+// One k-block (64 k) of up to RT weight tiles: 128-bit shared-memory reads of this lane's column / 16-k chunk, PRMT +
+// HSUB2 dequant, optional gamma pair, and the MMAs with w outer / tile inner so the tiles' accumulator chains interleave.
+// D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col); not volatile: a pure function of its operands, so the
+// compiler may interleave the independent chains of different tiles and hoist the dequant of the next operand
+__device__ __forceinline__ void ds_mma(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// One k-block (64 k) of exactly NT weight tiles (compile-time: no per-tile branches around the warp-synchronous MMAs):
+// 128-bit shared-memory reads of this lane's column / 16-k chunk, PRMT + HSUB2 dequant, optional gamma pair, and the
+// MMAs with w outer / tile inner so the tiles' accumulator chains interleave.
+template <int NT, bool FOLD>
+__device__ __forceinline__ void ds_mma_kblock(float (&acc)[NT][4], const uint4 (&af)[4], const uint8_t* ring, unsigned item0,
+    int item_stride, uint32_t lane_off, const uint4& glo, const uint4& ghi)
+{
+    uint4 wv[NT];
+#pragma unroll
+    for (int jj = 0; jj < NT; ++jj)
+        wv[jj] = *reinterpret_cast<const uint4*>(ring + (size_t) ((item0 + (unsigned) (jj * item_stride)) % kDsSlots) * kDsSlotBytes + lane_off);
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+    {
+        const __half2 g_lo = ds_u2h2(ds_sel4(glo, w)), g_hi = ds_u2h2(ds_sel4(ghi, w));
+#pragma unroll
+        for (int jj = 0; jj < NT; ++jj)
+        {
+            __half2 lo, hi;
+            dequant_word(ds_sel4(wv[jj], w), lo, hi);
+            if constexpr (FOLD)
+            {
+                lo = __hmul2(lo, g_lo);
+                hi = __hmul2(hi, g_hi);
+            }
+            ds_mma(acc[jj], af[w], h2u(lo), h2u(hi));
+        }
+    }
+}
+
+// this warp's two k-blocks of NT tiles starting at ring item `item0` (unit stride `item_stride`), partial sums to `scr`
+template <int NT, bool FOLD>
+__device__ __forceinline__ void ds_mma_tiles(const uint4 (&af0)[4], const uint4 (&af1)[4], bool kv0, bool kv1, const uint8_t* ring,
+    unsigned item0, int item_stride, uint32_t off0, uint32_t off1, const uint4 (&glo)[2], const uint4 (&ghi)[2], float* scr,
+    int g, int t, bool accumulate)
+{
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        if (accumulate)
+        {
+            const float2 lo = *reinterpret_cast<const float2*>(scr + (size_t) j * 128 + g * 8 + 2 * t);
+            const float2 hi = *reinterpret_cast<const float2*>(scr + (size_t) j * 128 + (g + 8) * 8 + 2 * t);
+            acc[j][0] = lo.x, acc[j][1] = lo.y, acc[j][2] = hi.x, acc[j][3] = hi.y;
+        }
+        else
+            acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    }
+    if (kv0)
+        ds_mma_kblock<NT, FOLD>(acc, af0, ring, item0, item_stride, off0, glo[0], ghi[0]);
+    if (kv1)
+        ds_mma_kblock<NT, FOLD>(acc, af1, ring, item0, item_stride, off1, glo[1], ghi[1]);
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        *reinterpret_cast<float2*>(scr + (size_t) j * 128 + g * 8 + 2 * t) = make_float2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<float2*>(scr + (size_t) j * 128 + (g + 8) * 8 + 2 * t) = make_float2(acc[j][2], acc[j][3]);
+    }
+}
+
+// rt (1..5) tiles as groups of at most three (register budget), each group a branch-free instantiation
+template <bool FOLD>
+__device__ __forceinline__ void ds_mma_round(int rt, const uint4 (&af0)[4], const uint4 (&af1)[4], bool kv0, bool kv1,
+    const uint8_t* ring, unsigned item0, int item_stride, uint32_t off0, uint32_t off1, const uint4 (&glo)[2],
+    const uint4 (&ghi)[2], float* scr, int g, int t, bool accumulate)
+{
+#define DS_TILES(NT, FIRST)                                                                                            \
+    ds_mma_tiles<NT, FOLD>(af0, af1, kv0, kv1, ring, item0 + (unsigned) ((FIRST) * item_stride), item_stride, off0, off1, glo, \
+        ghi, scr + (size_t) (FIRST) * 128, g, t, accumulate)
+    switch (rt)
+    {
+    case 1: DS_TILES(1, 0); break;
+    case 2: DS_TILES(2, 0); break;
+    case 3: DS_TILES(3, 0); break;
+    case 4: DS_TILES(2, 0); DS_TILES(2, 2); break;
+    case 5: DS_TILES(3, 0); DS_TILES(2, 3); break;
+    default: break;
+    }
+#undef DS_TILES
+}
+
+__device__ __forceinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m, DsCtx& cx)
 {
     const int lane = cx.lane, warp = cx.warp, tid = cx.tid;
     const int g = lane >> 2, t = lane & 3;
     const DsGemmShape shp{a.K, a.N, ds_rot(a.which, cx.G)};
     const int nq = shp.nq(), KU = a.K / nq, nkbu = KU >> 6;
     const int first = shp.first_tile(cx.c, cx.G), nt = shp.ntiles(cx.c, cx.G);
-    const bool fold = a.gamma != nullptr;
-    const int R = min(kDsRoundTiles, max(1, 9 / nq)); // tiles per round: a round never holds more than 9 ring slots
+    const bool fold = a.gamma != nullptr; // only with nq == 1 (hidden size <= 1280, checked on the host)
+    // tiles per reduction round.  Deep-K matmuls (fc2: four 1280-k units per tile) take 2 tiles per round so a round
+    // never holds more than 8 ring slots, and run on the second, register-lean code path below.
+    constexpr int RB = 2;
+    const int R = nq == 1 ? kDsRoundTiles : RB;
     // this warp's k-blocks inside a unit: warp, warp + 10
-    const bool kv0 = warp < nkbu, kv1 = warp + kDsCW < nkbu;
+    const int kbl0 = warp, kbl1 = warp + kDsCW;
+    const bool kv0 = kbl0 < nkbu, kv1 = kbl1 < nkbu;
+    // byte offset of this lane's 16 bytes inside a k-block of a weight unit: column g of the tile (row pair g/2, parity
+    // g%2), 16-k chunk t
+    const uint32_t lane_off = (uint32_t) ((g >> 1) * 2 * KU + (g & 1) * 64 + t * 16);
 
     // ---- static operands, requested before the grid barrier ----
     // epilogue item of this thread in a round: (tile jj, row, column pair cp)
     const int e_jj = tid >> 6, e_row = (tid & 63) >> 2, e_cp = tid & 3;
     float e_sc[2] = {0.f, 0.f}, e_bias[2] = {0.f, 0.f}, e_c1[2] = {0.f, 0.f}, e_c2[2] = {0.f, 0.f}, e_res[2] = {0.f, 0.f};
+    // The per-column vectors are static data in HBM: their lines are pulled into L2 before the grid barrier (a DRAM
+    // round trip hidden behind the wait) and the values are loaded right after the MMAs were issued, under the reduction
+    // -- holding ten more registers across the MMAs would spill.
+    auto prefetch_epi_static = [&](int j0)
+    {
+        if (e_jj < min(R, nt - j0) && e_cp == 0 && e_row < 4)
+        {
+            const int n0 = 8 * (first + (j0 + e_jj) * cx.G);
+            const void* ptr = e_row == 0 ? (const void*) (a.scales + n0)
+                : e_row == 1             ? (const void*) (a.bias != nullptr ? a.bias + n0 : a.scales + n0)
+                : e_row == 2             ? (const void*) (fold ? (const void*) (a.c1s + n0) : (const void*) (a.scales + n0))
+                                         : (const void*) (fold ? (const void*) (a.c2 + n0) : (const void*) (a.scales + n0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+    };
     auto load_epi_static = [&](int j0)
     {
         if (e_jj < min(R, nt - j0))
@@ -338,92 +570,89 @@ __device__ __noinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m, Ds
             }
         }
     };
-    load_epi_static(0);
+    prefetch_epi_static(0);
     uint4 glo[2], ghi[2]; // gamma pairs of this thread's B fragments: lo = k 16t+2w.., hi = +8, per k-block
+    glo[0] = glo[1] = ghi[0] = ghi[1] = make_uint4(0u, 0u, 0u, 0u);
     if (fold)
     {
-#pragma unroll
-        for (int kbi = 0; kbi < 2; ++kbi)
+        if (kv0)
         {
-            const int kbl = warp + kDsCW * kbi;
-            if (kbl < nkbu)
-            {
-                const uint4* gp = reinterpret_cast<const uint4*>(a.gamma + 64 * kbl + 16 * t);
-                glo[kbi] = __ldg(gp);
-                ghi[kbi] = __ldg(gp + 1);
-            }
+            const uint4* gp = reinterpret_cast<const uint4*>(a.gamma + 64 * kbl0 + 16 * t);
+            glo[0] = __ldg(gp), ghi[0] = __ldg(gp + 1);
+        }
+        if (kv1)
+        {
+            const uint4* gp = reinterpret_cast<const uint4*>(a.gamma + 64 * kbl1 + 16 * t);
+            glo[1] = __ldg(gp), ghi[1] = __ldg(gp + 1);
         }
     }
 
     ds_grid_wait(cx);
+    ds_stamp(cx, 0);
 
     for (int j0 = 0; j0 < nt || j0 == 0; j0 += R)
     {
         const int rt = max(0, min(R, nt - j0));
-        if (j0 > 0)
-            load_epi_static(j0);
-        float acc[kDsRoundTiles][4];
-#pragma unroll
-        for (int j = 0; j < kDsRoundTiles; ++j)
-            acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        float st_n = 0.f, st_mean[2] = {0.f, 0.f}, st_m2[2] = {0.f, 0.f};
-        for (int q = 0; q < nq; ++q)
+        float* scr = cx.sm.scratch + ((size_t) (warp * kDsRoundTiles) * 16) * 8;
+        if (nq == 1)
         {
-            // A fragments of this warp's two k-blocks of quarter q
-            uint4 af[2][4];
+            // ---- path A: one 1280-k unit per tile, up to 5 tiles, optional folded LayerNorm ----
+            uint4 af0[4], af1[4];
+            if (kv0)
+                ds_load_a(a.A, kbl0, lane, af0);
+            if (kv1)
+                ds_load_a(a.A, kbl1, lane, af1);
 #pragma unroll
-            for (int kbi = 0; kbi < 2; ++kbi)
+            for (int jj = 0; jj < kDsRoundTiles; ++jj)
             {
-                const int kbl = warp + kDsCW * kbi;
-                if (kbl < nkbu)
+                if (jj < rt)
                 {
-                    const __half* ap = a.A + ((size_t) ((q * nkbu + kbl) * 4) * 32 + lane) * 8;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w)
-                        af[kbi][w] = ldcg_u4(ap + (size_t) w * 32 * 8);
-                }
-                else
-                {
-#pragma unroll
-                    for (int w = 0; w < 4; ++w)
-                        af[kbi][w] = make_uint4(0u, 0u, 0u, 0u);
+                    const unsigned it = cx.item + (unsigned) jj;
+                    ds_mbar_wait(cx, &cx.sm.full[it % kDsSlots], (it / kDsSlots) & 1, DS_ERR_RING_FULL_WAIT);
                 }
             }
+            ds_stamp(cx, 4);
+            if (fold)
+                ds_mma_round<true>(rt, af0, af1, kv0, kv1, cx.sm.ring, cx.item, 1, lane_off + kbl0 * 128, lane_off + kbl1 * 128, glo,
+                    ghi, scr, g, t, false);
+            else
+                ds_mma_round<false>(rt, af0, af1, kv0, kv1, cx.sm.ring, cx.item, 1, lane_off + kbl0 * 128, lane_off + kbl1 * 128, glo,
+                    ghi, scr, g, t, false);
+            ds_stamp(cx, 5);
             if (fold && j0 == 0)
             {
                 // LayerNorm statistics of rows g and g+8 over this warp's k-blocks (shifted sums, then exact halving
-                // merges over the 4 lanes of a row: equal counts)
-                const int nv = (kv0 ? 1 : 0) + (kv1 ? 1 : 0);
-                if (nv > 0)
+                // merges over the 4 lanes of a row: equal counts); after the MMAs were issued: off their critical path
+                float st_n = 0.f, st_mean[2] = {0.f, 0.f}, st_m2[2] = {0.f, 0.f};
+                if (kv0)
                 {
-                    const float sh0 = __low2float(*reinterpret_cast<const __half2*>(&af[0][0].x));
-                    const float sh1 = __low2float(*reinterpret_cast<const __half2*>(&af[0][0].y));
+                    const float sh0 = __low2float(*reinterpret_cast<const __half2*>(&af0[0].x));
+                    const float sh1 = __low2float(*reinterpret_cast<const __half2*>(&af0[0].y));
                     float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
-#pragma unroll
-                    for (int kbi = 0; kbi < 2; ++kbi)
+                    auto accum = [&](const uint4 (&af)[4])
                     {
-                        if (kbi < nv)
+#pragma unroll
+                        for (int w = 0; w < 4; ++w)
                         {
+                            const uint32_t r0[2] = {af[w].x, af[w].z};
+                            const uint32_t r1[2] = {af[w].y, af[w].w};
 #pragma unroll
-                            for (int w = 0; w < 4; ++w)
+                            for (int i = 0; i < 2; ++i)
                             {
-                                const uint32_t r0[2] = {af[kbi][w].x, af[kbi][w].z};
-                                const uint32_t r1[2] = {af[kbi][w].y, af[kbi][w].w};
-#pragma unroll
-                                for (int i = 0; i < 2; ++i)
-                                {
-                                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&r0[i]));
-                                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&r1[i]));
-                                    const float d0 = f0.x - sh0, d1 = f0.y - sh0, d2 = f1.x - sh1, d3 = f1.y - sh1;
-                                    sa0 += d0 + d1;
-                                    sb0 = fmaf(d0, d0, fmaf(d1, d1, sb0));
-                                    sa1 += d2 + d3;
-                                    sb1 = fmaf(d2, d2, fmaf(d3, d3, sb1));
-                                }
+                                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&r0[i]));
+                                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&r1[i]));
+                                const float d0 = f0.x - sh0, d1 = f0.y - sh0, d2 = f1.x - sh1, d3 = f1.y - sh1;
+                                sa0 += d0 + d1;
+                                sb0 = fmaf(d0, d0, fmaf(d1, d1, sb0));
+                                sa1 += d2 + d3;
+                                sb1 = fmaf(d2, d2, fmaf(d3, d3, sb1));
                             }
                         }
-                    }
-                    float cn = 16.f * (float) nv;
+                    };
+                    accum(af0);
+                    if (kv1)
+                        accum(af1);
+                    float cn = kv1 ? 32.f : 16.f;
                     const float rn = 1.f / cn;
                     float cm0 = sh0 + sa0 * rn, cM0 = sb0 - sa0 * sa0 * rn;
                     float cm1 = sh1 + sa1 * rn, cM1 = sb1 - sa1 * sa1 * rn;
@@ -441,61 +670,58 @@ __device__ __noinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m, Ds
                     }
                     st_n = cn, st_mean[0] = cm0, st_m2[0] = cM0, st_mean[1] = cm1, st_m2[1] = cM1;
                 }
-            }
-#pragma unroll
-            for (int jj = 0; jj < kDsRoundTiles; ++jj)
-            {
-                if (jj >= rt)
-                    break;
-                const unsigned it = cx.item + (unsigned) (jj * nq + q);
-                const unsigned s = it % kDsSlots;
-                ds_mbar_wait(cx, &cx.sm.full[s], (it / kDsSlots) & 1, DS_ERR_RING_FULL_WAIT);
-                const uint8_t* wb = cx.sm.ring + (size_t) s * kDsSlotBytes + (size_t) (g >> 1) * 2 * KU + (g & 1) * 64 + t * 16;
-#pragma unroll
-                for (int kbi = 0; kbi < 2; ++kbi)
+                if (t == 0)
                 {
-                    const int kbl = warp + kDsCW * kbi;
-                    if (kbl < nkbu)
-                    {
-                        const uint4 wv = *reinterpret_cast<const uint4*>(wb + kbl * 128);
-                        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
-                        const uint32_t gl[4] = {glo[kbi].x, glo[kbi].y, glo[kbi].z, glo[kbi].w};
-                        const uint32_t gh[4] = {ghi[kbi].x, ghi[kbi].y, ghi[kbi].z, ghi[kbi].w};
-#pragma unroll
-                        for (int w = 0; w < 4; ++w)
-                        {
-                            __half2 lo, hi;
-                            dequant_word(words[w], lo, hi);
-                            if (fold)
-                            {
-                                lo = __hmul2(lo, *reinterpret_cast<const __half2*>(&gl[w]));
-                                hi = __hmul2(hi, *reinterpret_cast<const __half2*>(&gh[w]));
-                            }
-                            mma_m16n8k16(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3], af[kbi][w].x, af[kbi][w].y,
-                                af[kbi][w].z, af[kbi][w].w, h2u(lo), h2u(hi));
-                        }
-                    }
+                    float* sp = cx.sm.stats + (size_t) warp * 16 * 3;
+                    sp[g * 3 + 0] = st_n, sp[g * 3 + 1] = st_mean[0], sp[g * 3 + 2] = st_m2[0];
+                    sp[(g + 8) * 3 + 0] = st_n, sp[(g + 8) * 3 + 1] = st_mean[1], sp[(g + 8) * 3 + 2] = st_m2[1];
                 }
             }
         }
-        // ---- k-partials -> shared memory, reduce in warp order ----
-#pragma unroll
-        for (int jj = 0; jj < kDsRoundTiles; ++jj)
+        else
         {
-            if (jj < rt)
+            // ---- path B: deep K (nq units per tile), <= 2 tiles per round.  The A fragments of two quarters are
+            // requested together, so the nq L2 round trips overlap pairwise instead of queueing behind each other. ----
+            // The partial sums of a warp live in its own scratch rows between quarters (re-read by the same thread: no
+            // barrier needed), so the register footprint is one quarter pair's A fragments + <= 2 tiles of accumulators.
+            uint4 afA[2][4], afB[2][4]; // even / odd quarter of a pair: [k-block][w]
+#pragma unroll 1
+            for (int q = 0; q < nq; q += 2)
             {
-                float* dst = cx.sm.scratch + ((size_t) (warp * kDsRoundTiles + jj) * 16) * 8;
-                *reinterpret_cast<float2*>(dst + g * 8 + 2 * t) = make_float2(acc[jj][0], acc[jj][1]);
-                *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * t) = make_float2(acc[jj][2], acc[jj][3]);
+                const bool two = q + 1 < nq;
+                if (kv0)
+                    ds_load_a(a.A, q * nkbu + kbl0, lane, afA[0]);
+                if (kv1)
+                    ds_load_a(a.A, q * nkbu + kbl1, lane, afA[1]);
+                if (two && kv0)
+                    ds_load_a(a.A, (q + 1) * nkbu + kbl0, lane, afB[0]);
+                if (two && kv1)
+                    ds_load_a(a.A, (q + 1) * nkbu + kbl1, lane, afB[1]);
+#pragma unroll
+                for (int jj = 0; jj < RB; ++jj)
+                {
+                    if (jj < rt)
+                    {
+                        const unsigned it = cx.item + (unsigned) (jj * nq + q);
+                        ds_mbar_wait(cx, &cx.sm.full[it % kDsSlots], (it / kDsSlots) & 1, DS_ERR_RING_FULL_WAIT);
+                        if (two)
+                            ds_mbar_wait(cx, &cx.sm.full[(it + 1) % kDsSlots], ((it + 1) / kDsSlots) & 1, DS_ERR_RING_FULL_WAIT);
+                    }
+                }
+                if (q == 0)
+                    ds_stamp(cx, 4);
+                ds_mma_round<false>(rt, afA[0], afA[1], kv0, kv1, cx.sm.ring, cx.item + (unsigned) q, nq, lane_off + kbl0 * 128,
+                    lane_off + kbl1 * 128, glo, ghi, scr, g, t, q > 0);
+                if (two)
+                    ds_mma_round<false>(rt, afB[0], afB[1], kv0, kv1, cx.sm.ring, cx.item + (unsigned) (q + 1), nq,
+                        lane_off + kbl0 * 128, lane_off + kbl1 * 128, glo, ghi, scr, g, t, true);
             }
+            ds_stamp(cx, 5);
         }
-        if (fold && j0 == 0 && t == 0)
-        {
-            float* sp = cx.sm.stats + (size_t) warp * 16 * 3;
-            sp[g * 3 + 0] = st_n, sp[g * 3 + 1] = st_mean[0], sp[g * 3 + 2] = st_m2[0];
-            sp[(g + 8) * 3 + 0] = st_n, sp[(g + 8) * 3 + 1] = st_mean[1], sp[(g + 8) * 3 + 2] = st_m2[1];
-        }
+        ds_stamp(cx, 1);
+        load_epi_static(j0); // L2 hits (prefetched before the barrier); in flight under the reduction
         consumer_sync();
+        ds_stamp(cx, 2);
         if (tid == 0)
         {
             // the round's weight slots are drained: hand them back to the producer
@@ -503,6 +729,7 @@ __device__ __noinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m, Ds
                 mbar_arrive(&cx.sm.empty[(cx.item + (unsigned) u) % kDsSlots]);
         }
         cx.item += (unsigned) (rt * nq);
+        // ---- reduce the ten k-partials in warp order, epilogue ----
         if (e_jj < rt)
         {
             float s0 = 0.f, s1 = 0.f;
@@ -550,6 +777,7 @@ __device__ __noinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m, Ds
         if (j0 + R < nt)
             consumer_sync(); // the scratch area is reused by the next round
     }
+    ds_stamp(cx, 3);
     ds_grid_arrive(cx);
 }
 
@@ -567,7 +795,7 @@ struct DsMmha
     __half* ctx_frag;
 };
 
-__device__ __noinline__ void ds_mmha_phase(const DsMmha& a, const DsModel& m, DsCtx& cx)
+__device__ __forceinline__ void ds_mmha_phase(const DsMmha& a, const DsModel& m, DsCtx& cx)
 {
     constexpr int NIT = 4;
     const int lane = cx.lane, warp = cx.warp;
@@ -588,22 +816,17 @@ __device__ __noinline__ void ds_mmha_phase(const DsMmha& a, const DsModel& m, Ds
 
     int tlen = 0;
     float s_qo = 1.f, s_oq = 1.f;
-    __half2 kw[NIT][8], vw[NIT][8];
+    // raw cache bytes of one pass (16 dims of NIT keys per lane for K and for V); converted to fp16 at the point of use:
+    // keeping the converted values live across the barrier spilled registers, and a spill is an L2 round trip here
+    KvChunk<true> kreg[NIT], vreg[NIT];
     auto fetch = [&](int pass)
     {
-        KvChunk<true> kreg[NIT], vreg[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it)
         {
             const int key = min((wi + nw * (NIT * pass + it)) * 8 + kl, m.Smax - 1);
             kreg[it].load(kc, (size_t) key * kDh + chunk * 16);
             vreg[it].load(vc, (size_t) key * kDh + chunk * 16);
-        }
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-        {
-            kreg[it].unpack(kw[it]);
-            vreg[it].unpack(vw[it]);
         }
     };
     if (active)
@@ -618,6 +841,7 @@ __device__ __noinline__ void ds_mmha_phase(const DsMmha& a, const DsModel& m, Ds
     ds_grid_wait(cx);
 
     float m_run = -FLT_MAX, l_run = 0.f, s_cur = -FLT_MAX;
+    __half2 vcur_h = __float2half2_rn(0.f); // the finalising warp's two dims of this step's v
     float o[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i)
@@ -635,6 +859,7 @@ __device__ __noinline__ void ds_mmha_phase(const DsMmha& a, const DsModel& m, Ds
         }
         if (wi == 0)
         {
+            vcur_h = __ldcg(reinterpret_cast<const __half2*>(a.qkv + (size_t) b * 3 * hidden + 2 * hidden + h * kDh + 2 * lane));
             const uint4 k0 = ldcg_u4(qp + hidden), k1 = ldcg_u4(qp + hidden + 8);
             const uint4 v0 = ldcg_u4(qp + 2 * hidden), v1 = ldcg_u4(qp + 2 * hidden + 8);
             *reinterpret_cast<uint4*>(&kh[0]) = k0;
@@ -675,14 +900,16 @@ __device__ __noinline__ void ds_mmha_phase(const DsMmha& a, const DsModel& m, Ds
                 const int kg = (wi + nw * (NIT * pass + it)) * 8;
                 if (kg < tlen)
                 {
-                    __half2 h0 = __hmul2(q2[0], kw[it][0]);
-                    __half2 h1 = __hmul2(q2[4], kw[it][4]);
-                    h0 = __hfma2(q2[1], kw[it][1], h0);
-                    h1 = __hfma2(q2[5], kw[it][5], h1);
-                    h0 = __hfma2(q2[2], kw[it][2], h0);
-                    h1 = __hfma2(q2[6], kw[it][6], h1);
-                    h0 = __hfma2(q2[3], kw[it][3], h0);
-                    h1 = __hfma2(q2[7], kw[it][7], h1);
+                    __half2 kw[8];
+                    kreg[it].unpack(kw);
+                    __half2 h0 = __hmul2(q2[0], kw[0]);
+                    __half2 h1 = __hmul2(q2[4], kw[4]);
+                    h0 = __hfma2(q2[1], kw[1], h0);
+                    h1 = __hfma2(q2[5], kw[5], h1);
+                    h0 = __hfma2(q2[2], kw[2], h0);
+                    h1 = __hfma2(q2[6], kw[6], h1);
+                    h0 = __hfma2(q2[3], kw[3], h0);
+                    h1 = __hfma2(q2[7], kw[7], h1);
                     const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
                     float sv = (f0.x + f0.y) + (f1.x + f1.y);
                     sv += __shfl_xor_sync(0xffffffffu, sv, 1);
@@ -713,9 +940,11 @@ __device__ __noinline__ void ds_mmha_phase(const DsMmha& a, const DsModel& m, Ds
                 const float e = __expf(sc[it] - m_new);
                 l_run += e;
                 const __half2 p2 = __float2half2_rn(e);
+                __half2 vw[8];
+                vreg[it].unpack(vw);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    o2[i] = __hfma2(p2, vw[it][i], o2[i]);
+                    o2[i] = __hfma2(p2, vw[i], o2[i]);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -773,8 +1002,7 @@ __device__ __noinline__ void ds_mmha_phase(const DsMmha& a, const DsModel& m, Ds
             a1 += wt * ov.y;
         }
         const float inv_sum = __fdividef(1.f, gl + 1.e-6f); // Template.h:1756
-        const float2 vcur = __half22float2(__ldcg(reinterpret_cast<const __half2*>(
-            a.qkv + (size_t) b * 3 * hidden + 2 * hidden + h * kDh + 2 * lane)));
+        const float2 vcur = __half22float2(vcur_h);
         const __half2 o2 = __floats2half2_rn((a0 * s_qo + e_cur * vcur.x) * inv_sum, (a1 * s_qo + e_cur * vcur.y) * inv_sum);
         *reinterpret_cast<__half2*>(a.ctx_frag + frag_index(b, h * kDh + 2 * lane)) = o2;
     }
@@ -789,7 +1017,7 @@ struct DsXattn
     __half* ctx_frag;
 };
 
-__device__ __noinline__ void ds_xattn_phase(const DsXattn& a, const DsModel& m, DsCtx& cx)
+__device__ __forceinline__ void ds_xattn_phase(const DsXattn& a, const DsModel& m, DsCtx& cx)
 {
     constexpr int NIT = kDsChunkKeys / 8;
     const int lane = cx.lane, warp = cx.warp;
@@ -919,12 +1147,14 @@ struct DsParams
     const __half* pos_emb;
     __half* x_out;
     unsigned* sync;
+    long long* dbg;
     __half* x;   // A-fragment order [16 x d]
     __half* ctx; // A-fragment order [16 x d]
     __half* u;   // A-fragment order [16 x dff]
     __half* qkv; // row-major [16][3d]
     __half* q;   // row-major [16][d]
     int vocab, n_ctx;
+    int l2_ahead; // items the L2 prefetch lane runs ahead of the ring producer (0: off)
     float eps;
 };
 
@@ -937,8 +1167,10 @@ __global__ void __launch_bounds__(kDsThreads, 1) decoder_step_kernel(const DsPar
     cx.sm.stats = cx.sm.scratch + kDsScratchFloats;
     cx.sm.full = reinterpret_cast<uint64_t*>(cx.sm.stats + kDsStatFloats);
     cx.sm.empty = cx.sm.full + kDsSlots;
-    cx.sm.dead = reinterpret_cast<volatile int*>(cx.sm.empty + kDsSlots);
+    cx.sm.dead = smem_u32(cx.sm.empty + kDsSlots);
+    cx.sm.progress = cx.sm.dead + 4;
     cx.sync = p.sync;
+    cx.dbg = p.dbg;
     cx.phase = 0;
     cx.item = 0;
     cx.c = blockIdx.x;
@@ -955,22 +1187,29 @@ __global__ void __launch_bounds__(kDsThreads, 1) decoder_step_kernel(const DsPar
             mbar_init(&cx.sm.full[s], 1);
             mbar_init(&cx.sm.empty[s], 1);
         }
-        *cx.sm.dead = 0;
+        reinterpret_cast<volatile int*>(cx.sm.empty + kDsSlots)[0] = 0;
+        reinterpret_cast<volatile int*>(cx.sm.empty + kDsSlots)[1] = 0;
         fence_mbar_init();
         fence_proxy_async_smem();
     }
     __syncthreads();
 
-    if (cx.warp == kDsCW)
+    if (cx.warp >= kDsCW)
     {
-        // ---- producer warp: weights and the cross-KV cache are static data, no dependency on the previous kernel ----
-        if (cx.lane == 0)
-            ds_producer(m, cx);
+        // ---- producer warps: weights and the cross-KV cache are static data, no dependency on the previous kernel ----
+        // (an L2 prefetch lane running 12-48 items ahead of the ring producer was measured: 1-10 % slower, the
+        // prefetched lines compete with the ring's own fills; ds_producer<true> is kept for experiments only)
+        if (cx.lane == 0 && cx.warp == kDsCW)
+            ds_producer<false>(m, cx, 0u);
         return;
     }
 
     // ---- consumers ----
     grid_dep_wait(); // tokens / lengths / the previous step's cache rows come from earlier kernels on the stream
+#if defined(B200_DS_DEBUG)
+    if (cx.dbg != nullptr && cx.tid == 0)
+        cx.dbg[(size_t) cx.c * kDsDbgPhases * 2] = ds_globaltimer();
+#endif
     {
         // token + positional embedding -> x (A-fragment order); fp16 add like embed_kernel (glue.cu)
         const int nkb = m.d >> 6;
@@ -991,60 +1230,58 @@ __global__ void __launch_bounds__(kDsThreads, 1) decoder_step_kernel(const DsPar
         }
         ds_grid_arrive(cx);
     }
+    // One call site per phase function (all inlined: no stack frame, no parameter structs in local memory -- the
+    // acquire loads of the grid barrier invalidate L1, which would turn every spilled field into an L2 round trip on
+    // the critical path).  The layer's 32 pointers are staged in shared memory one layer ahead.
+    unsigned long long* ltab = reinterpret_cast<unsigned long long*>(cx.sm.stats + kDsStatFloats) + 2 * kDsSlots + 8;
+    if (cx.tid < 32)
+        ltab[cx.tid] = __ldg(reinterpret_cast<const unsigned long long*>(m.layers) + cx.tid);
+    consumer_sync();
+#pragma unroll 1
     for (int l = 0; l < m.L; ++l)
     {
-        const b200_decoder_layer& ly = m.layers[l];
+        const unsigned long long* lp = ltab + (l & 1) * 32;
         const bool last = l + 1 == m.L;
+        if (!last && cx.tid < 32) // next layer's pointers (consumed after several more consumer_sync()s)
+            ltab[((l + 1) & 1) * 32 + cx.tid] = __ldg(reinterpret_cast<const unsigned long long*>(m.layers + l + 1) + cx.tid);
+#pragma unroll 1
+        for (int sidx = 0; sidx < 8; ++sidx)
         {
-            DsGemm a{};
-            a.W = ly.qkv_w, a.scales = static_cast<const __half*>(ly.qkv_scales), a.bias = static_cast<const __half*>(ly.qkv_bias);
-            a.gamma = static_cast<const __half*>(ly.attn_ln_gamma), a.c1s = ly.qkv_c1s, a.c2 = ly.qkv_c2;
-            a.A = p.x, a.out_rm = p.qkv, a.K = m.d, a.N = 3 * m.d, a.act = B200_ACT_NONE, a.which = 0, a.eps = p.eps;
-            ds_gemm_phase(a, m, cx);
-        }
-        {
-            DsMmha a{p.qkv, static_cast<int8_t*>(ly.self_kv), ly.kv_scale_orig_quant, ly.kv_scale_quant_orig, p.seq_len, p.ctx};
-            ds_mmha_phase(a, m, cx);
-        }
-        {
-            DsGemm a{};
-            a.W = ly.attn_out_w, a.scales = static_cast<const __half*>(ly.attn_out_scales);
-            a.bias = static_cast<const __half*>(ly.attn_out_bias);
-            a.A = p.ctx, a.resid = p.x, a.out_frag = p.x, a.K = m.d, a.N = m.d, a.act = B200_ACT_NONE, a.which = 1, a.eps = p.eps;
-            ds_gemm_phase(a, m, cx);
-        }
-        {
-            DsGemm a{};
-            a.W = ly.cross_q_w, a.scales = static_cast<const __half*>(ly.cross_q_scales);
-            a.bias = static_cast<const __half*>(ly.cross_q_bias);
-            a.gamma = static_cast<const __half*>(ly.cross_ln_gamma), a.c1s = ly.cross_q_c1s, a.c2 = ly.cross_q_c2;
-            a.A = p.x, a.out_rm = p.q, a.K = m.d, a.N = m.d, a.act = B200_ACT_NONE, a.which = 2, a.eps = p.eps;
-            ds_gemm_phase(a, m, cx);
-        }
-        {
-            DsXattn a{p.q, ly.cross_kv_scale_quant_orig, p.ctx};
-            ds_xattn_phase(a, m, cx);
-        }
-        {
-            DsGemm a{};
-            a.W = ly.cross_out_w, a.scales = static_cast<const __half*>(ly.cross_out_scales);
-            a.bias = static_cast<const __half*>(ly.cross_out_bias);
-            a.A = p.ctx, a.resid = p.x, a.out_frag = p.x, a.K = m.d, a.N = m.d, a.act = B200_ACT_NONE, a.which = 3, a.eps = p.eps;
-            ds_gemm_phase(a, m, cx);
-        }
-        {
-            DsGemm a{};
-            a.W = ly.fc1_w, a.scales = static_cast<const __half*>(ly.fc1_scales), a.bias = static_cast<const __half*>(ly.fc1_bias);
-            a.gamma = static_cast<const __half*>(ly.mlp_ln_gamma), a.c1s = ly.fc1_c1s, a.c2 = ly.fc1_c2;
-            a.A = p.x, a.out_frag = p.u, a.K = m.d, a.N = m.dff, a.act = B200_ACT_GELU_ERF, a.which = 4, a.eps = p.eps;
-            ds_gemm_phase(a, m, cx);
-        }
-        {
-            DsGemm a{};
-            a.W = ly.fc2_w, a.scales = static_cast<const __half*>(ly.fc2_scales), a.bias = static_cast<const __half*>(ly.fc2_bias);
-            a.A = p.u, a.resid = p.x, a.out_frag = p.x, a.out_rm = last ? p.x_out : nullptr;
-            a.K = m.dff, a.N = m.d, a.act = B200_ACT_NONE, a.which = 5, a.eps = p.eps;
-            ds_gemm_phase(a, m, cx);
+            if (sidx == 1)
+            {
+                DsMmha a{p.qkv, reinterpret_cast<int8_t*>(lp[27]), reinterpret_cast<const float*>(lp[28]),
+                    reinterpret_cast<const float*>(lp[29]), p.seq_len, p.ctx};
+                ds_mmha_phase(a, m, cx);
+            }
+            else if (sidx == 4)
+            {
+                DsXattn a{p.q, reinterpret_cast<const float*>(lp[31]), p.ctx};
+                ds_xattn_phase(a, m, cx);
+            }
+            else
+            {
+                // matmul g: 0 qkv, 1 attn_out, 2 cross_q, 3 cross_out, 4 fc1, 5 fc2; even g carry a folded LayerNorm
+                const int g = sidx == 0 ? 0 : (sidx < 4 ? sidx - 1 : sidx - 2);
+                const bool fold = (g & 1) == 0;
+                const int wb = 9 * (g >> 1) + (fold ? 1 : 6); // index of the weight pointer in b200_decoder_layer
+                DsGemm a;
+                a.gamma = fold ? reinterpret_cast<const __half*>(lp[wb - 1]) : nullptr;
+                a.W = reinterpret_cast<const int8_t*>(lp[wb]);
+                a.scales = reinterpret_cast<const __half*>(lp[wb + 1]);
+                a.bias = reinterpret_cast<const __half*>(lp[wb + 2]);
+                a.c1s = fold ? reinterpret_cast<const float*>(lp[wb + 3]) : nullptr;
+                a.c2 = fold ? reinterpret_cast<const float*>(lp[wb + 4]) : nullptr;
+                a.K = g == 5 ? m.dff : m.d;
+                a.N = g == 0 ? 3 * m.d : (g == 4 ? m.dff : m.d);
+                a.A = (g == 1 || g == 3) ? p.ctx : (g == 5 ? p.u : p.x);
+                a.resid = (g & 1) ? p.x : nullptr;
+                a.out_frag = (g & 1) ? p.x : (g == 4 ? p.u : nullptr);
+                a.out_rm = g == 0 ? p.qkv : (g == 2 ? p.q : ((g == 5 && last) ? p.x_out : nullptr));
+                a.act = g == 4 ? B200_ACT_GELU_ERF : B200_ACT_NONE;
+                a.which = g;
+                a.eps = p.eps;
+                ds_gemm_phase(a, m, cx);
+            }
         }
     }
     // ---- leave the barrier words zero for the next launch: the last CTA out resets them ----
@@ -1064,6 +1301,16 @@ __global__ void __launch_bounds__(kDsThreads, 1) decoder_step_kernel(const DsPar
 } // namespace b200
 
 using namespace b200;
+
+static void* g_ds_debug = nullptr;
+
+/* Debug aid: device buffer of n_ctas * 512 * 2 int64 receiving %globaltimer stamps of every following step launch
+ * (per CTA and phase: [0] grid wait returned, [1] phase work done); NULL switches it off. */
+extern "C" int b200_debug_decoder_step_timeline(void* device_buffer)
+{
+    g_ds_debug = device_buffer;
+    return B200_OK;
+}
 
 extern "C" size_t b200_decoder_step_scratch_bytes(int num_heads, int d_ff)
 {
@@ -1118,6 +1365,8 @@ extern "C" int b200_decoder_step(const b200_decoder_step_params* p, b200_stream_
     k.qkv = reinterpret_cast<__half*>(s), s += 96 * (size_t) d;
     k.q = reinterpret_cast<__half*>(s);
     k.vocab = p->vocab, k.n_ctx = p->n_ctx, k.eps = p->ln_eps;
+    k.dbg = static_cast<long long*>(g_ds_debug);
+    k.l2_ahead = 0;
     B200_LAUNCH(decoder_step_kernel, dim3(G), dim3(kDsThreads), kDsSmemBytes, as_stream(stream), k);
     return B200_OK;
 }

@@ -376,6 +376,9 @@ size_t b200_decoder_step_scratch_bytes(int num_heads, int d_ff);
 int b200_decoder_step(const b200_decoder_step_params* params, b200_stream_t stream);
 /* Debug: error word of the last steps run on this scratch (0 = no barrier / ring wait timed out); synchronises. */
 int b200_decoder_step_status(const void* scratch, int32_t* status_host);
+/* Debug aid: device buffer of n_ctas * 512 * 2 int64 that receives %globaltimer stamps of every following step launch
+ * (per CTA and phase: [0] grid barrier passed, [1] phase work done); NULL switches it off (tools/step_phases.py). */
+int b200_debug_decoder_step_timeline(void* device_buffer);
 
 #ifdef __cplusplus
 }
