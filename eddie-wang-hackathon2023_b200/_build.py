@@ -34,6 +34,11 @@ if TC_DEBUG:
     COMMON = COMMON + ["-DB200_TC_DEBUG=1"]
 if DS_DEBUG:
     COMMON = COMMON + ["-DB200_DS_DEBUG=1"]
+# experiment switches (bisecting): B200_EXTRA_DEFS="-DX -DY"
+EXTRA_DEFS = os.environ.get("B200_EXTRA_DEFS", "").split()
+if EXTRA_DEFS:
+    COMMON = COMMON + EXTRA_DEFS
+    DEBUG_STAMPS = True
 
 
 def _sources():
@@ -63,7 +68,7 @@ def _headers_stamp():
 
 def _compile(src, stamp, verbose):
     rel = os.path.relpath(src, PKG).replace(os.sep, "_")
-    obj = os.path.join(OBJDIR, f"{rel}.{stamp}{'.tcdbg' if TC_DEBUG else ''}{'.dsdbg' if DS_DEBUG else ''}.o")
+    obj = os.path.join(OBJDIR, f"{rel}.{stamp}{'.tcdbg' if TC_DEBUG else ''}{'.dsdbg' if DS_DEBUG else ''}{('.' + hashlib.sha256(' '.join(EXTRA_DEFS).encode()).hexdigest()[:8]) if EXTRA_DEFS else ''}.o")
     if os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(src):
         return obj
     cmd = [NVCC] + ARCH + COMMON + (["-x", "cu"] if src.endswith(".cpp") else []) + ["-c", src, "-o", obj]
@@ -87,7 +92,7 @@ def build(verbose=False, force=False):
         objs = list(ex.map(lambda s: _compile(s, stamp, verbose), srcs))
     out = os.path.join(LIBDIR, LIBNAME)
     flavour = os.path.join(LIBDIR, ".flavour")
-    want = ("tc-debug " if TC_DEBUG else "") + ("ds-debug" if DS_DEBUG else "") if DEBUG_STAMPS else "release"
+    want = ("tc-debug " if TC_DEBUG else "") + ("ds-debug " if DS_DEBUG else "") + " ".join(EXTRA_DEFS) if DEBUG_STAMPS else "release"
     have = open(flavour).read().strip() if os.path.exists(flavour) else ""
     if (not os.path.exists(out)) or have != want or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-Xlinker", "--version-script=" + os.path.join(PKG, "exports.map")]

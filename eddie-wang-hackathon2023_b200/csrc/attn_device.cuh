@@ -161,11 +161,30 @@ __device__ __forceinline__ void xa_load16(const uint8_t* p, __half2 (&w)[8])
     }
 }
 
+// 16 offset-binary cache bytes -> 8 half2 holding 1024 + byte (PRMT only, no bias subtraction): for the score MMA the
+// constant 1152 = 1024 + 128 per element is removed once per (row, head) as 1152 * sum(q) instead of once per element
+__device__ __forceinline__ void xa_load16_biased(const uint8_t* p, __half2 (&w)[8])
+{
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const uint32_t l = __byte_perm(u[i], 0x64646464u, 0x5250);
+        const uint32_t h = __byte_perm(u[i], 0x64646464u, 0x5351);
+        w[2 * i] = *reinterpret_cast<const __half2*>(&l);
+        w[2 * i + 1] = *reinterpret_cast<const __half2*>(&h);
+    }
+}
+
 // one chunk of keys: scores on the tensor cores (mma.sync m16n8k16, the 16 keys of two warp iterations are the
 // rows of A, q is column 0 of B), online softmax, then p.v on the fp16 pipe.  FULL: no key of the chunk is masked.
-template <bool INT8, int NIT, bool FULL>
+// KOFF (int8 cache only): the keys enter the MMA as 1024 + byte and `koff` = 1152 * sum_d q[d] is subtracted from the
+// fp32 score (exact products, fp32 accumulation: the cancellation costs ~1e-6 relative) -- 8 fewer instructions per lane
+// and 8 keys in a loop that is issue-bound.  The running state is only rescaled when the maximum moved.
+template <bool INT8, int NIT, bool FULL, bool KOFF = false>
 __device__ __forceinline__ void xa_chunk(const uint8_t* kst, const uint8_t* vst, int nk, int kl, int lane, float sscale,
-    const uint32_t (&bq)[8], float& m_run, float& l_run, float (&o)[16])
+    const uint32_t (&bq)[8], float& m_run, float& l_run, float (&o)[16], float koff = 0.f)
 {
     constexpr int ESZ = INT8 ? 1 : 2;
     float sc[NIT];
@@ -174,16 +193,33 @@ __device__ __forceinline__ void xa_chunk(const uint8_t* kst, const uint8_t* vst,
     for (int it = 0; it < NIT; it += 2)
     {
         __half2 w0[8], w1[8];
-        xa_load16<INT8>(kst + (size_t) it * 8 * kDh * ESZ, w0);
-        xa_load16<INT8>(kst + (size_t) (it + 1) * 8 * kDh * ESZ, w1);
+        if constexpr (KOFF && INT8)
+        {
+            xa_load16_biased(kst + (size_t) it * 8 * kDh, w0);
+            xa_load16_biased(kst + (size_t) (it + 1) * 8 * kDh, w1);
+        }
+        else
+        {
+            xa_load16<INT8>(kst + (size_t) it * 8 * kDh * ESZ, w0);
+            xa_load16<INT8>(kst + (size_t) (it + 1) * 8 * kDh * ESZ, w1);
+        }
         float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             mma_m16n8k16(c0, c1, c2, c3, h2u(w0[2 * j]), h2u(w1[2 * j]), h2u(w0[2 * j + 1]), h2u(w1[2 * j + 1]),
                 bq[2 * j], bq[2 * j + 1]);
         // column 0 of D lives in the lanes with chunk == 0: c0 = key it*8+kl, c2 = key (it+1)*8+kl
-        float s0 = __shfl_sync(0xffffffffu, c0, lane & ~3) * sscale;
-        float s1 = __shfl_sync(0xffffffffu, c2, lane & ~3) * sscale;
+        float s0 = __shfl_sync(0xffffffffu, c0, lane & ~3), s1 = __shfl_sync(0xffffffffu, c2, lane & ~3);
+        if constexpr (KOFF && INT8)
+        {
+            s0 = (s0 - koff) * sscale;
+            s1 = (s1 - koff) * sscale;
+        }
+        else
+        {
+            s0 *= sscale;
+            s1 *= sscale;
+        }
         if (!FULL)
         {
             s0 = (it * 8 + kl < nk) ? s0 : -FLT_MAX;
@@ -197,12 +233,15 @@ __device__ __forceinline__ void xa_chunk(const uint8_t* kst, const uint8_t* vst,
     m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 8));
     m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, 16));
     // online softmax in the log2 domain: rescale the running state to the new maximum
-    const float corr = fast_exp2(m_run - m_new); // 0 on the first chunk (m_run = -FLT_MAX)
-    m_run = m_new;
-    l_run *= corr;
+    if (m_new != m_run) // warp-uniform (m_new was reduced over the warp; every lane carries the same m_run)
+    {
+        const float corr = fast_exp2(m_run - m_new); // 0 on the first chunk (m_run = -FLT_MAX)
+        m_run = m_new;
+        l_run *= corr;
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        o[i] *= corr;
+        for (int i = 0; i < 16; ++i)
+            o[i] *= corr;
+    }
 #pragma unroll
     for (int it = 0; it < NIT; ++it)
     {

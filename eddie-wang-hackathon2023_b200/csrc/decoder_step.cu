@@ -529,21 +529,8 @@ __device__ __forceinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m,
     // epilogue item of this thread in a round: (tile jj, row, column pair cp)
     const int e_jj = tid >> 6, e_row = (tid & 63) >> 2, e_cp = tid & 3;
     float e_sc[2] = {0.f, 0.f}, e_bias[2] = {0.f, 0.f}, e_c1[2] = {0.f, 0.f}, e_c2[2] = {0.f, 0.f}, e_res[2] = {0.f, 0.f};
-    // The per-column vectors are static data in HBM: their lines are pulled into L2 before the grid barrier (a DRAM
-    // round trip hidden behind the wait) and the values are loaded right after the MMAs were issued, under the reduction
-    // -- holding ten more registers across the MMAs would spill.
-    auto prefetch_epi_static = [&](int j0)
-    {
-        if (e_jj < min(R, nt - j0) && e_cp == 0 && e_row < 4)
-        {
-            const int n0 = 8 * (first + (j0 + e_jj) * cx.G);
-            const void* ptr = e_row == 0 ? (const void*) (a.scales + n0)
-                : e_row == 1             ? (const void*) (a.bias != nullptr ? a.bias + n0 : a.scales + n0)
-                : e_row == 2             ? (const void*) (fold ? (const void*) (a.c1s + n0) : (const void*) (a.scales + n0))
-                                         : (const void*) (fold ? (const void*) (a.c2 + n0) : (const void*) (a.scales + n0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-        }
-    };
+    // The per-column vectors are static data in HBM: requested before the grid barrier (a DRAM round trip hidden behind
+    // the wait).
     auto load_epi_static = [&](int j0)
     {
         if (e_jj < min(R, nt - j0))
@@ -570,7 +557,7 @@ __device__ __forceinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m,
             }
         }
     };
-    prefetch_epi_static(0);
+    load_epi_static(0);
     uint4 glo[2], ghi[2]; // gamma pairs of this thread's B fragments: lo = k 16t+2w.., hi = +8, per k-block
     glo[0] = glo[1] = ghi[0] = ghi[1] = make_uint4(0u, 0u, 0u, 0u);
     if (fold)
@@ -719,7 +706,8 @@ __device__ __forceinline__ void ds_gemm_phase(const DsGemm& a, const DsModel& m,
             ds_stamp(cx, 5);
         }
         ds_stamp(cx, 1);
-        load_epi_static(j0); // L2 hits (prefetched before the barrier); in flight under the reduction
+        if (j0 > 0)
+            load_epi_static(j0); // later rounds (small grids only): in flight under the reduction
         consumer_sync();
         ds_stamp(cx, 2);
         if (tid == 0)
@@ -1029,6 +1017,10 @@ __device__ __forceinline__ void ds_xattn_phase(const DsXattn& a, const DsModel& 
     const float sscale = s_qo * 0.125f * 1.4426950408889634f;
 
     ds_grid_wait(cx);
+#if defined(B200_DS_DEBUG)
+    long long dbg_wait = 0, dbg_chunks = 0;
+    const long long dbg_t0 = clock64();
+#endif
 
     uint4 qn0 = make_uint4(0, 0, 0, 0), qn1 = qn0;
     if (nbh > 0)
@@ -1043,14 +1035,21 @@ __device__ __forceinline__ void ds_xattn_phase(const DsXattn& a, const DsModel& 
         const int p = cx.c + r * cx.G;
         const int b = p / m.H, h = p - b * m.H;
         uint32_t bq[8];
+        float koff; // 1152 * sum of q over the 64 dims: the bias of the 1024 + byte key values (xa_chunk KOFF)
         {
             const uint32_t u[8] = {qn0.x, qn0.y, qn0.z, qn0.w, qn1.x, qn1.y, qn1.z, qn1.w}; // u[j] = (d2j, d2j+1)
+            float qs = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
                 bq[2 * j] = kl == 0 ? __byte_perm(u[2 * j], u[2 * j + 1], 0x5410) : 0u;
                 bq[2 * j + 1] = kl == 0 ? __byte_perm(u[2 * j], u[2 * j + 1], 0x7632) : 0u;
+                const float2 f0 = __half22float2(ds_u2h2(u[2 * j])), f1 = __half22float2(ds_u2h2(u[2 * j + 1]));
+                qs += (f0.x + f0.y) + (f1.x + f1.y);
             }
+            qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+            qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+            koff = 1152.f * qs;
         }
         if (r + 1 < nbh)
         {
@@ -1073,13 +1072,23 @@ __device__ __forceinline__ void ds_xattn_phase(const DsXattn& a, const DsModel& 
             const unsigned it = cx.item + i;
             const unsigned s = it % kDsSlots;
             const int nk = min(kDsChunkKeys, m.S - ch * kDsChunkKeys);
+#if defined(B200_DS_DEBUG)
+            const long long tw0 = clock64();
+#endif
             ds_mbar_wait(cx, &cx.sm.full[s], (it / kDsSlots) & 1, DS_ERR_RING_FULL_WAIT);
+#if defined(B200_DS_DEBUG)
+            dbg_wait += clock64() - tw0;
+            ++dbg_chunks;
+#endif
             const uint8_t* kst = cx.sm.ring + (size_t) s * kDsSlotBytes + (size_t) (kl * kDh + chunk * 16);
             const uint8_t* vst = kst + kDsSlotBytes / 2;
+            // (Splitting the 80-key chunk into 48 + 32 keys -- two online-softmax updates per slot, 6 instead of 10 score
+            // registers -- removed the spills of this loop but produced wrong sums for full chunks on the B200; the cause
+            // was not found in the time available, so the chunk stays one 10-iteration update.)
             if (nk == kDsChunkKeys)
-                xa_chunk<true, NIT, true>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o);
+                xa_chunk<true, NIT, true, true>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o, koff);
             else
-                xa_chunk<true, NIT, false>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o);
+                xa_chunk<true, NIT, false, true>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o, koff);
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&cx.sm.empty[s]);
@@ -1135,6 +1144,13 @@ __device__ __forceinline__ void ds_xattn_phase(const DsXattn& a, const DsModel& 
         }
     }
     cx.item += (unsigned) (nbh * m.nch);
+#if defined(B200_DS_DEBUG)
+    if (cx.dbg != nullptr && cx.c == 30 && cx.tid == 0 && cx.phase < kDsDbgPhases)
+    {
+        long long* f = cx.dbg + (size_t) cx.G * kDsDbgPhases * 2 + (size_t) cx.phase * 16;
+        f[10] = dbg_wait, f[11] = dbg_chunks, f[12] = clock64() - dbg_t0;
+    }
+#endif
     ds_grid_arrive(cx);
 }
 

@@ -43,9 +43,20 @@ def _mel(batch, dims, seed):
     return torch.randn(batch, dims.n_mels, 2 * dims.n_audio_ctx).clamp(-1, 1).half().float()
 
 
+@pytest.fixture(scope="module")
+def oracle_run():
+    """GPU encoder output + the oracle's decode of it, shared by both decoder paths (about 3 minutes of host CPU)."""
+    return _oracle_run()
+
+
 @pytest.mark.timeout(1800)
-def test_large_v2_batch16_greedy_tokens_against_oracle():
-    from b200_whisper.runtime import WhisperDecoding, WhisperEncoder
+@pytest.mark.parametrize("step_kernel", [False, True], ids=["operator-chain", "persistent-step-kernel"])
+def test_large_v2_batch16_greedy_tokens_against_oracle(oracle_run, step_kernel):
+    _check(oracle_run, step_kernel)
+
+
+def _oracle_run():
+    from b200_whisper.runtime import WhisperEncoder
     torch.set_num_threads(os.cpu_count() or 1)
     dims = wo.LARGE_V2
     t0 = time.perf_counter()
@@ -79,8 +90,20 @@ def test_large_v2_batch16_greedy_tokens_against_oracle():
     strong = margins >= MARGIN
     t_oracle = time.perf_counter() - t0 - t_enc
 
+    print(f"\n[gate3] oracle: encoder+quantize {t_enc:.0f}s, decode {t_oracle:.0f}s; events with margin < {MARGIN}: "
+          f"{(~strong).sum().item()} of {strong.numel()}; min margin {margins.min().item():.4f}")
+    return dict(dims=dims, sd=sd, xa=xa, kv_s=kv_s, ckv_s=ckv_s, ref_tokens=ref_tokens, ref_logits=ref_logits, margins=margins,
+                strong=strong)
+
+
+def _check(o, step_kernel):
+    from b200_whisper.runtime import WhisperDecoding
+    dims, sd, xa, kv_s, ckv_s = o["dims"], o["sd"], o["xa"], o["kv_s"], o["ckv_s"]
+    ref_tokens, ref_logits, margins, strong = o["ref_tokens"], o["ref_logits"], o["margins"], o["strong"]
     # ---- GPU decoder -------------------------------------------------------------------------------------------
     dec = WhisperDecoding(dims, sd, B, kv_s, ckv_s)
+    assert dec.step_kernel_available
+    dec.step_kernel = step_kernel
     dec.set_encoder_output(xa)
     # (B) free running, CUDA graph
     got = dec.decode([PROMPT] * B, N_NEW).cpu().long()
@@ -94,9 +117,10 @@ def test_large_v2_batch16_greedy_tokens_against_oracle():
         tf_err.append((dec.logits.cpu() - ref_logits[:, t]).abs().max().item())
     tf_tokens = torch.stack(tf_tokens, 1).cpu().long()
     scale = ref_logits.abs().max().item()
-    print(f"\n[gate3] oracle: encoder+quantize {t_enc:.0f}s, decode {t_oracle:.0f}s; logit scale {scale:.2f}; "
-          f"teacher-forced max |dlogit| {max(tf_err):.4f}; events with margin < {MARGIN}: {(~strong).sum().item()} of "
-          f"{strong.numel()}; min margin {margins.min().item():.4f}")
+    print(f"\n[gate3 {'step kernel' if step_kernel else 'operator chain'}] logit scale {scale:.2f}; teacher-forced max "
+          f"|dlogit| {max(tf_err):.4f}")
+    if step_kernel:
+        assert dec.step_kernel_status() == 0
 
     # (A) every step's logits within tolerance; arg-max identical wherever the oracle is not at a near-tie
     assert max(tf_err) <= 1e-2 * scale, f"teacher-forced logits err {max(tf_err)} vs scale {scale}"
@@ -120,5 +144,6 @@ def test_large_v2_batch16_greedy_tokens_against_oracle():
     print(f"[gate3] free-running matched prefix per row: {prefix}; rows identical for all {N_NEW} tokens: {full}/{B}; "
           f"teacher-forced flips on near-ties: {weak_flips}")
     # floors (seed 0, recorded from the B200 run): most rows run the full length, none diverges early
-    assert full >= B // 2, f"only {full} of {B} rows reproduce all {N_NEW} oracle tokens"
-    assert sum(prefix) >= int(0.75 * B * N_NEW)
+    # (recorded on B200 with the persistent step kernel: 16 / 16 rows identical for all 64 tokens, 0 flips)
+    assert full >= 12, f"only {full} of {B} rows reproduce all {N_NEW} oracle tokens"
+    assert sum(prefix) >= int(0.9 * B * N_NEW)

@@ -88,3 +88,6 @@ print("CTA 0 barrier path (SM cycles; mean over the matmul -> matmul barriers): 
 v = np.array([[fine[p][9] - fine[p][8], fine[p + 1][7] - fine[p][9], fine[p + 1][0] - fine[p + 1][7]]
               for p in range(1, nph - 1) if (p % 8) not in (2, 5) and ((p + 1) % 8) not in (2, 5)], dtype=np.float64)
 print("  ", " ".join(f"{x:8.0f}" for x in v.mean(0)))
+v = np.array([[fine[5 + 8 * l][k] for k in (10, 11, 12)] for l in range(L)], dtype=np.float64).mean(0)
+print(f"CTA 30 (2 pairs), warp 0 in the cross-attention phase: {v[1]:.1f} chunks, {v[0]:.0f} cycles waiting for ring data, "
+      f"{v[2]:.0f} cycles in the phase -> {(v[2] - v[0]) / max(v[1], 1):.0f} cycles of work per chunk")
