@@ -242,13 +242,44 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def time_decoder(dims, sd, batch, dev, steps, warmup, seed):
+    """Device-resident CUDA-graph steps of a decoder with `batch` utterances: returns ms per step (CUDA events)."""
+    import torch
+    from b200_whisper.runtime import WhisperDecoding
+    L = dims.n_text_layer
+    dec = WhisperDecoding(dims, sd, batch, kv_scales=[0.05] * L, cross_kv_scales=[0.03] * L, device=dev)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    dec.set_cross_kv([torch.randint(-127, 128, (batch, 2, dims.n_text_head, dims.n_audio_ctx, 64), generator=g, device=dev,
+                                    dtype=torch.int8) for _ in range(L)])
+    dec.reset()
+    dec.prefill([PROMPT] * batch)
+    dec.capture()
+    for _ in range(max(warmup, 3)):
+        dec.step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        dec.step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    del dec
+    torch.cuda.empty_cache()
+    return ms
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=BATCH, help="utterances per GPU (weak scaling; the headline is 16)")
+    ap.add_argument("--total-batch", type=int, default=0,
+                    help="BASELINE.json configs[3]: this many utterances sharded over the GPUs (strong scaling); "
+                         "per-GPU batch = total / world.  The default run reports this at 64 as the `strong_scaling` key.")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 and strong-scaling extra measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer decoder layers (result is INVALID)")
@@ -280,11 +311,14 @@ def main():
     if args.layers:
         dims.n_text_layer = args.layers
     B = args.batch
+    strong = args.total_batch > 0
+    if strong:
+        assert args.total_batch % world == 0, "--total-batch must be divisible by the number of GPUs"
+        B = args.total_batch // world
     lib = bw.load()
     sd = gpu_state_dict(dims, dev, seed=rank)
     L = dims.n_text_layer
     dec = WhisperDecoding(dims, sd, B, kv_scales=[0.05] * L, cross_kv_scales=[0.03] * L, device=dev)
-    del sd
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     # synthetic int8 cross-KV cache (the encoder and CrossAttn_KV run once per utterance, outside the decoder step)
     dec.set_cross_kv([torch.randint(-127, 128, (B, 2, dims.n_text_head, dims.n_audio_ctx, 64), generator=g, device=dev,
@@ -362,6 +396,29 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.item())
+
+    # ---- extras: BASELINE.json configs[1] (batch 1) and configs[3] (64 utterances sharded over the GPUs) -----------
+    extras = {}
+    if not args.no_extras and not args.no_graph and args.layers is None:
+        steps_x = min(args.steps, 32)
+        if world == 1:
+            ms1 = time_decoder(dims, sd, 1, dev, steps_x, args.warmup, 300)
+            b1_bytes = L * (12 * dims.n_text_state ** 2) + dims.n_vocab * dims.n_text_state * 2 \
+                + L * 2 * dims.n_text_state * dims.n_audio_ctx + L * 2 * dims.n_text_state * (len(PROMPT) + steps_x)
+            extras["batch1"] = {"workload": "configs[1]: batch 1 decoder step", "ms_per_step": ms1, "tokens_per_s": 1e3 / ms1,
+                                "algorithmic_bytes_per_step": b1_bytes,
+                                "frac_of_hbm_peak": b1_bytes / (ms1 / 1e3) / 1e9 / measured_peak()[0]}
+        if not strong and 64 % world == 0:
+            bs = 64 // world
+            ms_s = time_decoder(dims, sd, bs, dev, steps_x, args.warmup, 400 + rank)
+            ts = torch.tensor([ms_s], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            ms_s = float(ts.item())
+            extras["strong_scaling"] = {"workload": "configs[3]: 64 utterances sharded over the GPUs", "total_batch": 64,
+                                        "batch_per_gpu": bs, "n_gpus": world, "ms_per_step": ms_s,
+                                        "tokens_per_s": 64 / (ms_s / 1e3), "scaling": "strong"}
+    del sd
 
     # ---- rooflines, measured live with CUDA events around CUDA-graph replays (no host launch cost inside) ---------
     # The dominant kernel BY TIME is the tcgen05 weight-only GEMM (192 launches per step, ~60 % of the step in
@@ -491,7 +548,8 @@ def main():
             cb = cpu_baseline(steps=8)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f16 activations x int8 weights, int8 KV (fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": "whisper-large-v2 decoder greedy step: int8 weight-only + int8 self/cross KV, "
@@ -507,6 +565,7 @@ def main():
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_peak": step_frac},
             "kernels": gemm_stats,
         }
+        line.update(extras)
         if cb is not None:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)

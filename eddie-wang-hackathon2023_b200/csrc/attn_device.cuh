@@ -203,11 +203,18 @@ __device__ __forceinline__ void xa_chunk(const uint8_t* kst, const uint8_t* vst,
             xa_load16<INT8>(kst + (size_t) it * 8 * kDh * ESZ, w0);
             xa_load16<INT8>(kst + (size_t) (it + 1) * 8 * kDh * ESZ, w1);
         }
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        // four INDEPENDENT accumulators (one per 16-dim slice) summed afterwards: a chain of four dependent mma.sync
+        // costs four tensor-pipe latencies per 16 keys, and this loop has only 2-3 warps per scheduler to hide them
+        float ca[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            mma_m16n8k16(c0, c1, c2, c3, h2u(w0[2 * j]), h2u(w1[2 * j]), h2u(w0[2 * j + 1]), h2u(w1[2 * j + 1]),
-                bq[2 * j], bq[2 * j + 1]);
+        {
+            ca[j][0] = ca[j][1] = ca[j][2] = ca[j][3] = 0.f;
+            mma_m16n8k16(ca[j][0], ca[j][1], ca[j][2], ca[j][3], h2u(w0[2 * j]), h2u(w1[2 * j]), h2u(w0[2 * j + 1]),
+                h2u(w1[2 * j + 1]), bq[2 * j], bq[2 * j + 1]);
+        }
+        const float c0 = (ca[0][0] + ca[1][0]) + (ca[2][0] + ca[3][0]);
+        const float c2 = (ca[0][2] + ca[1][2]) + (ca[2][2] + ca[3][2]);
         // column 0 of D lives in the lanes with chunk == 0: c0 = key it*8+kl, c2 = key (it+1)*8+kl
         float s0 = __shfl_sync(0xffffffffu, c0, lane & ~3), s1 = __shfl_sync(0xffffffffu, c2, lane & ~3);
         if constexpr (KOFF && INT8)

@@ -152,6 +152,10 @@ def test_large_v2_width_two_layers_against_oracle():
     got = torch.stack(got, 1).cpu().long()
     margins = torch.stack([(l.topk(2).values[:, 0] - l.topk(2).values[:, 1]) for l in ref_logits], 1)
     for b in range(B):
-        weak = (margins[b] < 0.05).nonzero()
-        upto = int(weak[0]) + 1 if len(weak) else n_new
-        assert got[b, :upto].tolist() == ref_tokens[b, :upto].tolist(), (b, got[b].tolist(), ref_tokens[b].tolist())
+        # tokens must be identical up to the first place where they differ -- and that place must be a near-tie of the
+        # oracle itself (a flipped near-tie changes every later token); seed 5 leaves every row a clear start
+        diff = (got[b] != ref_tokens[b]).nonzero()
+        first = int(diff[0]) if len(diff) else n_new
+        assert first >= 3, (b, got[b].tolist(), ref_tokens[b].tolist())
+        if first < n_new:
+            assert margins[b, first].item() < 0.05, (b, first, margins[b].tolist(), got[b].tolist(), ref_tokens[b].tolist())

@@ -70,13 +70,15 @@ def test_reference_gemv_pins_oracle_and_kernels(k, n):
 
 
 @pytest.mark.parametrize("int8", [True, False])
-@pytest.mark.parametrize("past", [5, 37, 200])
-def test_reference_mmha_matches(int8, past):
+@pytest.mark.parametrize("B,past,masked", [(3, 5, False), (3, 37, False), (3, 200, False), (16, 37, False),
+                                           (16, 447, False),  # headline batch, last slot of Smax = 448
+                                           (3, 200, True), (16, 100, True)])  # padding keys via masked_tokens
+def test_reference_mmha_matches(int8, B, past, masked):
     from b200_whisper import _lib
     ref = _ref()
     lib = _lib.load()
-    torch.manual_seed(past)
-    B, H, D, Smax = 3, 20, 64, 448
+    torch.manual_seed(past + B)
+    H, D, Smax = 20, 64, 448
     hidden = H * D
     dev = "cuda"
     qkv = torch.randn((B, 3 * hidden), device=dev).half()
@@ -89,9 +91,17 @@ def test_reference_mmha_matches(int8, past):
         cache0 = torch.randn((B, 2, H, Smax, D), device=dev).half()
     seq = torch.full((B,), past, dtype=torch.int32, device=dev)
     zeros = torch.zeros((B,), dtype=torch.int32, device=dev)
+    mask = None
+    if masked:
+        # nonzero = key excluded (padding between prompt and generated tokens, Template.h:1678-1680,1730); never the
+        # whole row, never the slot being written
+        mask = (torch.rand((B, Smax), device=dev) < 0.25).to(torch.int32)
+        mask[:, 0] = 0
+        mask[:, past:] = 0
+    mask_ptr = None if mask is None else mask.data_ptr()
 
     c_ref, o_ref = cache0.clone(), torch.empty((B, hidden), dtype=torch.float16, device=dev)
-    rc = ref.ref_gpu_mmha(qkv.data_ptr(), o_ref.data_ptr(), c_ref.data_ptr(), seq.data_ptr(), None, zeros.data_ptr(),
+    rc = ref.ref_gpu_mmha(qkv.data_ptr(), o_ref.data_ptr(), c_ref.data_ptr(), seq.data_ptr(), mask_ptr, zeros.data_ptr(),
                           oq.data_ptr(), qo.data_ptr(), B, H, Smax, past, past, 1 if int8 else 0, 1.0, _stream())
     torch.cuda.synchronize()
     assert rc == 0
@@ -101,7 +111,7 @@ def test_reference_mmha_matches(int8, past):
     p.qkv, p.qkv_bias, p.out = qkv.data_ptr(), None, o_our.data_ptr()
     p.kv_cache = c_our.data_ptr()
     p.sequence_lengths = seq.data_ptr()
-    p.masked_tokens = None
+    p.masked_tokens = mask_ptr
     p.kv_scale_orig_quant = oq.data_ptr()
     p.kv_scale_quant_orig = qo.data_ptr()
     p.batch_size, p.num_heads, p.head_size = B, H, D
