@@ -369,6 +369,8 @@ def main():
     l0 = lib.b200_launch_count()
     ev0.record()
     for _ in range(args.steps):
+        if dec._host_len >= dims.n_text_ctx:  # only with --steps beyond the text context: rewind the lengths (one fill)
+            dec.rewind(len(PROMPT))
         dec.step()
     ev1.record()
     barrier()
@@ -384,11 +386,15 @@ def main():
     # ---- e2e: host buffers in/out every step --------------------------------------------------------
     import numpy as np
     host_tokens = np.array(dec.next_tokens.cpu().numpy(), dtype=np.int32)
+    # same self-attention lengths as the device-resident measurement above (the workload must not drift between the two)
+    dec.rewind(len(PROMPT) + max(args.warmup, 3) - 3)
     for _ in range(3):
         host_tokens = dec.step_host(host_tokens).numpy().copy()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        if dec._host_len >= dims.n_text_ctx:
+            dec.rewind(len(PROMPT))
         host_tokens = dec.step_host(host_tokens).numpy().copy()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -396,6 +402,32 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.item())
+
+    # ---- e2e through the reference's own boundary: the same step, one plugin enqueue per operator ----------------------
+    # (WeightOnlyQuantMatmulPlugin::enqueue x 6 + GPTAttentionPlugin::enqueue per layer via include/b200_plugin_harness.h,
+    # unfused LayerNorm / bias / GELU / residual layers in between, eager launches, host token buffers in and out)
+    e2e_plugin = None
+    if not args.no_extras and args.layers is None:
+        from b200_whisper.runtime import PluginDecoderStep
+        stepper = PluginDecoderStep(dec)
+        dec.rewind(len(PROMPT) + max(args.warmup, 3) - 3)
+        n_p = max(4, min(args.steps, 16))
+        for _ in range(3):
+            host_tokens = stepper.step_host(host_tokens).numpy().copy()
+        barrier()
+        enq0 = stepper.enqueues
+        t0 = time.perf_counter()
+        for _ in range(n_p):
+            host_tokens = stepper.step_host(host_tokens).numpy().copy()
+        barrier()
+        tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        e2e_plugin = {"value": world * B * n_p / float(tp.item()), "unit": UNIT, "steps": n_p,
+                      "ms_per_step": 1e3 * float(tp.item()) / n_p,
+                      "plugin_enqueues_per_step": (stepper.enqueues - enq0) // n_p,
+                      "path": "IPluginV2DynamicExt::enqueue per operator (eager, unfused glue), host token buffers"}
+        stepper.close()
 
     # ---- extras: BASELINE.json configs[1] (batch 1) and configs[3] (64 utterances sharded over the GPUs) -----------
     extras = {}
@@ -566,6 +598,8 @@ def main():
             "kernels": gemm_stats,
         }
         line.update(extras)
+        if e2e_plugin is not None:
+            line["e2e_plugin"] = e2e_plugin
         if cb is not None:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)

@@ -1172,7 +1172,7 @@ static int xattn_launch_rowhead(const XAttnParams& p, const XaPlan& pl, cudaStre
     return B200_OK;
 }
 
-int* tc_counter_slot(int needed);
+int* tc_counter_slot(int needed, cudaStream_t stream);
 } // namespace b200
 
 extern "C" size_t b200_cross_attention_workspace_bytes(int batch_size, int num_heads, int head_size, int kv_len)
@@ -1234,7 +1234,7 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     }
     B200_REQUIRE(workspace && workspace_bytes >= pl.ws_bytes, B200_ERR_WORKSPACE,
         "cross attention: workspace of %zu bytes needed, got %zu", pl.ws_bytes, workspace_bytes);
-    p.counters = tc_counter_slot(batch_size * num_heads);
+    p.counters = tc_counter_slot(batch_size * num_heads, st);
     B200_REQUIRE(p.counters != nullptr, B200_ERR_UNSUPPORTED, "cross attention: %d (row, head) pairs exceed the counter slot",
         batch_size * num_heads);
     switch (pl.cfg * 2 + (int8_kv_cache ? 1 : 0))

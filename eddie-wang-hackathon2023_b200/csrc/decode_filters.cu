@@ -14,7 +14,7 @@
 
 namespace b200
 {
-int* tc_counter_slot(int needed);
+int* tc_counter_slot(int needed, cudaStream_t stream);
 
 struct RangeAcc
 {
@@ -198,7 +198,7 @@ extern "C" int b200_whisper_filtered_argmax(const float* logits, int rows, int v
     B200_REQUIRE(rows <= 256, B200_ERR_UNSUPPORTED, "filtered argmax: %d rows exceed the scratch slot", rows);
     B200_REQUIRE_DEVICE();
     constexpr int parts = 8;
-    int* slot = tc_counter_slot(rows * (parts * 6 + 1));
+    int* slot = tc_counter_slot(rows * (parts * 6 + 1), as_stream(stream));
     B200_REQUIRE(slot != nullptr, B200_ERR_CUDA, "filtered argmax: no scratch slot");
     // counters first (they must be zero between launches and reset themselves), partial results after them
     int* counters = slot;

@@ -9,7 +9,7 @@
 
 namespace b200
 {
-int* tc_counter_slot(int needed);
+int* tc_counter_slot(int needed, cudaStream_t stream);
 
 // y = (x - mean) * rsqrt(var + eps) * gamma + beta, statistics in fp32 (torch_model.py:25-27 casts to float).
 // one CTA (128 threads) per row; cols % 8 == 0; row cached in registers (cols <= 8192).
@@ -388,8 +388,8 @@ __global__ void l2_prefetch_kernel(const uint8_t* __restrict__ p, size_t bytes, 
 }
 
 int logits_tc(const __half* x, const __half* emb, float* logits, int rows, int cols, int vocab, cudaStream_t stream);
-extern int g_logits_policy;
-int g_logits_policy = 0; // 0 auto (tcgen05), 1 simt
+extern thread_local int g_logits_policy;
+thread_local int g_logits_policy = 0; // 0 auto (tcgen05), 1 simt; per calling thread (test switch)
 
 } // namespace b200
 
@@ -514,7 +514,7 @@ extern "C" int b200_logits_argmax_fp16(const void* x, const void* emb, void* log
     {
         // scratch: one 64-bit key and one arrival counter per row (library owned, self-resetting)
         B200_REQUIRE(rows <= 4096, B200_ERR_UNSUPPORTED, "argmax: %d rows exceed the scratch slot", rows);
-        int* slot = tc_counter_slot(3 * rows + 2);
+        int* slot = tc_counter_slot(3 * rows + 2, st);
         B200_REQUIRE(slot != nullptr, B200_ERR_CUDA, "argmax: no scratch slot");
         unsigned long long* packed = reinterpret_cast<unsigned long long*>(slot);
         int* counters = slot + 2 * rows;

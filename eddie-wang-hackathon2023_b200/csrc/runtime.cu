@@ -55,19 +55,23 @@ bool device_ok()
     return g_dev_ok == 1;
 }
 
-static int g_pdl = -1;
+static std::atomic<int> g_pdl{-1};
 
 bool pdl_enabled()
 {
-    if (g_pdl < 0)
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0)
     {
         const char* e = getenv("B200_PDL");
-        g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+        g_pdl.store(v, std::memory_order_relaxed);
     }
-    return g_pdl == 1;
+    return v == 1;
 }
 
-static int g_static_kv = 0;
+// Per calling thread: the hint describes the caller's OWN launch sequence (its KV caches are not written by the
+// kernel in front of the attention launch), so it must not leak into launches other threads / plugin contexts make.
+static thread_local int g_static_kv = 0;
 
 bool static_kv_hint()
 {

@@ -20,7 +20,9 @@ void tc_set_timeline_buffer(long long* p, int max_launches);
 bool woq_tc_can_fold_ln(int M, int N, int K);
 void woq_tc_plan_query(int M, int N, int K, int* mt, int* m_tiles, int* n_tiles, int* splits, int* cluster);
 
-static int g_policy = 0; // 0 auto, 1 simt, 2 tcgen05
+// 0 auto, 1 simt, 2 tcgen05.  Per calling thread (a test / tuning switch, never set on the serving path): plugin
+// instances enqueueing from other threads keep the automatic dispatch whatever a test thread forces.
+static thread_local int g_policy = 0;
 
 // One thread per weight column n: walks the column through the preprocessed layout exactly like the GEMM's dequant
 // warps do (same 16-byte chunks, same PRMT/HSUB2 conversion, same HMUL2 by the gamma pair) and sums

@@ -1287,8 +1287,25 @@ TcPlan plan_tc(int M, int N, int K)
 
 static int* g_counters = nullptr;
 static std::mutex g_counter_mu;
-static unsigned g_counter_slot = 0;
-constexpr int kCounterSlots = 64, kCounterSlotInts = 16384;
+// Counter / scratch slots are handed out PER STREAM: a slot is only safe to reuse once the launch that used it has
+// finished, and stream order is the one ordering the library can rely on (launch N + kSlotsPerStream on a stream runs
+// after launch N even under programmatic dependent launch, whose overlap reaches one or two kernels back).  Every
+// stream the library sees (including a capture stream: the addresses are baked into the captured graph, and the
+// graph's nodes keep the stream's order) owns a private range of the pool, so kernels of concurrent streams -- forked
+// decoder chains, an encoder overlapping a decoder graph replay, two plugin contexts enqueueing from two threads --
+// never share a slot.  More than kSlotStreams distinct streams recycle the least recently used range.
+constexpr int kSlotStreams = 16, kSlotsPerStream = 16, kCounterSlots = kSlotStreams * kSlotsPerStream, kCounterSlotInts = 16384;
+
+struct SlotRange
+{
+    cudaStream_t stream;
+    unsigned next;
+    unsigned long long last_use;
+    bool used;
+};
+
+static SlotRange g_slot_ranges[kSlotStreams];
+static unsigned long long g_slot_clock = 0;
 
 int tc_init()
 {
@@ -1301,15 +1318,35 @@ int tc_init()
     return B200_OK;
 }
 
-// Hands out one self-resetting counter slot (kCounterSlotInts ints, all zero between launches) round-robin.
-int* tc_counter_slot(int needed)
+// Hands out one self-resetting counter slot (kCounterSlotInts ints, all zero between launches) from `stream`'s range.
+int* tc_counter_slot(int needed, cudaStream_t stream)
 {
     if (needed > kCounterSlotInts)
         return nullptr;
     if (g_counters == nullptr && tc_init() != B200_OK)
         return nullptr;
     std::lock_guard<std::mutex> lk(g_counter_mu);
-    return g_counters + (size_t) (g_counter_slot++ % kCounterSlots) * kCounterSlotInts;
+    int idx = -1;
+    for (int i = 0; i < kSlotStreams && idx < 0; ++i)
+        if (g_slot_ranges[i].used && g_slot_ranges[i].stream == stream)
+            idx = i;
+    if (idx < 0)
+    {
+        for (int i = 0; i < kSlotStreams && idx < 0; ++i)
+            if (!g_slot_ranges[i].used)
+                idx = i;
+        if (idx < 0)
+        {
+            idx = 0;
+            for (int i = 1; i < kSlotStreams; ++i)
+                if (g_slot_ranges[i].last_use < g_slot_ranges[idx].last_use)
+                    idx = i;
+        }
+        g_slot_ranges[idx] = SlotRange{stream, 0u, 0ull, true};
+    }
+    SlotRange& r = g_slot_ranges[idx];
+    r.last_use = ++g_slot_clock;
+    return g_counters + ((size_t) idx * kSlotsPerStream + (r.next++ % kSlotsPerStream)) * kCounterSlotInts;
 }
 
 template <int MT, int SS, int AS, bool CL>
@@ -1422,7 +1459,7 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     p.residual = residual;
     p.C = C;
     p.slabs = static_cast<float*>(workspace);
-    p.counters = tc_counter_slot(pl.m_tiles * pl.n_tiles <= kCounterSlotInts ? pl.m_tiles * pl.n_tiles : 1);
+    p.counters = tc_counter_slot(pl.m_tiles * pl.n_tiles <= kCounterSlotInts ? pl.m_tiles * pl.n_tiles : 1, stream);
     if (fold_gamma != nullptr)
     {
         p.fold_x = A;

@@ -91,8 +91,10 @@ class WhisperPipeline:
         """run.py:57-66 for a batch of waveforms: greedy decode from the tokenizer's sot sequence with the logit filters
         on, tokens cut at the first end-of-text (decoding.py:836-840), text when the tokenizer has a vocabulary.
         -> list of {"tokens": [...], "text": str or None, "sum_logprob": float}; with detect_language also "language",
-        "language_probs" and "no_speech_prob" (run.py:58; the prompt keeps the tokenizer's language, as the reference
-        does when options.language is set)."""
+        "language_probs" and "no_speech_prob" (run.py:58), and -- the reference's default, DecodingOptions.language =
+        None -- every utterance is decoded from ITS detected language token: decoding.py:738-739 writes it into
+        tokens[:, sot_index + 1] before the main loop.  detect_language=False keeps the tokenizer's language (the
+        reference with options.language set)."""
         if getattr(self, "_filter_tokenizer", None) is not tokenizer:
             self.enable_filters(tokenizer)
         prompt = list(tokenizer.sot_sequence)
@@ -110,7 +112,13 @@ class WhisperPipeline:
             extra = self.detect_language(xa, tokenizer) if detect_language else None
             if extra is None:
                 self.decoder.set_encoder_output(xa)
-            tok = self.decoder.decode([prompt] * self.B, sample_len).cpu().tolist()
+            prompts = [list(prompt) for _ in range(self.B)]
+            if extra is not None and len(prompt) > 1:
+                lang_tok0 = tokenizer.all_language_tokens[0]
+                codes = tokenizer.all_language_codes
+                for i, code in enumerate(extra[0]):
+                    prompts[i][1] = lang_tok0 + codes.index(code)
+            tok = self.decoder.decode(prompts, sample_len).cpu().tolist()
             lp = self.decoder.logit_filter.sum_logprobs.cpu().tolist()
             for row, s in zip(tok[:nb], lp[:nb]):
                 ids = row[:row.index(tokenizer.eot)] if tokenizer.eot in row else row

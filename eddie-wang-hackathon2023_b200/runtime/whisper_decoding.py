@@ -264,6 +264,7 @@ class WhisperDecoding:
 
     def reset(self):
         self.seq_len.zero_()
+        self._host_len = 0  # host-side copy of the (uniform) sequence length: bounds checks without a device read
         if getattr(self, "logit_filter", None) is not None:
             self.logit_filter.reset()
 
@@ -366,6 +367,8 @@ class WhisperDecoding:
         B = self.B
         prompt = torch.as_tensor(prompt_tokens, dtype=torch.int32, device=self.device).view(B, -1).contiguous()
         S = prompt.shape[1]
+        if S > self.Smax:
+            raise ValueError(f"prompt of {S} tokens exceeds n_text_ctx = {self.Smax}")
         rows = B * S
         pos = torch.arange(S, dtype=torch.int32, device=self.device).repeat(B)
         x = self._buf("x", rows, self.d)
@@ -376,6 +379,7 @@ class WhisperDecoding:
         last = x.view(B, S, self.d)[:, S - 1, :].contiguous()
         self._head(last, B, self.logits, self.next_tokens)
         self.seq_len.fill_(S)
+        self._host_len = S
         self.tokens.copy_(self.next_tokens)
         return self.next_tokens
 
@@ -479,8 +483,21 @@ class WhisperDecoding:
         self.graph_host = gh
         return g
 
+    def rewind(self, length):
+        """Sets every sequence back to `length` cached tokens (benchmarks: a long run of steps stays inside n_text_ctx
+        and keeps a bounded self-attention length).  The cache keeps its bytes; only the lengths move."""
+        if not 0 < length <= self.Smax:
+            raise ValueError(f"length {length} outside (0, {self.Smax}]")
+        self.seq_len.fill_(length)
+        self._host_len = length
+
     def step(self):
-        """One greedy generation step for the whole batch; consumes self.tokens, produces self.next_tokens."""
+        """One greedy generation step for the whole batch; consumes self.tokens, produces self.next_tokens.
+        Raises once the text context is full: the reference stops at n_text_ctx (decoding.py:324,749); past it the
+        kernels would only clamp (last KV slot overwritten, last position reused) and return garbage silently."""
+        if getattr(self, "_host_len", 0) >= self.Smax:
+            raise RuntimeError(f"the text context is full ({self.Smax} tokens): reset() or prefill() before stepping on")
+        self._host_len = getattr(self, "_host_len", 0) + 1
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -490,6 +507,9 @@ class WhisperDecoding:
     def step_host(self, tokens_host=None):
         """End-to-end step with HOST buffers: pinned token ids in -> pinned next-token ids out."""
         if tokens_host is not None and getattr(self, "graph_host", None) is not None:
+            if getattr(self, "_host_len", 0) >= self.Smax:
+                raise RuntimeError(f"the text context is full ({self.Smax} tokens): reset() or prefill() before stepping on")
+            self._host_len = getattr(self, "_host_len", 0) + 1
             self._pinned_in.copy_(torch.as_tensor(tokens_host, dtype=torch.int32))
             self.graph_host.replay()
             torch.cuda.current_stream(self.device).synchronize()
@@ -504,11 +524,19 @@ class WhisperDecoding:
 
     def decode(self, prompt_tokens, n_new, use_graph=True):
         """Greedy decode (logit filters off): returns int32 [B, n_new] on the device."""
+        S = len(prompt_tokens[0]) if not torch.is_tensor(prompt_tokens) else prompt_tokens.shape[-1]
+        if S + n_new - 1 > self.Smax:
+            raise ValueError(f"prompt ({S}) + {n_new} new tokens do not fit n_text_ctx = {self.Smax}")
         self.reset()
         out = torch.empty((self.B, n_new), dtype=torch.int32, device=self.device)
         out[:, 0] = self.prefill(prompt_tokens)
         if use_graph and self.graph is None and n_new > 1:
             self.capture()
         for t in range(1, n_new):
-            out[:, t] = self.step() if use_graph else (self._step_body() or self.next_tokens)
+            if use_graph:
+                out[:, t] = self.step()
+            else:
+                self._host_len += 1
+                self._step_body()
+                out[:, t] = self.next_tokens
         return out

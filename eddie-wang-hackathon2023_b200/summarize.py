@@ -76,10 +76,18 @@ def evaluate(pipeline, tokenizer, waveforms, references: Sequence[str], sample_l
         raise RuntimeError("a vocabulary is needed to turn tokens into text: get_tokenizer(..., vocab_path=...)")
     normalizer = normalizer or basic_normalizer
     keep = [i for i, w in enumerate(waveforms) if len(w) <= max_samples]
+    if not keep:
+        raise ValueError(f"no utterance to score: all {len(waveforms)} are longer than {max_samples} samples (30 s)")
     from . import whisper_utils
     import numpy as np
-    batch = np.stack([whisper_utils.pad_or_trim(np.asarray(waveforms[i], dtype=np.float32), pipeline.n_samples) for i in keep])
-    results = pipeline.transcribe(batch, tokenizer, sample_len=sample_len)
+    # one decoder batch at a time (the reference streams one file at a time, summarize.py:112-140): a LibriSpeech split
+    # padded to 30 s per utterance is gigabytes of host AND device memory if stacked in one piece
+    results = []
+    step = max(1, int(getattr(pipeline, "B", 1)))
+    for b0 in range(0, len(keep), step):
+        batch = np.stack([whisper_utils.pad_or_trim(np.asarray(waveforms[i], dtype=np.float32), pipeline.n_samples)
+                          for i in keep[b0:b0 + step]])
+        results.extend(pipeline.transcribe(batch, tokenizer, sample_len=sample_len))
     hyps = [clean_hypothesis(r["text"]) for r in results]
     refs = [references[i] for i in keep]
     wer = word_error_rate([normalizer(r) for r in refs], [normalizer(h) for h in hyps])

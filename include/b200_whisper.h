@@ -60,7 +60,9 @@ int b200_set_pdl(int enabled);
  * NOT written by the kernel launched right before them on the stream (true inside a decoder step: a cache row is
  * written one step before it is read, the lengths are bumped after the step's last kernel).  With the hint the
  * attention kernels fetch (and, for self-attention, convert) the cache before griddepcontrol.wait, so only the dot
- * products remain once the preceding projection has finished.  Default off (always safe). */
+ * products remain once the preceding projection has finished.  Default off (always safe).  The switch belongs to the
+ * CALLING THREAD (thread-local): it qualifies the launches that thread makes next and is invisible to other threads, so
+ * plugin instances enqueueing concurrently never see each other's hint. */
 int b200_set_static_kv_hint(int enabled);
 /* Fire-and-forget prefetch of [ptr, ptr+bytes) into L2 (cp.async.bulk.prefetch.L2); ptr 16-byte aligned. */
 int b200_l2_prefetch(const void* ptr, size_t bytes, b200_stream_t stream);
@@ -131,7 +133,8 @@ int b200_woq_ln_fold_prepare(const int8_t* Wproc, const void* scales, const void
 int b200_woq_int8_gemm_ln_folded(const void* X, const void* ln_gamma, const void* ln_beta, const float* c1s,
     const float* c2, float ln_eps, int M, int K, const int8_t* Wproc, const void* scales, int N, const void* bias,
     int activation, const void* residual, void* C, void* workspace, size_t workspace_bytes, b200_stream_t stream);
-/* Forces a kernel family for tests/benchmarks: 0 = auto, 1 = SIMT GEMV, 2 = tcgen05 GEMM. */
+/* Forces a kernel family for tests/benchmarks: 0 = auto, 1 = SIMT GEMV, 2 = tcgen05 GEMM.  Thread-local: it affects the
+ * calling thread's launches only (other threads keep the automatic dispatch). */
 int b200_woq_set_kernel_policy(int policy);
 /* Debug aid: device buffer of >= 16 int64 receiving clock64() stamps of CTA (0,0,0) of each following tcgen05 GEMM
  * launch at its phase boundaries; NULL switches it off. */

@@ -22,8 +22,9 @@ class FakeDecoder:
         self.tags = xa[:, 0, 0].long().tolist()
 
     def decode(self, prompts, n_new, use_graph=True):
-        assert len(prompts) == self.B and all(p == prompts[0] for p in prompts)
+        assert len(prompts) == self.B and all(len(p) == len(prompts[0]) for p in prompts)
         self.calls.append((list(self.tags), list(prompts[0]), n_new))
+        self.prompt_rows = getattr(self, "prompt_rows", []) + [[list(p) for p in prompts]]
         rows = []
         for tag in self.tags:
             row = [1000 + 10 * tag + i for i in range(n_new)]
@@ -73,7 +74,16 @@ def test_transcribe_cuts_at_eot_and_attaches_language():
     assert pipe.decoder.filters[0] == tk.eot and pipe.decoder.filters[2] == tk.timestamp_begin
     assert pipe.decoder.filters[3] == 220 and pipe.decoder.filters[5] == 50          # blank id, 1.0 s / 0.02 s
     assert set(pipe.decoder.filters[4]) == {tk.transcribe, tk.translate, tk.sot, tk.sot_prev, tk.sot_lm, tk.no_speech}
-    assert [c[1] for c in pipe.decoder.calls] == [list(tk.sot_sequence)] * 2
+    # the reference's default (options.language = None): every utterance is decoded from ITS detected language token
+    # (decoding.py:738-739); two different languages in one batch
+    lang0 = tk.all_language_tokens[0]
+    sot, task = tk.sot_sequence[0], tk.sot_sequence[2]
+    assert pipe.decoder.prompt_rows == [[[sot, lang0 + 0, task], [sot, lang0 + 1, task]],
+                                        [[sot, lang0 + 2, task], [sot, lang0 + 2, task]]]   # slice 2: utterance 2 + padding
+    # without detection the tokenizer's language is kept for every row (options.language set)
+    pipe2 = make_pipe(2, tk)
+    pipe2.transcribe([0, 1], tk, sample_len=4)
+    assert pipe2.decoder.prompt_rows == [[list(tk.sot_sequence)] * 2]
     assert [len(r["tokens"]) for r in res] == [6, 3, 6]                                # utterance 1 ended at its eot
     assert res[1]["tokens"] == [1010, 1011, 1012] and tk.eot not in res[1]["tokens"]
     assert [r["sum_logprob"] for r in res] == [0.0, -1.0, -2.0]

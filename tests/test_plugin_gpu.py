@@ -165,3 +165,111 @@ def test_gpt_attention_paged_kv_through_plugin():
                 assert torch.equal(pool[blk, 0, :, t % tpb], cache[bi, kv, :, t])
     lin.destroy()
     pag.destroy()
+
+
+def test_decoder_step_through_the_plugin_classes_matches_the_fused_path():
+    """runtime.PluginDecoderStep: every Linear through WeightOnlyQuantMatmulPlugin::enqueue, self-attention through
+    GPTAttentionPlugin::enqueue, unfused LayerNorm / bias / GELU / residual layers in between (the reference's graph)
+    -- against runtime.WhisperDecoding's fused kernels on the same weights, caches and tokens."""
+    from b200_whisper.runtime import PluginDecoderStep, WhisperDecoding
+    from oracle import whisper_oracle as wo
+    dims = wo.ModelDimensions(80, 1500, 1280, 20, 1, 51865, 448, 1280, 20, 2)
+    B, prompt, n_new = 4, [50258, 50259, 50359], 5
+    sd = wo.synthetic_state_dict(dims, seed=5, decoder_only=True)
+    L = dims.n_text_layer
+    g = torch.Generator(device="cuda").manual_seed(7)
+    cross = [torch.randint(-127, 128, (B, 2, dims.n_text_head, 200, 64), generator=g, device="cuda", dtype=torch.int8)
+             for _ in range(L)]
+
+    def run(through_plugins):
+        dec = WhisperDecoding(dims, sd, B, [0.05] * L, [0.03] * L, n_audio_ctx=200)
+        dec.set_cross_kv([c.clone() for c in cross])
+        dec.reset()
+        dec.prefill([prompt] * B)
+        stepper = PluginDecoderStep(dec) if through_plugins else None
+        toks, logits = [], []
+        for _ in range(n_new):
+            toks.append((stepper.step() if stepper else (dec._step_body() or dec.next_tokens)).clone())
+            if not through_plugins:
+                dec._host_len += 1
+            logits.append(dec.logits.clone())
+        n_enq = stepper.enqueues if stepper else 0
+        if stepper:
+            stepper.close()
+        return torch.stack(toks, 1).cpu(), torch.stack(logits, 1).float().cpu(), n_enq
+
+    t_fused, l_fused, _ = run(False)
+    t_plug, l_plug, n_enq = run(True)
+    assert n_enq == n_new * L * 7            # six matmul plugin enqueues + one attention plugin enqueue per layer
+    scale = l_fused.abs().max().item()
+    # same arithmetic up to the rounding points of the fused epilogues / folded LayerNorm (DESIGN.md, numerics)
+    assert (l_plug - l_fused).abs().max().item() <= 2e-2 * scale
+    margins = l_fused.topk(2, dim=-1).values
+    clear = (margins[..., 0] - margins[..., 1]) > 0.05 * scale
+    same_history = torch.cat([torch.ones(B, 1, dtype=torch.bool), (t_plug == t_fused).cumprod(1)[:, :-1].bool()], 1)
+    assert ((t_plug == t_fused) | ~clear | ~same_history).all()
+    assert (t_plug[:, 0] == t_fused[:, 0]).all()
+
+
+def test_two_threads_enqueue_concurrently():
+    """Two plugin instances enqueueing from two host threads on two streams (two execution contexts of an engine): the
+    library's switches are thread-local and its counter / scratch slots are per stream, so neither thread can disturb
+    the other.  One thread additionally flips the test-only switches the whole time."""
+    import threading
+
+    import b200_whisper as bw
+    from b200_whisper import _lib
+    lib = _lib.load()
+    m, n, k = 16, 1280, 5120                     # split-K decode shape: uses the arrival counters / cluster exchange
+    torch.manual_seed(0)
+    weight = gen((k, n), 3)
+    raw, proc, scales = bw.ops._symmetric_quantize_last_axis_of_batched_matrix(weight, torch.int8)
+    w, s = proc.cuda().view(torch.float32), scales.cuda()
+    xs = [(gen((m, k), 10 + t) * 4).cuda().view(1, m, k) for t in range(2)]
+    refs = []
+    plug0 = TrtPlugin.create("WeightOnlyQuantMatmul", woq_fields())
+    ins = [((1, m, k), "float16"), (tuple(w.shape), "float32"), (tuple(s.shape), "float16")]
+    outs = [((1, m, n), "float16")]
+    ws0 = torch.empty((max(plug0.workspace_size(ins, outs), 16),), dtype=torch.uint8, device="cuda")
+    for x in xs:                                  # single-threaded answers first
+        o = torch.empty((1, m, n), dtype=torch.float16, device="cuda")
+        assert plug0.enqueue(ins, outs, [x.data_ptr(), w.data_ptr(), s.data_ptr()], [o.data_ptr()], ws0.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream) == 0
+        torch.cuda.synchronize()
+        refs.append(o.clone())
+    plug0.destroy()
+    errors = []
+
+    def worker(t):
+        try:
+            plug = TrtPlugin.create("WeightOnlyQuantMatmul", woq_fields())
+            stream = torch.cuda.Stream()
+            ws = torch.empty((ws0.numel(),), dtype=torch.uint8, device="cuda")
+            o = torch.empty((1, m, n), dtype=torch.float16, device="cuda")
+            with torch.cuda.stream(stream):
+                for it in range(200):
+                    if t == 1:                    # thread-local: must not leak into thread 0's launches
+                        lib.b200_set_static_kv_hint(it & 1)
+                        lib.b200_woq_set_kernel_policy(2 if it & 1 else 0)
+                    rc = plug.enqueue(ins, outs, [xs[t].data_ptr(), w.data_ptr(), s.data_ptr()], [o.data_ptr()],
+                                      ws.data_ptr(), stream.cuda_stream)
+                    if rc != 0:
+                        raise RuntimeError(f"enqueue rc {rc}")
+                    if it % 50 == 49:
+                        stream.synchronize()
+                        if not torch.equal(o, refs[t]):
+                            raise AssertionError(f"thread {t}, iteration {it}: output differs from the single-threaded run")
+            stream.synchronize()
+            plug.destroy()
+            if t == 1:
+                lib.b200_set_static_kv_hint(0)
+                lib.b200_woq_set_kernel_policy(0)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

@@ -47,9 +47,12 @@ def test_evaluate_over_a_fake_pipeline():
 
     class FakePipe:
         n_samples = 480000
+        B = 2
+        shapes = []
 
         def transcribe(self, batch, tokenizer, sample_len=None):
-            assert batch.shape == (2, 480000) and batch.dtype == np.float32          # the 31 s utterance was skipped
+            assert batch.shape[0] <= self.B and batch.shape[1] == 480000 and batch.dtype == np.float32
+            self.shapes.append(batch.shape[0])
             return [{"text": texts[int(row[0])], "tokens": [], "sum_logprob": 0.0} for row in batch]
 
     waves = [np.full(16000, 0, np.float32), np.full(32000, 1, np.float32), np.full(16000 * 31, 2, np.float32)]
@@ -58,5 +61,12 @@ def test_evaluate_over_a_fake_pipeline():
     out = sm.evaluate(FakePipe(), tk, waves, refs)
     assert out["skipped"] == 1 and out["hypotheses"] == [" MISTER QUILTER IS THE APOSTLE", " NOR IS HE"]
     assert out["wer"] == pytest.approx(1 / 8)                                         # one substitution in eight words
+    assert FakePipe.shapes == [2]                                                     # the 31 s utterance was skipped
+    # streamed one decoder batch at a time: five utterances, batch 2 -> slices of 2, 2, 1 (never the whole split at once)
+    FakePipe.shapes.clear()
+    out = sm.evaluate(FakePipe(), tk, [waves[0], waves[1]] * 2 + [waves[0]], [refs[0], refs[1]] * 2 + [refs[0]])
+    assert FakePipe.shapes == [2, 2, 1] and len(out["hypotheses"]) == 5
+    with pytest.raises(ValueError, match="no utterance"):
+        sm.evaluate(FakePipe(), tk, [waves[2]], ["X"])                                # nothing survives the length filter
     with pytest.raises(RuntimeError, match="vocabulary"):
         sm.evaluate(FakePipe(), types.SimpleNamespace(encoding=None), waves, refs)

@@ -36,13 +36,17 @@ def graph_ms(body, reps=3):
 
 
 print(f"{'K->N':>12s} {'M':>6s} {'us/launch':>10s} {'weight GB/s':>12s} {'TFLOP/s':>9s}")
-for k, n in ((1280, 3840), (1280, 5120), (5120, 1280)):
-    L = 16
+# the fourth shape of config 5 is the logits projection 1280 -> 51865, padded to 51904 (a multiple of 64) for the int8 layout
+SHAPES = [tuple(int(v) for v in s.split("x")) for s in os.environ.get("SWEEP_SHAPES", "1280x3840,1280x5120,5120x1280,1280x51904").split(",")]
+for k, n in SHAPES:
+    L = 16 if k * n < (32 << 20) else 4   # distinct weight sets per graph: > L2 in total either way
+    if n > 6000 and "SWEEP_M" not in os.environ:
+        os.environ["SWEEP_M_"] = "1,2,4,8,16,32,64,128,256"
     ws_ = []
     for i in range(L):
         w = ((torch.rand((k, n), device=dev) * 2 - 1) * 0.05).half()
         ws_.append(bw.ops.symmetric_quantize_last_axis_of_batched_matrix(w, torch.int8))
-    for m in [int(v) for v in os.environ.get("SWEEP_M", "1,2,4,8,16,32,64,128,256,1500,24000").split(",")]:
+    for m in [int(v) for v in os.environ.get("SWEEP_M", os.environ.get("SWEEP_M_", "1,2,4,8,16,32,64,128,256,1500,24000")).split(",")]:
         x = (torch.rand((m, k), device=dev) * 2 - 1).half()
         o = torch.empty((m, n), dtype=torch.float16, device=dev)
         wk = torch.empty((lib.b200_woq_workspace_bytes(m, n, k),), dtype=torch.uint8, device=dev)
