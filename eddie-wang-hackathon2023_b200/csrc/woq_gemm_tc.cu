@@ -1153,9 +1153,23 @@ static PFN_encodeTiled get_encode()
     return fn;
 }
 
+// The driver entry point needs a CURRENT context.  A host thread that has made no runtime call yet (a second TensorRT
+// execution context enqueueing from its own thread) has none: bind the device's primary context once per thread with a
+// no-op runtime call.  (Found by tests/test_plugin_gpu.py::test_two_threads_enqueue_concurrently: CUresult 201.)
+static void bind_context_once()
+{
+    static thread_local bool bound = false;
+    if (!bound)
+    {
+        cudaFree(nullptr);
+        bound = true;
+    }
+}
+
 int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uint64_t dim0, uint64_t dim1,
     uint64_t stride1_bytes, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz)
 {
+    bind_context_once();
     PFN_encodeTiled enc = get_encode();
     B200_REQUIRE(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[2] = {dim0, dim1};
@@ -1174,6 +1188,7 @@ int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dt, const void* base, uin
     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, uint32_t estride1,
     CUtensorMapSwizzle swz)
 {
+    bind_context_once();
     PFN_encodeTiled enc = get_encode();
     B200_REQUIRE(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[3] = {dim0, dim1, dim2};

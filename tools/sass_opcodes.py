@@ -27,7 +27,7 @@ def main():
             cur = re.sub(r"\(.*$", "", cur).replace("void ", "")
             counts.setdefault(cur, collections.Counter())
             continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
         if m and cur is not None:
             op = m.group(1)
             total[cur] += 1
