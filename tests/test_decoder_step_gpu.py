@@ -54,12 +54,25 @@ def _compare(dims, seed, B, n_steps, S_enc=None, ctas=0, tol=4e-3):
     assert new.step_kernel_status() == 0, f"step kernel wait timed out: status {new.step_kernel_status():#x}"
     t_old, l_old = _run(old, B, n_steps)
     scale = l_old.abs().max().item()
-    err = (l_new - l_old).abs().max().item()
     assert torch.isfinite(l_new).all()
+    # logits are comparable while both paths have decoded the same tokens (an exact tie of the top two logits -- seen
+    # with these random weights -- may legitimately resolve differently and changes everything after it)
+    same = torch.ones(t_new.shape, dtype=torch.bool, device=t_new.device)
+    for b in range(B):
+        d = (t_new[b] != t_old[b]).nonzero()
+        if len(d):
+            same[b, int(d[0]) + 1:] = False
+            top2 = l_old[b, int(d[0])].topk(2).values
+            assert (top2[0] - top2[1]).item() <= 2 * tol * scale, "tokens diverged on a clear decision"
+    assert same[:, :2].all(), "tokens diverged within the first steps"
+    err = ((l_new - l_old).abs().amax(-1) * same).max().item()
     assert err <= tol * scale, f"logits differ by {err} (scale {scale})"
     # the appended self-attention cache rows: same quantization rule on (nearly) the same k / v -> at most an LSB
+    # (rows written while both paths were on the same history)
+    n_same = int(same.all(0).sum().item())          # steps (incl. the prefill's token) before the first divergence
+    rows = len(PROMPT) + max(n_same - 1, 0)
     for i in range(dims.n_text_layer):
-        a, b = new.self_kv[i].int(), old.self_kv[i].int()
+        a, b = new.self_kv[i][:, :, :, :rows].int(), old.self_kv[i][:, :, :, :rows].int()
         assert (a - b).abs().max().item() <= 1
         assert (a != b).float().mean().item() < 0.02
     top2 = l_old.topk(2, -1).values
