@@ -37,7 +37,7 @@ def test_scratch_size_and_argument_validation():
     import b200_whisper
     from b200_whisper import _lib
     lib = b200_whisper.load()
-    assert lib.b200_decoder_step_scratch_bytes(20, 5120) == 256 + 64 * 1280 * 8 + 64 * 5120 + 4 * 128 * 1280
+    assert lib.b200_decoder_step_scratch_bytes(20, 5120) == 256 + 192 * 1280 + 32 * 5120
     assert lib.b200_decoder_step_scratch_bytes(0, 5120) == 0
     assert lib.b200_decoder_step(None, None) == 1
     p = _lib.DecoderStepParams()
