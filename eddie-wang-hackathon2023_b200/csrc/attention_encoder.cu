@@ -7,11 +7,33 @@
 // double-buffered in shared memory with cp.async (16-byte chunks XOR-swizzled by the row so every ldmatrix is
 // conflict-free); scores and P.V run on the tensor cores (mma.sync.m16n8k16, fp32 accumulate), the online softmax
 // lives in registers (ex2 with the scale folded into one FFMA, lazily rescaled accumulators), the score accumulators are re-used in place as the fp16 A fragments of P.
-// Round 1 uses the warp-level mma.sync path (the encoder runs once per utterance, off the decoder-step metric); a
-// tcgen05 / TMEM version of this kernel is the natural round-2 upgrade.
+// That warp-level mma.sync kernel (round 1) is kept for comparison (B200_ENC_ATTN=mma: 588 us per launch at batch 16).
+// The default since round 2 is attention_bidir_tc_kernel below (306 us), the same flash-attention recurrence on the
+// 5th-generation tensor cores:
+//   * CTA = 128 query rows of one (batch, head); Q and the K / V tiles (64 rows x 64 dims, 128B-swizzled) arrive by 3-D
+//     TMA boxes straight out of the fused [B, S, 3*H*64] projection (rows beyond S are zero-filled by the TMA unit);
+//   * S_j = Q.K_j^T is one 128 x 64 x 64 UMMA chain (SS form, four tcgen05.mma of K = 16) into 64 TMEM columns; the
+//     score buffer is double-buffered and the MMA warp runs two tiles ahead, so the softmax warps never wait for it;
+//   * four softmax warps own one query row per thread = one TMEM lane: tcgen05.ld brings the row's 64 scores into
+//     registers, row maximum / exp2 / row sum need no shuffles at all, P goes back to TMEM as packed fp16 (tcgen05.st,
+//     double-buffered) and never touches shared memory;
+//   * O += P_j.V_j is a 128 x 64 x 64 UMMA chain with A = P FROM TMEM and B = the V tile as it lies in shared memory
+//     (keys x dims = MN-major B operand: the same TMA image as a K-major tile, only the instruction descriptor's
+//     b_major bit differs);
+//   * the accumulator O (64 TMEM columns) is rescaled lazily (only when a row maximum grew by more than 2^8 since the
+//     maximum the accumulators are expressed in -- the rule of the mma.sync kernel) by the softmax warps between two
+//     P.V chains; warp 4 is the TMA producer (four K / V stages), warp 5 issues the MMAs from one elected lane;
+//   * 256 TMEM columns and 80 KB of shared memory per CTA: two CTAs share an SM.
+// Measured on the way (profiles/r02_encoder_attention.txt): 128-key tiles with S and P sharing columns 426 us; Q.K^T of
+// the next tile under the exponentials 374 us; scores read from TMEM in 32-column pieces instead of 128 live registers
+// (no spills) 326 us; 64-key tiles with both buffers doubled 306 us.  Moving a quarter / a third / half of the
+// exponentials to an FMA-pipe polynomial (the FlashAttention-4 trick) made it SLOWER (348 / 373 / 407 us): the kernel is
+// not MUFU-bound, its softmax warps (two per scheduler) are latency-bound on the barrier / TMEM round trips of each tile.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace b200
 {
@@ -259,9 +281,322 @@ __global__ void __launch_bounds__(128) attention_bidir_kernel(const __half* __re
             *reinterpret_cast<uint32_t*>(ob + (size_t) r1 * H * kD + d) = pack_h2(o[j][2] * i1, o[j][3] * i1);
     }
 }
+
+// =====================================================================================================================
+// tcgen05 / TMEM kernel
+// =====================================================================================================================
+namespace
+{
+constexpr int kTM = 128;                 // query rows per CTA (UMMA M)
+constexpr int kTN = 64;                  // keys per tile
+constexpr int kTcBox = 64 * kD * 2;      // bytes of one TMA box (64 rows x 64 dims): 8 KB; Q = two boxes
+constexpr int kTcStages = 4;             // K / V tiles in flight
+// TMEM columns: S double-buffered, P double-buffered, O -- 256 in all, so two CTAs share an SM's 512
+constexpr uint32_t kTcTmemCols = 256;
+constexpr uint32_t kTcColS = 0;          // [0, 64), [64, 128): fp32 scores of tile j in buffer j & 1
+constexpr uint32_t kTcColP = 128;        // [128, 160), [160, 192): fp16 probabilities, two keys per column
+constexpr uint32_t kTcColO = 192;        // [192, 256): fp32 output accumulator
+// kind::f16, fp32 accumulate, A and B fp16; M = 128, N = 64; Q.K^T: both operands K-major; P.V: B (= V) MN-major
+constexpr uint32_t kIdescQK = (1u << 4) | ((uint32_t) (kTN >> 3) << 17) | ((uint32_t) (kTM >> 4) << 24);
+constexpr uint32_t kIdescPV = (1u << 4) | (1u << 16) | ((uint32_t) (kD >> 3) << 17) | ((uint32_t) (kTM >> 4) << 24);
+constexpr size_t kTcSmem = (size_t) (2 + 2 * kTcStages) * kTcBox + 1024 /* alignment slack */ + 256 /* barriers */;
+} // namespace
+
+struct AttnTcParams
+{
+    __half* out; // [B, S, H * 64]
+    int S, H;
+};
+
+__global__ void __launch_bounds__(192, 2) attention_bidir_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnTcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;                       // 128 rows: two boxes
+    uint8_t* sK = sQ + 2 * kTcBox;
+    uint8_t* sV = sK + kTcStages * kTcBox;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kTcStages * kTcBox);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;                 // [stages]
+    uint64_t* v_full = k_full + kTcStages;
+    uint64_t* k_free = v_full + kTcStages;
+    uint64_t* v_free = k_free + kTcStages;
+    uint64_t* s_full = v_free + kTcStages;       // [2] S = Q.K^T of a tile is in TMEM
+    uint64_t* s_free = s_full + 2;               // [2] the 128 softmax threads have read it for the last time
+    uint64_t* p_full = s_free + 2;               // [2] the 128 softmax threads have written P
+    uint64_t* p_free = p_full + 2;               // [2] the tile's P.V chain has finished
+    uint64_t* o_done = p_free + 2;               // the last P.V chain has finished
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kTM, h = blockIdx.y, b = blockIdx.z;
+    const int S = p.S, H = p.H;
+    const int n_tiles = (S + kTN - 1) / kTN;
+
+    if (threadIdx.x == 0)
+    {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < kTcStages; ++s)
+        {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&k_free[s], 1);
+            mbar_init(&v_free[s], 1);
+        }
+        for (int s = 0; s < 2; ++s)
+        {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_free[s], 128);
+            mbar_init(&p_full[s], 128);
+            mbar_init(&p_free[s], 1);
+        }
+        mbar_init(o_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4 && lane == 0)
+        tma_prefetch_desc(&tmQKV);
+    if (warp == 5)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTcTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 4)
+    {
+        // ---- TMA producer ----
+        if (elect_one_sync())
+        {
+            grid_dep_wait(); // the projection kernel in front of this one wrote qkv
+            mbar_arrive_expect_tx(q_full, 2 * kTcBox);
+            tma_load_3d(sQ, &tmQKV, h * kD, q0, b, q_full);
+            tma_load_3d(sQ + kTcBox, &tmQKV, h * kD, q0 + 64, b, q_full);
+            for (int j = 0; j < n_tiles; ++j)
+            {
+                const int st = j % kTcStages;
+                if (j >= kTcStages)
+                    mbar_wait(&k_free[st], ((j / kTcStages) - 1) & 1);
+                mbar_arrive_expect_tx(&k_full[st], kTcBox);
+                tma_load_3d(sK + st * kTcBox, &tmQKV, (H + h) * kD, j * kTN, b, &k_full[st]);
+                if (j >= kTcStages)
+                    mbar_wait(&v_free[st], ((j / kTcStages) - 1) & 1);
+                mbar_arrive_expect_tx(&v_full[st], kTcBox);
+                tma_load_3d(sV + st * kTcBox, &tmQKV, (2 * H + h) * kD, j * kTN, b, &v_full[st]);
+            }
+        }
+    }
+    else if (warp == 5)
+    {
+        // ---- MMA issuer: the whole warp runs the warp-uniform loop, one elected lane issues ----
+        grid_dep_launch_dependents();
+        mbar_wait(q_full, 0);
+        const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ));
+        // S_j[128 x 64] = Q[128 x 64] . K_j[64 x 64]^T into score buffer j & 1: two tiles ahead of the softmax warps, so
+        // they never wait for the tensor cores
+        auto issue_qk = [&](int j)
+        {
+            const int st = j % kTcStages;
+            mbar_wait(&k_full[st], (j / kTcStages) & 1);
+            tc_fence_after();
+            const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK + st * kTcBox));
+            if (elect_one_sync())
+            {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    tc_mma_ss(tmem_base + kTcColS + (uint32_t) (j & 1) * kTN, qdesc + 2 * k4, kdesc + 2 * k4, kIdescQK, k4 != 0 ? 1u : 0u);
+                tc_commit(&k_free[st]);
+                tc_commit(&s_full[j & 1]);
+            }
+            __syncwarp();
+        };
+        issue_qk(0);
+        if (n_tiles > 1)
+            issue_qk(1);
+        for (int j = 0; j < n_tiles; ++j)
+        {
+            const int st = j % kTcStages, bf = j & 1;
+            const uint32_t ph = (uint32_t) (j >> 1) & 1;
+            mbar_wait(&p_full[bf], ph);
+            mbar_wait(&v_full[st], (j / kTcStages) & 1);
+            tc_fence_after();
+            const uint64_t vdesc = umma_desc_k_sw128(smem_u32(sV + st * kTcBox));
+            if (elect_one_sync())
+            {
+                // O[128 x 64] += P_j[128 x 64] (TMEM, 8 columns per 16 keys) . V_j[64 keys x 64 dims] (MN-major B: 16 keys
+                // = two 8-row swizzle atoms of 1024 bytes)
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    tc_mma_ts(tmem_base + kTcColO, tmem_base + kTcColP + (uint32_t) bf * 32 + 8 * k4, vdesc + 128 * k4, kIdescPV,
+                        (j | k4) != 0 ? 1u : 0u);
+                tc_commit(&v_free[st]);
+                tc_commit(&p_free[bf]);
+                if (j == n_tiles - 1)
+                    tc_commit(o_done);
+            }
+            __syncwarp();
+            if (j + 2 < n_tiles)
+            {
+                mbar_wait(&s_free[bf], ph); // the softmax threads are done with S_j
+                issue_qk(j + 2);
+            }
+        }
+    }
+    else
+    {
+        // ---- softmax warps: thread = query row = TMEM lane ----
+        const uint32_t trow = tmem_base + ((uint32_t) (warp * 32) << 16);
+        const float sl2 = 0.125f * 1.4426950408889634f; // 1/sqrt(64) * log2(e)
+        constexpr float kLazy = 8.0f;
+        float m = -FLT_MAX, l = 0.f; // m: the maximum (raw score units) the accumulators are expressed in
+        for (int j = 0; j < n_tiles; ++j)
+        {
+            const int bf = j & 1;
+            const uint32_t ph = (uint32_t) (j >> 1) & 1;
+            const uint32_t tS = trow + kTcColS + (uint32_t) bf * kTN, tP = trow + kTcColP + (uint32_t) bf * 32;
+            mbar_wait(&s_full[bf], ph);
+            tc_fence_after();
+            const int valid = S - j * kTN; // keys of this tile that exist (>= 64 except in the last tile)
+            // The row's 64 scores are read from TMEM twice, 32 columns at a time (TMEM reads are nowhere near a limit; a
+            // whole row of scores in registers spilled): pass 1 = row maximum, pass 2 = exponentials.  Four independent
+            // max / sum chains instead of one long dependent chain per row.
+            uint32_t ra[32], rb[32];
+            float mx4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+            tc_ld_x32(tS, ra);
+            tc_ld_x32(tS + 32, rb);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+            {
+                const uint32_t* cur = c ? rb : ra;
+                if (valid >= kTN)
+                {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(cur[i]));
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        mx4[i & 3] = fmaxf(mx4[i & 3], 32 * c + i < valid ? __uint_as_float(cur[i]) : -FLT_MAX);
+                }
+            }
+            // every score is in registers now: the Q.K^T of tile j + 2 may overwrite this buffer
+            tc_fence_before();
+            mbar_arrive(&s_free[bf]);
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            const bool grow = (mx - m) * sl2 > kLazy; // always true on the first tile
+            if (__any_sync(0xffffffffu, grow))
+            {
+                const float nm = grow ? fmaxf(m, mx) : m;
+                const float corr = ex2((m - nm) * sl2); // 0 on the first tile, 1 for rows that keep their maximum
+                m = nm;
+                l *= corr;
+                if (j > 0)
+                {
+                    // O is quiet between the previous tile's P.V chain (p_free) and this tile's (it waits for p_full)
+                    mbar_wait(&p_free[bf ^ 1], (uint32_t) ((j - 1) >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t orr[32];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+                    {
+                        tc_ld_x32(trow + kTcColO + 32 * hh, orr);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            orr[i] = __float_as_uint(__uint_as_float(orr[i]) * corr);
+                        tc_st_x32p(trow + kTcColO + 32 * hh, orr);
+                    }
+                }
+            }
+            if (j >= 2)
+            {
+                mbar_wait(&p_free[bf], (uint32_t) ((j - 2) >> 1) & 1); // the P.V chain of tile j - 2 has read this P buffer
+                tc_fence_after();
+            }
+            const float bias = -m * sl2;
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+            {
+                const uint32_t* cur = c ? rb : ra;
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2)
+                {
+                    float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
+                    if (valid < kTN)
+                    {
+                        s0 = 32 * c + i < valid ? s0 : -FLT_MAX;
+                        s1 = 32 * c + i + 1 < valid ? s1 : -FLT_MAX;
+                    }
+                    const float p0 = ex2(fmaf(s0, sl2, bias));
+                    const float p1 = ex2(fmaf(s1, sl2, bias));
+                    rs4[(i >> 1) & 3] += p0 + p1;
+                    pk[i >> 1] = pack_h2(p0, p1); // keys (2c, 2c + 1) = one 32-bit TMEM column of the A operand
+                }
+                tc_st_x16(tP + 16 * c, pk);
+            }
+            l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&p_full[bf]);
+        }
+        // ---- finish: O / l -> fp16 -> global (one 128-byte row per thread) ----
+        mbar_wait(o_done, 0);
+        tc_fence_after();
+        const int r = q0 + warp * 32 + lane;
+        const float inv = 1.f / l;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t) b * S + min(r, S - 1)) * H * kD + (size_t) h * kD);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+        {
+            uint32_t orr[32];
+            tc_ld_x32(trow + kTcColO + 32 * hh, orr);
+            tc_wait_ld();
+            if (r < S)
+            {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    uint4 v;
+                    v.x = pack_h2(__uint_as_float(orr[8 * c + 0]) * inv, __uint_as_float(orr[8 * c + 1]) * inv);
+                    v.y = pack_h2(__uint_as_float(orr[8 * c + 2]) * inv, __uint_as_float(orr[8 * c + 3]) * inv);
+                    v.z = pack_h2(__uint_as_float(orr[8 * c + 4]) * inv, __uint_as_float(orr[8 * c + 5]) * inv);
+                    v.w = pack_h2(__uint_as_float(orr[8 * c + 6]) * inv, __uint_as_float(orr[8 * c + 7]) * inv);
+                    dst[4 * hh + c] = v;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5)
+    {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
+    }
+}
 } // namespace b200
 
 using namespace b200;
+
+static int enc_attn_mode()
+{
+    static int mode = -1; // 0 = tcgen05 (default), 1 = mma.sync (B200_ENC_ATTN=mma)
+    if (mode < 0)
+    {
+        const char* e = getenv("B200_ENC_ATTN");
+        mode = (e != nullptr && e[0] == 'm') ? 1 : 0;
+    }
+    return mode;
+}
 
 extern "C" int b200_attention_bidirectional_fp16(const void* qkv, void* out, int batch_size, int seq_len, int num_heads,
     int head_size, b200_stream_t stream)
@@ -272,6 +607,28 @@ extern "C" int b200_attention_bidirectional_fp16(const void* qkv, void* out, int
     if (batch_size == 0 || seq_len == 0)
         return B200_OK;
     B200_REQUIRE_DEVICE();
+    if (enc_attn_mode() == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+    {
+        // 3-D view [B][S][3*H*64] of the fused projection; a box = 64 dims x 64 rows of one batch element, rows past S
+        // zero-filled
+        CUtensorMap tm;
+        const uint64_t row_bytes = (uint64_t) 3 * num_heads * kD * 2;
+        if (int rc = make_tmap_3d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, qkv, (uint64_t) 3 * num_heads * kD, (uint64_t) seq_len,
+                (uint64_t) batch_size, row_bytes, row_bytes * (uint64_t) seq_len, kD, 64, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B))
+            return rc;
+        static bool attr_tc = false;
+        if (!attr_tc)
+        {
+            B200_CUDA(cudaFuncSetAttribute(attention_bidir_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTcSmem));
+            B200_CUDA(cudaFuncSetAttribute(attention_bidir_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                cudaSharedmemCarveoutMaxShared));
+            attr_tc = true;
+        }
+        AttnTcParams prm{static_cast<__half*>(out), seq_len, num_heads};
+        B200_LAUNCH(attention_bidir_tc_kernel, dim3((seq_len + kTM - 1) / kTM, num_heads, batch_size), dim3(192), kTcSmem,
+            as_stream(stream), tm, prm);
+        return B200_OK;
+    }
     const size_t smem = 5 * (size_t) kTile;
     static bool attr_set = false;
     if (!attr_set)
