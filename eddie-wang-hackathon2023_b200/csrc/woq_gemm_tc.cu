@@ -1277,6 +1277,17 @@ TcPlan plan_tc(int M, int N, int K)
             // of the dequant would run after the dependency resolves; a 16-CTA (non-portable) cluster halves that
             if (g_cluster16 && pl.MT <= 32 && s2 == 8 && kb_total > 8 * 6 && tiles * 16 <= cap && kb_total >= 32)
                 s2 = 16;
+            // 128-row tiles with a shallow K (1280: 20 k-blocks): the 64 KB DSMEM exchange of a split costs more than
+            // the halved main loop saves (1280 -> 5120 at M = 128: 13.4 us split 2-way, slower than the 9.4 us of M = 256
+            // whose 80 tiles run unsplit); keep the split for deep K only
+            static int min_kb128 = -1;
+            if (min_kb128 < 0)
+            {
+                const char* e = getenv("B200_TC_SPLIT128_MIN_KB");
+                min_kb128 = e != nullptr ? atoi(e) : 40;
+            }
+            if (pl.MT == 128 && kb_total < min_kb128)
+                s2 = 1;
             splits = s2;
             cluster = s2 > 1 ? 1 : 0;
         }

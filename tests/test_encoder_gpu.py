@@ -55,3 +55,29 @@ def test_mel_to_tokens_pipeline_matches_oracle():
     dec.set_encoder_output(xa)
     got = dec.decode([prompt] * B, n_new)
     assert got.cpu().tolist() == ref_tokens.tolist()
+
+
+def test_encoder_large_v2_width_full_length_matches_oracle():
+    """The headline encoder shape end to end, not kernel by kernel: large-v2 width (1280, 20 heads), all 1500 frames,
+    4 layers, batch 2 -- the conv stem at full size, the M = 3000 tcgen05 GEMMs with their in-place residual epilogues,
+    the tcgen05 attention over 24 key tiles with a partial last one -- against the oracle encoder
+    (T/tensorrt_llm/models/whisper/model.py:124-172; oracle W/torch_model.py:152-171) with identically dequantized
+    weights."""
+    from b200_whisper.runtime import WhisperEncoder
+    dims = wo.ModelDimensions(80, 1500, 1280, 20, 4, 51865, 448, 1280, 20, 1)
+    B = 2
+    sd = wo.synthetic_state_dict(dims, seed=4)
+    sd = {k: v for k, v in sd.items() if k.startswith("encoder.")}
+    sdq = wo.quantize_state_dict(sd, dims, decoder_only=False)
+    mel = _mel(B, dims, 31)
+    with torch.no_grad():
+        ref = wo.encoder_forward(sdq, dims, mel)
+    enc = WhisperEncoder(dims, sd)
+    out = enc(mel.cuda())
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (B, 1500, 1280) and torch.isfinite(out.float()).all()
+    diff = (out.float().cpu() - ref).abs()
+    scale = max(1.0, ref.abs().max().item())
+    print(f"\n[encoder 1280 x 1500 x 4 layers, B=2] max |diff| {diff.max().item():.4f}, mean {diff.mean().item():.5f}, scale {scale:.2f}")
+    assert diff.max().item() <= 2e-2 * scale, f"encoder output err {diff.max().item()}"
+    assert diff.mean().item() <= 3e-3
