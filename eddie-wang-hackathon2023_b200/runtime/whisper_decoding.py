@@ -315,10 +315,11 @@ class WhisperDecoding:
             else:
                 self._ln(x, lay["cross_ln"], h, rows)
                 self._gemm(h, rows, lay["cross_q"], q, ws=ws)
-            rc = self.lib.b200_cross_attention(q.data_ptr(), ckv_i.data_ptr(), lay["ckv_qo"].data_ptr(),
-                                               ctx.data_ptr(), rows, s_q, H, Dh, self.S_enc, 1, ws.data_ptr(),
-                                               ws.numel(), st)
-            _lib.check(rc, "cross_attention")
+            if not getattr(self, "_measure_without_cross_attention", False):  # bench.py: in-graph cost by difference
+                rc = self.lib.b200_cross_attention(q.data_ptr(), ckv_i.data_ptr(), lay["ckv_qo"].data_ptr(),
+                                                   ctx.data_ptr(), rows, s_q, H, Dh, self.S_enc, 1, ws.data_ptr(),
+                                                   ws.numel(), st)
+                _lib.check(rc, "cross_attention")
             if prefetch and i + 1 < self.L:
                 # layer i's cross-KV is dead now: start pulling layer i+1's while the MLP and the next self-attention run
                 self._side.wait_stream(main)
