@@ -65,10 +65,6 @@ struct TcParams
     int splits;
     int cluster;  // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
     int x3_depth; // > 0: tmX is a 3-D map (64 k, rows, k-blocks) whose box holds this many k-blocks: ONE activation load
-    // decode tiles (x3_depth > 0): the dequant warps fetch the activation tile themselves (plain loads + swizzled shared-memory
-    // stores) right after the dependency resolves instead of the producer issuing a TMA box -- the tile is 10-20 KB that the
-    // previous kernel has just written (L2 hits): the load round trip is shorter than the TMA unit's issue-to-complete time
-    const __half* x_ldg; // non-null: [M, K] activations for that path
     long long* gt;  // optional: 4 global-timer values of this launch (min entry, min dependency return, max store, -)
     long long* dbg; // optional: clock64() stamps of CTA (0,0,0) at the phase boundaries (b200_debug_tc_timing)
 };
@@ -317,7 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         for (int s = 0; s < SS; ++s)
         {
             mbar_init(&full[s], 1);
-            mbar_init(&xfull[s], (s == 0 && p.x_ldg != nullptr) ? (uint32_t) kTcDequantWarps : 1u);
+            mbar_init(&xfull[s], 1);
         }
         fence_mbar_init();
         fence_proxy_async_smem();
@@ -389,11 +385,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
             grid_dep_wait();
             TC_STAMP(15);
             TC_GT(atomicMin, 1);
-            if (p.x_ldg != nullptr)
-            {
-                // the dequant warps load the activation tile (see below)
-            }
-            else if (p.x3_depth > 0)
+            if (p.x3_depth > 0)
             {
                 // the whole k range of this CTA as one 3-D box (a rank with one block less also receives its
                 // neighbour's first block into an unused stage: the byte count is the full box either way)
@@ -547,28 +539,6 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                 TC_STAMP(16 + 4 * i + 1);
             if (i == 0 && tq == 0)
                 TC_STAMP(4);
-            if (p.x_ldg != nullptr && i + 1 == (nkb < AS ? nkb : AS))
-            {
-                // every TMEM stage that needs no MMA to retire first is filled: now wait for the previous kernel and bring
-                // this CTA's activation tile in -- [k-block][row][64 halves], 128B-swizzled exactly as the TMA box would
-                // have written it (16-byte chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4)); rows beyond M are zeros
-                grid_dep_wait();
-                const int total = nkb * MT * 8;
-                for (int idx = tq; idx < total; idx += kDq)
-                {
-                    const int kbi = idx / (MT * 8), rem = idx - kbi * (MT * 8);
-                    const int r = rem >> 3, c = rem & 7;
-                    const int row = m_tile * MT + r;
-                    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                    if (row < p.M)
-                        val = __ldcg(reinterpret_cast<const uint4*>(p.x_ldg + (size_t) row * p.K + (size_t) (kb_begin + kbi) * 64 + c * 8));
-                    *reinterpret_cast<uint4*>(smX + kbi * XTileBytes + r * 128 + ((c ^ (r & 7)) << 4)) = val;
-                }
-                fence_proxy_async_smem(); // generic-proxy stores -> visible to the tensor core's (async proxy) reads
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(&xfull[0]);
-            }
         }
 
         const int m_valid = min(MT, p.M - m_tile * MT);
@@ -1510,8 +1480,6 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
         return rc;
     TcParams p{};
     p.x3_depth = x3_depth;
-    static const bool xldg_enabled = getenv("B200_TC_XLDG") == nullptr || getenv("B200_TC_XLDG")[0] != '0';
-    p.x_ldg = (x3_depth > 0 && xldg_enabled) ? A : nullptr;
     p.scales = scales;
     p.bias = bias;
     p.residual = residual;
