@@ -1,4 +1,4 @@
-"""One weight-only GEMM launch of a given shape (for ncu captures): python tools/gemm_one.py M K N"""
+"""One weight-only GEMM launch of a given shape (for ncu captures): python tools/gemm_one.py M K N [gelu]"""
 import os
 import sys
 
@@ -16,8 +16,14 @@ p, s = bw.ops.symmetric_quantize_last_axis_of_batched_matrix(w, torch.int8)
 x = (torch.rand((m, k), device=dev) * 2 - 1).half()
 o = torch.empty((m, n), dtype=torch.float16, device=dev)
 wk = torch.empty((lib.b200_woq_workspace_bytes(m, n, k),), dtype=torch.uint8, device=dev)
+gelu = len(sys.argv) > 4 and sys.argv[4] == "gelu"
+bias = (torch.rand((n,), device=dev) * 0.1).half()
 for _ in range(3):
-    lib.b200_woq_int8_gemm(x.data_ptr(), m, k, p.data_ptr(), s.data_ptr(), n, o.data_ptr(), wk.data_ptr(), wk.numel(),
-                           torch.cuda.current_stream().cuda_stream)
+    if gelu:  # the fc1 launch of the encoder: bias + erf GELU in the epilogue
+        lib.b200_woq_int8_gemm_fused(x.data_ptr(), m, k, p.data_ptr(), s.data_ptr(), n, bias.data_ptr(), _lib.ACT_GELU_ERF, None,
+                                     o.data_ptr(), wk.data_ptr(), wk.numel(), torch.cuda.current_stream().cuda_stream)
+    else:
+        lib.b200_woq_int8_gemm(x.data_ptr(), m, k, p.data_ptr(), s.data_ptr(), n, o.data_ptr(), wk.data_ptr(), wk.numel(),
+                               torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 print("done")
