@@ -8,7 +8,7 @@
 // conflict-free); scores and P.V run on the tensor cores (mma.sync.m16n8k16, fp32 accumulate), the online softmax
 // lives in registers (ex2 with the scale folded into one FFMA, lazily rescaled accumulators), the score accumulators are re-used in place as the fp16 A fragments of P.
 // That warp-level mma.sync kernel (round 1) is kept for comparison (B200_ENC_ATTN=mma: 588 us per launch at batch 16).
-// The default since round 2 is attention_bidir_tc_kernel below (306 us), the same flash-attention recurrence on the
+// The default since round 2 is attention_bidir_tc_kernel below (277 us), the same flash-attention recurrence on the
 // 5th-generation tensor cores:
 //   * CTA = 128 query rows of one (batch, head); Q and the K / V tiles (64 rows x 64 dims, 128B-swizzled) arrive by 3-D
 //     TMA boxes straight out of the fused [B, S, 3*H*64] projection (rows beyond S are zero-filled by the TMA unit);
@@ -26,9 +26,12 @@
 //   * 256 TMEM columns and 80 KB of shared memory per CTA: two CTAs share an SM.
 // Measured on the way (profiles/r02_encoder_attention.txt): 128-key tiles with S and P sharing columns 426 us; Q.K^T of
 // the next tile under the exponentials 374 us; scores read from TMEM in 32-column pieces instead of 128 live registers
-// (no spills) 326 us; 64-key tiles with both buffers doubled 306 us.  Moving a quarter / a third / half of the
-// exponentials to an FMA-pipe polynomial (the FlashAttention-4 trick) made it SLOWER (348 / 373 / 407 us): the kernel is
-// not MUFU-bound, its softmax warps (two per scheduler) are latency-bound on the barrier / TMEM round trips of each tile.
+// (no spills) 326 us; 64-key tiles with both buffers doubled 306 us; key masking hoisted out of the per-element path (ncu:
+// ISETP + FSEL were 22 % of all instructions, on every tile) 284 us; one redundant barrier wait per tile removed 277 us.
+// Moving part of the exponentials to an FMA-pipe polynomial (the FlashAttention-4 trick, ex2_fma / B200_ATTN_POLY_EVERY)
+// is neutral to slower at every stage (348 / 373 / 407 us at a quarter / third / half on the 326 us version; 293 / 286 us
+// at 1/4 and 1/8 on the 284 us version): the kernel is not MUFU-bound, its softmax warps (two per scheduler) are
+// latency-bound on the barrier / TMEM round trips of each tile.
 #include <float.h>
 #include <stdlib.h>
 
@@ -77,6 +80,21 @@ __device__ __forceinline__ float ex2(float x)
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// 2^x on the FMA pipe (x <= ~8): round-to-nearest split x = n + f, |f| <= 0.5, degree-4 polynomial of 2^f (relative
+// error 4e-5, a tenth of the fp16 rounding P gets anyway), n added to the exponent field (the FlashAttention-4 trick for
+// kernels whose exponentials saturate the MUFU unit: 16 per clock per SM)
+__device__ __forceinline__ float ex2_fma(float x)
+{
+    x = fmaxf(x, -126.f);
+    const float t = x + 12582912.f; // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(f, 0.0096181291f, 0.0555041087f);
+    p = fmaf(p, f, 0.2402265070f);
+    p = fmaf(p, f, 0.6931471806f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b)
@@ -299,6 +317,10 @@ constexpr uint32_t kTcColO = 192;        // [192, 256): fp32 output accumulator
 // kind::f16, fp32 accumulate, A and B fp16; M = 128, N = 64; Q.K^T: both operands K-major; P.V: B (= V) MN-major
 constexpr uint32_t kIdescQK = (1u << 4) | ((uint32_t) (kTN >> 3) << 17) | ((uint32_t) (kTM >> 4) << 24);
 constexpr uint32_t kIdescPV = (1u << 4) | (1u << 16) | ((uint32_t) (kD >> 3) << 17) | ((uint32_t) (kTM >> 4) << 24);
+#ifndef B200_ATTN_POLY_EVERY
+#define B200_ATTN_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = B200_ATTN_POLY_EVERY; // every n-th pair of probabilities takes the FMA-pipe exponential (0: none)
 constexpr size_t kTcSmem = (size_t) (2 + 2 * kTcStages) * kTcBox + 1024 /* alignment slack */ + 256 /* barriers */;
 } // namespace
 
@@ -469,22 +491,23 @@ __global__ void __launch_bounds__(192, 2) attention_bidir_tc_kernel(const __grid
             tc_ld_x32(tS, ra);
             tc_ld_x32(tS + 32, rb);
             tc_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
+            if (valid < kTN)
             {
-                const uint32_t* cur = c ? rb : ra;
-                if (valid >= kTN)
-                {
+                // the last tile only: keys beyond S become -FLT_MAX once, here, so neither pass carries a per-element
+                // predicate (ncu: as written before, ISETP + FSEL were 22 % of the kernel's instructions on EVERY tile)
+                const uint32_t neg = __float_as_uint(-FLT_MAX);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(cur[i]));
-                }
-                else
+                for (int i = 0; i < 32; ++i)
                 {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        mx4[i & 3] = fmaxf(mx4[i & 3], 32 * c + i < valid ? __uint_as_float(cur[i]) : -FLT_MAX);
+                    ra[i] = i < valid ? ra[i] : neg;
+                    rb[i] = 32 + i < valid ? rb[i] : neg;
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+            {
+                mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(ra[i]));
+                mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(rb[i]));
             }
             // every score is in registers now: the Q.K^T of tile j + 2 may overwrite this buffer
             tc_fence_before();
@@ -515,11 +538,8 @@ __global__ void __launch_bounds__(192, 2) attention_bidir_tc_kernel(const __grid
                     }
                 }
             }
-            if (j >= 2)
-            {
-                mbar_wait(&p_free[bf], (uint32_t) ((j - 2) >> 1) & 1); // the P.V chain of tile j - 2 has read this P buffer
-                tc_fence_after();
-            }
+            // (this P buffer was last read by the P.V chain of tile j - 2: the MMA warp issued it BEFORE the Q.K^T chain of
+            // tile j, and s_full[j] -- a tcgen05.commit after that chain -- has been waited for above, so it is done)
             const float bias = -m * sl2;
             float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -530,14 +550,18 @@ __global__ void __launch_bounds__(192, 2) attention_bidir_tc_kernel(const __grid
 #pragma unroll
                 for (int i = 0; i < 32; i += 2)
                 {
-                    float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
-                    if (valid < kTN)
+                    const float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
+                    float p0, p1;
+                    if (kPolyEvery > 0 && ((i >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0)
                     {
-                        s0 = 32 * c + i < valid ? s0 : -FLT_MAX;
-                        s1 = 32 * c + i + 1 < valid ? s1 : -FLT_MAX;
+                        p0 = ex2_fma(fmaf(s0, sl2, bias));
+                        p1 = ex2_fma(fmaf(s1, sl2, bias));
                     }
-                    const float p0 = ex2(fmaf(s0, sl2, bias));
-                    const float p1 = ex2(fmaf(s1, sl2, bias));
+                    else
+                    {
+                        p0 = ex2(fmaf(s0, sl2, bias));
+                        p1 = ex2(fmaf(s1, sl2, bias));
+                    }
                     rs4[(i >> 1) & 3] += p0 + p1;
                     pk[i >> 1] = pack_h2(p0, p1); // keys (2c, 2c + 1) = one 32-bit TMEM column of the A operand
                 }
