@@ -841,14 +841,28 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
     {
         const int bh = blockIdx.x + r * gridDim.x;
         uint32_t bq[8];
+        float koff = 0.f; // int8 cache: 1152 * sum of q over the 64 dims, the bias of the 1024 + byte key values (xa_chunk KOFF)
         {
             const uint32_t u[8] = {qn0.x, qn0.y, qn0.z, qn0.w, qn1.x, qn1.y, qn1.z, qn1.w}; // u[j] = (d2j, d2j+1)
+            float qs = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
                 // B fragment of the score MMA: q is column 0, i.e. only the lanes of key group 0 carry it
                 bq[2 * j] = kl == 0 ? __byte_perm(u[2 * j], u[2 * j + 1], 0x5410) : 0u;     // (d4j, d4j+2)
                 bq[2 * j + 1] = kl == 0 ? __byte_perm(u[2 * j], u[2 * j + 1], 0x7632) : 0u; // (d4j+1, d4j+3)
+                if constexpr (INT8)
+                {
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u[2 * j]));
+                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u[2 * j + 1]));
+                    qs += (f0.x + f0.y) + (f1.x + f1.y);
+                }
+            }
+            if constexpr (INT8)
+            {
+                qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+                qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+                koff = 1152.f * qs;
             }
         }
         if (r + 1 < nbh)
@@ -869,10 +883,13 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
             mbar_wait(&bars[s], (i / ST) & 1);
             const uint8_t* kst = ring + s * kStageBytes + (size_t) (kl * kDh + chunk * 16) * ESZ;
             const uint8_t* vst = kst + kHalfBytes;
+            // int8 cache: the keys enter the score MMA as 1024 + byte (PRMT only), the constant part is removed once per
+            // (row, head) through koff -- 8 HSUB2 fewer per 8 keys in a loop whose issue slots are its limit (ncu source
+            // view of the round-1 kernel: 128 PRMT + 128 HADD2 of 471 instructions per 64-key chunk)
             if (nk == CK)
-                xa_chunk<INT8, NIT, true>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o);
+                xa_chunk<INT8, NIT, true, INT8>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o, koff);
             else
-                xa_chunk<INT8, NIT, false>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o);
+                xa_chunk<INT8, NIT, false, INT8>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o, koff);
             __syncwarp();
             if (lane == 0 && i + ST < tot)
                 issue(i + ST, s);
