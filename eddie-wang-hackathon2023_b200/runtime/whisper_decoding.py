@@ -104,6 +104,10 @@ class WhisperDecoding:
             self.layers.append(lay)
         # LayerNorm -> Linear pairs run as ONE kernel (B200_FUSE_LN=0: separate LayerNorm launch, for A/B timing)
         self.fuse_ln = os.environ.get("B200_FUSE_LN", "1") != "0"
+        # qkv projection + self-attention of the generation step as ONE kernel (csrc/qkv_mmha.cu).  Opt-in
+        # (B200_FUSE_QKV_MMHA=1 or .fuse_qkv_mmha = True): parity-green, but measured slower than the two tuned kernels it
+        # replaces (8.5 vs 7.6 us per layer at batch 16, step 1.38 vs 1.29 ms)
+        self.fuse_qkv_mmha = os.environ.get("B200_FUSE_QKV_MMHA", "0") == "1"
         if self.fuse_ln:
             st0 = torch.cuda.current_stream(dev).cuda_stream
             for lay in self.layers:
@@ -285,15 +289,28 @@ class WhisperDecoding:
         if prefetch:
             self._side.wait_stream(main)
             self._prefetch(0)
+        # generation phase: LayerNorm + qkv projection + self-attention as ONE kernel per layer (csrc/qkv_mmha.cu)
+        fused_qkv = (not context and self.fuse_ln and self.fuse_qkv_mmha and s_q == 1
+                     and self.lib.b200_qkv_mmha_decode_supported(nb, H, Dh) == 1)
         for i, lay in enumerate(self.layers):
-            if self.fuse_ln:
+            kv_i = self.self_kv[i] if nb == self.B else self.self_kv[i][b0:b0 + nb]
+            ckv_i = self.cross_kv[i] if nb == self.B else self.cross_kv[i][b0:b0 + nb]
+            if fused_qkv:
+                lin = lay["qkv"]
+                rc = self.lib.b200_qkv_mmha_decode(
+                    x.data_ptr(), lay["attn_ln"][0].data_ptr(), lin.c1s.data_ptr(), lin.c2.data_ptr(), 1e-5,
+                    lin.weight.data_ptr(), lin.scales.data_ptr(), lin.bias.data_ptr() if lin.bias is not None else None,
+                    kv_i.data_ptr(), self.seq_len[b0:b0 + nb].data_ptr(), lay["kv_oq"].data_ptr(), lay["kv_qo"].data_ptr(),
+                    ctx.data_ptr(), nb, H, Dh, self.Smax, st)
+                _lib.check(rc, "qkv_mmha_decode")
+            elif self.fuse_ln:
                 self._gemm_ln(x, lay["attn_ln"], rows, lay["qkv"], qkv, ws=ws)
             else:
                 self._ln(x, lay["attn_ln"], h, rows)
                 self._gemm(h, rows, lay["qkv"], qkv, ws=ws)
-            kv_i = self.self_kv[i] if nb == self.B else self.self_kv[i][b0:b0 + nb]
-            ckv_i = self.cross_kv[i] if nb == self.B else self.cross_kv[i][b0:b0 + nb]
-            if context:
+            if fused_qkv:
+                pass
+            elif context:
                 rc = self.lib.b200_attention_context(
                     qkv.data_ptr(), input_lengths.data_ptr() if input_lengths is not None else None, ctx.data_ptr(),
                     kv_i.data_ptr(), lay["kv_oq"].data_ptr(), nb, s_q, H, Dh, self.Smax, 1, 1.0, st)

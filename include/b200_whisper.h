@@ -180,6 +180,26 @@ typedef struct b200_mmha_params
 int b200_mmha_generation(const b200_mmha_params* params, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Generation phase, first two operators of a decoder layer as ONE kernel:
+ *     LayerNorm -> fused qkv projection (int8 weight-only + bias) -> masked self-attention over the int8 KV cache.
+ * Replaces, for the decoder step, the sequence  weight-only matmul plugin enqueue (weightOnlyQuantMatmulPlugin.cpp:162-222)
+ * -> bias layer -> GPTAttention plugin enqueueGeneration (gptAttentionCommon.cpp:649-780)  of  T/tensorrt_llm/models/whisper/
+ * model.py:74-118, i.e. b200_woq_int8_gemm_ln_folded + b200_mmha_generation here: both operators are head-local, so a
+ * thread-block cluster per head computes the head's 192 projection columns (split over k), exchanges the partial sums
+ * through distributed shared memory and runs the head's attention on the result -- one kernel boundary and one round
+ * trip of q / k / v through L2 fewer per layer (csrc/qkv_mmha.cu).
+ * x [B, d] fp16 raw residual rows (d = num_heads * 64); ln_gamma [d] fp16; c1s / c2 [3d] fp32 from b200_woq_ln_fold_prepare;
+ * Wproc / scales / bias: the qkv Linear (N = 3d) as for b200_woq_int8_gemm_ln_folded; kv_cache [B, 2, H, max_seq_len, 64]
+ * int8 (row sequence_lengths[b] is written); out [B, d] fp16.  batch_size <= 16.  b200_qkv_mmha_decode_supported tells
+ * whether a shape is handled (otherwise call the two operators).
+ * ---------------------------------------------------------------------------------------------- */
+int b200_qkv_mmha_decode_supported(int batch_size, int num_heads, int head_size);
+int b200_qkv_mmha_decode(const void* x, const void* ln_gamma, const float* c1s, const float* c2, float ln_eps,
+    const int8_t* Wproc, const void* scales, const void* bias, void* kv_cache, const int32_t* sequence_lengths,
+    const float* kv_scale_orig_quant, const float* kv_scale_quant_orig, void* out, int batch_size, int num_heads,
+    int head_size, int max_seq_len, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Context (prompt) phase: causal attention over S tokens per sequence + KV cache fill (optionally int8).
  * Replaces  GPTAttentionPluginCommon::enqueueContext  T/cpp/tensorrt_llm/plugins/gptAttentionCommon/gptAttentionCommon.cpp:361-620
  *           (add_fusedQKV_bias_transpose, transpose4dBatchMajorKVCache T/cpp/tensorrt_llm/kernels/unfusedAttentionKernels.cu:1106-1490,1552-1646,

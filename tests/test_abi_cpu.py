@@ -133,10 +133,13 @@ def test_tc_launch_plan_for_the_decoder_shapes(lib):
     assert plan(16, 5120, 1280) == (16, 1, 40, 4, 1)   # 160 CTAs: two per SM on a few SMs
     assert plan(16, 1280, 5120) == (16, 1, 10, 8, 1)   # 10 k-blocks per CTA = the whole weight ring
     assert plan(1, 3840, 1280)[0] == 16 and plan(1, 3840, 1280)[4] == 1
-    mt, mtiles, ntiles, splits, cluster = plan(128, 3840, 1280)
+    # 128-row tiles split K only when K is deep (round 2: the 64 KB DSMEM exchange of a split cost more than it saved at
+    # K = 1280 -- 1280 -> 5120 at M = 128 was slower than at M = 256, profiles/r02_gemm_sweep_midM.txt)
+    assert plan(128, 3840, 1280) == (128, 1, 30, 1, 0) and plan(128, 5120, 1280) == (128, 1, 40, 1, 0)
+    mt, mtiles, ntiles, splits, cluster = plan(128, 1280, 5120)
     assert mt == 128 and cluster == 1 and 2 <= splits <= 8
-    # fewer 256-row tiles than SMs: 128-row tiles instead (twice the CTAs, cluster split-K still available)
-    assert plan(256, 3840, 1280) == (128, 2, 30, 2, 1) and plan(256, 1280, 5120) == (128, 2, 10, 4, 1)
+    # fewer 256-row tiles than SMs: 128-row tiles instead (twice the CTAs, cluster split-K still available for deep K)
+    assert plan(256, 3840, 1280) == (128, 2, 30, 1, 0) and plan(256, 1280, 5120) == (128, 2, 10, 4, 1)
     assert plan(1500, 1280, 5120) == (128, 12, 10, 1, 0) and plan(1500, 3840, 1280)[:4] == (256, 6, 30, 1)
     assert plan(24000, 3840, 1280)[:4] == (256, 94, 30, 1)
     for m, n, k in [(16, 3840, 1280), (16, 1280, 5120), (32, 1280, 1280), (32, 3840, 1280), (4, 1280, 1280)]:
