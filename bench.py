@@ -458,7 +458,9 @@ def main():
     # Both get a roofline entry; `roofline` is the GEMM family, `roofline_cross_attention` the attention kernel.
     peak, peak_src = measured_peak()
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")  # dram bytes per launch from the round's ncu --set full captures
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f)
