@@ -787,7 +787,8 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
     const int chunk = lane & 3, kl = lane >> 2;
     uint8_t* ring = smem + (size_t) warp * ST * kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) W * ST * kStageBytes) + warp * ST;
-    float* parts = reinterpret_cast<float*>(smem + (size_t) W * ST * kStageBytes + sizeof(uint64_t) * W * ST); // [2][W][68]
+    // (barrier block rounded up to 16 bytes: the partials are read as float4 -- an odd W * ST, config E, misaligned them)
+    float* parts = reinterpret_cast<float*>(smem + (size_t) W * ST * kStageBytes + ((sizeof(uint64_t) * W * ST + 15) & ~size_t(15))); // [2][W][68]
 
     const int RH = p.B * p.H;
     const int nbh = (RH - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x; // pairs of this CTA (>= 1)
@@ -1139,7 +1140,7 @@ static XaPlan xattn_plan(int R, int H, int S, int int8)
     {
         const int slots = num_sms() * kOCC[g_xa_cfg];
         pl.blocks = R * H < slots ? R * H : slots;
-        pl.smem = (size_t) W * ST * 2 * ck * kDh * (int8 ? 1 : 2) + sizeof(uint64_t) * W * ST
+        pl.smem = (size_t) W * ST * 2 * ck * kDh * (int8 ? 1 : 2) + ((sizeof(uint64_t) * W * ST + 15) & ~size_t(15))
             + sizeof(float) * 2 * W * (kDh + 4);
         pl.ws_bytes = 0;
         return pl;
