@@ -83,6 +83,8 @@ _SIGS = {
     "b200_debug_tc_timeline": (_i, [_vp, _i]),
     "b200_mmha_generation": (_i, [ctypes.POINTER(MmhaParams), _vp]),
     "b200_qkv_mmha_decode_supported": (_i, [_i, _i, _i]),
+    "b200_cross_attention_qproj_supported": (_i, [_i, _i, _i, _i]),
+    "b200_cross_attention_qproj": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_qkv_mmha_decode": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_attention_context": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "b200_mmha_generation_paged": (_i, [ctypes.POINTER(MmhaParams), _vp, _i, _i, _vp]),

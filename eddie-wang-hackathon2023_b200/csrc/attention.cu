@@ -948,6 +948,338 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
     }
 }
 
+// ---- cross attention with its q projection inside ("q-fused row-head" kernel, generation phase, int8 cache) -------
+// One launch per layer instead of two: the LayerNorm-folded q projection (x -> LN -> Wq, the `cross_q` GEMM of the chain)
+// is computed by the attention CTAs themselves.  What this buys is not the projection's arithmetic (82 k MACs per
+// (row, head)) but a kernel boundary: the cross-KV stream -- 61 MB per layer at batch 16, the largest byte stream of the
+// step -- starts when the self-attention output projection finishes instead of one 3 us projection kernel later, and the
+// q projection runs under the cover of the ring's first fill (W x ST x 8 KB per SM).
+//  * CTA -> (head h, a contiguous run of batch rows): CTAs c, c + H, c + 2H, ... serve head c % H and split the B rows
+//    of that head between them (148 CTAs, 20 heads, 16 rows: 2 or 3 rows per CTA -- the same 3-pair critical path as the
+//    round-robin dealing of the plain row-head kernel), so ONE 64-column slice of Wq (K x 64 int8) serves all pairs of
+//    the CTA.
+//  * q = LN(x) Wq on mma.sync m16n8k16: the CTA's rows are rows 0..7 of A, the warps split K in 64-wide blocks.  The
+//    reference weight layout stores, per column and k-block, four 16-byte chunks whose 32-bit words are exactly the
+//    B fragments of four consecutive k16 steps; a lane loads the whole 16-byte chunk `t = lane % 4` (coalesced: a quad
+//    reads 64 contiguous bytes, a column pair 128) and the k order inside the block is permuted consistently for A
+//    (lane (g, t) feeds x[row g][64 kb + 16 t + ...]), which a dot product does not notice.  Same arithmetic as the
+//    folded GEMM: exact integers x gamma rounded to fp16 (HMUL2), fp32 accumulation, then
+//    q = fp16(fp16(rstd * (scale * acc - mean * c1s) + c2) + bias)   (b200_woq_ln_fold_prepare supplies c1s, c2).
+//  * weights, gamma, scales and the first ring stages are requested BEFORE griddepcontrol.wait (static data).
+struct XqParams
+{
+    const __half* x;      // [B, K] raw residual rows, K = H * 64
+    const uint8_t* W;     // processed int8 weight of the q Linear, [K/2][2K] bytes (N = K)
+    const __half* scales; // [K]
+    const __half* bias;   // [K] or null
+    const __half* gamma;  // [K]
+    const float* c1s;     // [K]
+    const float* c2;      // [K]
+    const void* kv;       // [B, 2, H, S, 64] offset-binary int8
+    const float* scale_quant_orig;
+    __half* out;          // [B, K]
+    int B, H, S, nch;
+    int maxr;             // rows per CTA the shared-memory layout is sized for (<= 8)
+    float eps, inv_sqrt_dh;
+};
+
+constexpr int kXqMaxKb = 2; // 64-wide k-blocks per warp (H <= 2 * warps)
+
+template <typename CFG>
+__global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_qproj_kernel(const XqParams p)
+{
+    constexpr int W = CFG::W, ST = CFG::ST, CK = CFG::CK;
+    constexpr int NIT = CK / 8;
+    constexpr int kHalfBytes = CK * kDh;
+    constexpr int kStageBytes = 2 * kHalfBytes;
+    constexpr int kPart = kDh + 4;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = lane & 3, kl = lane >> 2; // attention: 16-dim slice / key group;  projection: t / g of the fragments
+    uint8_t* ring = smem + (size_t) warp * ST * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) W * ST * kStageBytes) + warp * ST;
+    float* parts = reinterpret_cast<float*>(smem + (size_t) W * ST * kStageBytes + ((sizeof(uint64_t) * W * ST + 15) & ~size_t(15))); // [2][W][68]
+    float* qpart = parts + 2 * W * kPart;                       // [W][maxr][64] partial projections (one per k range)
+    float* stat = qpart + (size_t) W * p.maxr * kDh;            // [W][maxr][2] partial sums of (x - x0), (x - x0)^2
+    float* x0s = stat + (size_t) W * p.maxr * 2;                // [maxr (rounded up to even)] x0 of every row
+    __half* qs = reinterpret_cast<__half*>(x0s + ((p.maxr + 1) & ~1)); // [maxr][64] finished q rows
+
+    const int K = p.H * kDh, nkb = p.H;
+    // this CTA's head and rows
+    const int h = (int) blockIdx.x % p.H, idx = (int) blockIdx.x / p.H;
+    const int nc = ((int) gridDim.x - h + p.H - 1) / p.H; // CTAs serving head h
+    const int row0 = idx * p.B / nc, nr = (idx + 1) * p.B / nc - row0; // 1 <= nr <= maxr (host guarantees)
+    const int wc0 = warp * p.nch / W, wc1 = (warp + 1) * p.nch / W;
+    const int n_w = wc1 - wc0;
+    const int tot = nr * n_w;
+
+    if (lane == 0)
+    {
+        for (int s = 0; s < ST; ++s)
+            mbar_init(&bars[s], 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+    }
+    __syncwarp();
+    grid_dep_launch_dependents();
+
+    const uint64_t pol = policy_evict_first();
+    auto issue = [&](int i, int s)
+    {
+        const int r = i / n_w, ch = wc0 + (i - r * n_w);
+        const int b = row0 + r;
+        const int key0 = ch * CK;
+        const int nk = min(CK, p.S - key0);
+        const uint32_t bytes = (uint32_t) nk * kDh;
+        const uint8_t* kb = static_cast<const uint8_t*>(p.kv) + (((size_t) (b * 2 + 0) * p.H + h) * p.S + key0) * (size_t) kDh;
+        const uint8_t* vb = static_cast<const uint8_t*>(p.kv) + (((size_t) (b * 2 + 1) * p.H + h) * p.S + key0) * (size_t) kDh;
+        mbar_arrive_expect_tx(&bars[s], 2 * bytes);
+        bulk_g2s_hint(ring + s * kStageBytes, kb, bytes, &bars[s], pol);
+        bulk_g2s_hint(ring + s * kStageBytes + kHalfBytes, vb, bytes, &bars[s], pol);
+    };
+    // the cache is static inside a decoder step: the stream starts before the dependency wait
+    if (lane == 0)
+    {
+        for (int j = 0; j < ST && j < tot; ++j)
+            issue(j, j);
+    }
+
+    // ---- static operands of the projection: this warp's k-blocks of the head's 64 weight columns, gamma, and the
+    // per-column vectors of the outputs this thread will finish ----
+    const int kb0 = warp * nkb / W, nkw = (warp + 1) * nkb / W - kb0; // 0 .. kXqMaxKb
+    uint4 wv[kXqMaxKb][8], gv[kXqMaxKb][2];
+#pragma unroll
+    for (int j = 0; j < kXqMaxKb; ++j)
+    {
+        if (j < nkw)
+        {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+            {
+                const int n = h * kDh + 8 * nt + kl;
+                wv[j][nt] = __ldg(reinterpret_cast<const uint4*>(
+                    p.W + (size_t) (n >> 1) * 2 * K + (n & 1) * 64 + (size_t) (kb0 + j) * 128 + chunk * 16));
+            }
+            const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma + (size_t) (kb0 + j) * 64 + chunk * 16);
+            gv[j][0] = __ldg(g4);
+            gv[j][1] = __ldg(g4 + 1);
+        }
+    }
+    const int fr = (int) threadIdx.x >> 6, fc = (int) threadIdx.x & 63; // finishing thread: row slot, column of the head
+    float f_scale = 0.f, f_c1 = 0.f, f_c2 = 0.f, f_bias = 0.f;
+    if (fr < nr)
+    {
+        const int n = h * kDh + fc;
+        f_scale = __half2float(__ldg(p.scales + n));
+        f_c1 = __ldg(p.c1s + n);
+        f_c2 = __ldg(p.c2 + n);
+        if (p.bias != nullptr)
+            f_bias = __half2float(__ldg(p.bias + n));
+    }
+    const float s_qo = __ldg(p.scale_quant_orig);
+    const float sscale = s_qo * p.inv_sqrt_dh * 1.4426950408889634f;
+
+    grid_dep_wait(); // x comes from the previous kernel
+
+    // ---- q projection of the CTA's rows ----
+    {
+        const bool live = kl < nr; // fragment row g = kl carries batch row row0 + g
+        const __half* xrow = p.x + (size_t) (row0 + (live ? kl : 0)) * K;
+        uint4 xa[kXqMaxKb][2];
+        float sh = 0.f;
+        if (live)
+            sh = __half2float(__ldcg(xrow));
+#pragma unroll
+        for (int j = 0; j < kXqMaxKb; ++j)
+        {
+            xa[j][0] = xa[j][1] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < nkw && live)
+            {
+                const uint4* x4 = reinterpret_cast<const uint4*>(xrow + (size_t) (kb0 + j) * 64 + chunk * 16);
+                xa[j][0] = __ldcg(x4);
+                xa[j][1] = __ldcg(x4 + 1);
+            }
+        }
+        float acc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int j = 0; j < kXqMaxKb; ++j)
+        {
+            if (j < nkw)
+            {
+                const uint32_t a_lo[4] = {xa[j][0].x, xa[j][0].y, xa[j][0].z, xa[j][0].w};
+                const uint32_t a_hi[4] = {xa[j][1].x, xa[j][1].y, xa[j][1].z, xa[j][1].w};
+                const uint32_t g_lo[4] = {gv[j][0].x, gv[j][0].y, gv[j][0].z, gv[j][0].w};
+                const uint32_t g_hi[4] = {gv[j][1].x, gv[j][1].y, gv[j][1].z, gv[j][1].w};
+                if (live)
+                {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                    {
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&a_lo[c]));
+                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&a_hi[c]));
+                        const float d0 = f0.x - sh, d1 = f0.y - sh, d2 = f1.x - sh, d3 = f1.y - sh;
+                        sa += (d0 + d1) + (d2 + d3);
+                        sb = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sb))));
+                    }
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                {
+                    const uint32_t ww[4] = {wv[j][nt].x, wv[j][nt].y, wv[j][nt].z, wv[j][nt].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                    {
+                        __half2 lo, hi;
+                        dequant_word(ww[c], lo, hi);
+                        const __half2 b0 = __hmul2(lo, *reinterpret_cast<const __half2*>(&g_lo[c]));
+                        const __half2 b1 = __hmul2(hi, *reinterpret_cast<const __half2*>(&g_hi[c]));
+                        mma_m16n8k16(acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3], a_lo[c], 0u, a_hi[c], 0u, h2u(b0), h2u(b1));
+                    }
+                }
+            }
+        }
+        sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+        sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+        sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+        sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+        if (live)
+        {
+            float* qp = qpart + ((size_t) warp * p.maxr + kl) * kDh + 2 * chunk;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+                *reinterpret_cast<float2*>(qp + 8 * nt) = make_float2(acc[nt][0], acc[nt][1]);
+            if (chunk == 0)
+            {
+                *reinterpret_cast<float2*>(stat + ((size_t) warp * p.maxr + kl) * 2) = make_float2(sa, sb);
+                if (warp == 0)
+                    x0s[kl] = sh;
+            }
+        }
+        __syncthreads();
+        if (fr < nr)
+        {
+            float sum = 0.f, ta = 0.f, tb = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < W; ++w2)
+            {
+                sum += qpart[((size_t) w2 * p.maxr + fr) * kDh + fc];
+                const float2 st2 = *reinterpret_cast<const float2*>(stat + ((size_t) w2 * p.maxr + fr) * 2);
+                ta += st2.x;
+                tb += st2.y;
+            }
+            const float x0 = x0s[fr];
+            const float rk = 1.f / (float) K;
+            const float mean = x0 + ta * rk;
+            const float var = fmaxf((tb - ta * ta * rk) * rk, 0.f);
+            const float rstd = rsqrtf(var + p.eps);
+            const float y = rstd * (sum * f_scale - mean * f_c1) + f_c2;
+            __half o = __float2half_rn(y);
+            if (p.bias != nullptr)
+                o = __float2half_rn(__half2float(o) + f_bias);
+            qs[fr * kDh + fc] = o;
+        }
+        __syncthreads();
+    }
+
+    int i = 0;
+    for (int r = 0; r < nr; ++r)
+    {
+        const int bh = (row0 + r) * p.H + h;
+        uint32_t bq[8];
+        float koff = 0.f; // 1152 * sum of q over the 64 dims, the bias of the 1024 + byte key values (xa_chunk KOFF)
+        {
+            const uint4* qsrc = reinterpret_cast<const uint4*>(qs + r * kDh + chunk * 16);
+            const uint4 qn0 = qsrc[0], qn1 = qsrc[1];
+            const uint32_t u[8] = {qn0.x, qn0.y, qn0.z, qn0.w, qn1.x, qn1.y, qn1.z, qn1.w}; // u[j] = (d2j, d2j+1)
+            float qsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                bq[2 * j] = kl == 0 ? __byte_perm(u[2 * j], u[2 * j + 1], 0x5410) : 0u;     // (d4j, d4j+2)
+                bq[2 * j + 1] = kl == 0 ? __byte_perm(u[2 * j], u[2 * j + 1], 0x7632) : 0u; // (d4j+1, d4j+3)
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u[2 * j]));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&u[2 * j + 1]));
+                qsum += (f0.x + f0.y) + (f1.x + f1.y);
+            }
+            qsum += __shfl_xor_sync(0xffffffffu, qsum, 1);
+            qsum += __shfl_xor_sync(0xffffffffu, qsum, 2);
+            koff = 1152.f * qsum;
+        }
+        float m_run = -FLT_MAX, l_run = 0.f;
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            o[j] = 0.f;
+        for (int j = 0; j < n_w; ++j, ++i)
+        {
+            const int s = i % ST;
+            const int nk = min(CK, p.S - (wc0 + j) * CK);
+            mbar_wait(&bars[s], (i / ST) & 1);
+            const uint8_t* kst = ring + s * kStageBytes + (size_t) (kl * kDh + chunk * 16);
+            const uint8_t* vst = kst + kHalfBytes;
+            if (nk == CK)
+                xa_chunk<true, NIT, true, true>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o, koff);
+            else
+                xa_chunk<true, NIT, false, true>(kst, vst, nk, kl, lane, sscale, bq, m_run, l_run, o, koff);
+            __syncwarp();
+            if (lane == 0 && i + ST < tot)
+                issue(i + ST, s);
+        }
+        float l = l_run;
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+        {
+            float v = o[j];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            o[j] = v;
+        }
+        float* pr = parts + ((r & 1) * W + warp) * kPart;
+        if (kl == 0)
+        {
+            float* dst = pr + 4 + chunk * 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(o[4 * j + 0], o[4 * j + 2], o[4 * j + 1], o[4 * j + 3]);
+            if (chunk == 0)
+            {
+                pr[0] = m_run;
+                pr[1] = l;
+            }
+        }
+        __syncthreads();
+        if (warp == r % W)
+        {
+            const float* pb = parts + (r & 1) * W * kPart;
+            float gm = -FLT_MAX;
+#pragma unroll
+            for (int w2 = 0; w2 < W; ++w2)
+                gm = fmaxf(gm, pb[w2 * kPart]);
+            float gl = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < W; ++w2)
+            {
+                const float* ps = pb + w2 * kPart;
+                const float wt = fast_exp2(ps[0] - gm);
+                gl += wt * ps[1];
+                a0 += wt * ps[4 + lane];
+                a1 += wt * ps[4 + 32 + lane];
+            }
+            const float inv = s_qo / gl;
+            p.out[(size_t) bh * kDh + lane] = __float2half_rn(a0 * inv);
+            p.out[(size_t) bh * kDh + 32 + lane] = __float2half_rn(a1 * inv);
+        }
+    }
+}
+
 // fp16 K, V [B, S, H*64] -> cache [B, 2, H, S, 64] (int8-quantized or fp16).  grid (S, B), 128 threads... one
 // thread per 16-element chunk: H*4 chunks per token for K and again for V.
 template <bool INT8>
@@ -1270,6 +1602,84 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     case 10: return xattn_launch<false, XaCfgF>(p, pl, st);
     default: return xattn_launch<true, XaCfgF>(p, pl, st);
     }
+}
+
+namespace b200
+{
+// launch plan of the q-fused kernel: grid, rows per CTA, shared memory; ok = 0 when the shape is not handled
+struct XqPlan
+{
+    int ok, blocks, maxr, nch;
+    size_t smem;
+};
+
+static XqPlan xq_plan(int B, int H, int S)
+{
+    using CFG = XaCfgC;
+    XqPlan pl{};
+    if (B < 1 || H < 1 || S < 1 || H > kXqMaxKb * CFG::W)
+        return pl;
+    const int sms = num_sms();
+    if ((long long) B * H < sms) // fewer pairs than SMs: the plain kernels (whole pairs or split pairs per CTA) serve these
+        return pl;
+    pl.blocks = sms;
+    const int nc_min = sms / H; // CTAs of the least-served head
+    pl.maxr = (B + nc_min - 1) / nc_min;
+    if (pl.maxr * kDh > CFG::W * 32) // one finishing thread per (row, column)
+        return pl;
+    pl.nch = (S + CFG::CK - 1) / CFG::CK;
+    pl.smem = (size_t) CFG::W * CFG::ST * 2 * CFG::CK * kDh + ((sizeof(uint64_t) * CFG::W * CFG::ST + 15) & ~size_t(15))
+        + sizeof(float) * 2 * CFG::W * (kDh + 4) + sizeof(float) * CFG::W * pl.maxr * (kDh + 2) + sizeof(float) * ((pl.maxr + 1) & ~1) + sizeof(__half) * pl.maxr * kDh;
+    pl.ok = pl.smem <= 227 * 1024 ? 1 : 0;
+    return pl;
+}
+} // namespace b200
+
+extern "C" int b200_cross_attention_qproj_supported(int batch_size, int num_heads, int head_size, int kv_len)
+{
+    if (head_size != kDh)
+        return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return 0;
+    return xq_plan(batch_size, num_heads, kv_len).ok;
+}
+
+extern "C" int b200_cross_attention_qproj(const void* x, const void* ln_gamma, const float* c1s, const float* c2, float ln_eps,
+    const int8_t* Wproc, const void* scales, const void* bias, const void* cross_kv, const float* kv_scale_quant_orig,
+    void* out, int batch_size, int num_heads, int head_size, int kv_len, b200_stream_t stream)
+{
+    B200_REQUIRE(x && ln_gamma && c1s && c2 && Wproc && scales && cross_kv && kv_scale_quant_orig && out, B200_ERR_INVALID_ARG,
+        "null pointer");
+    B200_REQUIRE(head_size == kDh, B200_ERR_UNSUPPORTED, "head_size %d unsupported (only 64)", head_size);
+    B200_REQUIRE_DEVICE();
+    const XqPlan pl = xq_plan(batch_size, num_heads, kv_len);
+    B200_REQUIRE(pl.ok, B200_ERR_UNSUPPORTED, "q-fused cross attention: batch %d x %d heads x %d keys not handled (use "
+        "b200_woq_int8_gemm_ln_folded + b200_cross_attention)", batch_size, num_heads, kv_len);
+    using CFG = XaCfgC;
+    XqParams p{};
+    p.x = static_cast<const __half*>(x);
+    p.W = reinterpret_cast<const uint8_t*>(Wproc);
+    p.scales = static_cast<const __half*>(scales);
+    p.bias = static_cast<const __half*>(bias);
+    p.gamma = static_cast<const __half*>(ln_gamma);
+    p.c1s = c1s, p.c2 = c2;
+    p.kv = cross_kv;
+    p.scale_quant_orig = kv_scale_quant_orig;
+    p.out = static_cast<__half*>(out);
+    p.B = batch_size, p.H = num_heads, p.S = kv_len, p.nch = pl.nch, p.maxr = pl.maxr;
+    p.eps = ln_eps;
+    p.inv_sqrt_dh = 1.f / sqrtf((float) kDh);
+    static size_t attr_smem = 0;
+    if (pl.smem > attr_smem)
+    {
+        B200_CUDA(cudaFuncSetAttribute(cross_attention_qproj_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA(cudaFuncSetAttribute(cross_attention_qproj_kernel<CFG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            cudaSharedmemCarveoutMaxShared));
+        attr_smem = 227 * 1024;
+    }
+    B200_LAUNCH((cross_attention_qproj_kernel<CFG>), dim3(pl.blocks), dim3(CFG::W * 32), pl.smem, as_stream(stream), p);
+    return B200_OK;
 }
 
 extern "C" int b200_cross_kv_pack(const void* k, const void* v, void* cross_kv, const float* kv_scale_orig_quant,

@@ -108,6 +108,12 @@ class WhisperDecoding:
         # (B200_FUSE_QKV_MMHA=1 or .fuse_qkv_mmha = True): parity-green, but measured slower than the two tuned kernels it
         # replaces (8.5 vs 7.6 us per layer at batch 16, step 1.38 vs 1.29 ms)
         self.fuse_qkv_mmha = os.environ.get("B200_FUSE_QKV_MMHA", "0") == "1"
+        # generation phase: the cross-attention kernel computes its own q projection (csrc/attention.cu,
+        # cross_attention_qproj_kernel): one launch fewer per layer.  Opt-in (B200_FUSE_XQ=1 or .fuse_cross_q = True):
+        # parity-green, but measured slower than the two kernels it replaces (step 1.306 vs 1.292 ms at batch 16: the
+        # cross-attention is issue-bound, not stream-bound, so starting its stream earlier buys nothing and the projection
+        # sits on its critical path)
+        self.fuse_cross_q = os.environ.get("B200_FUSE_XQ", "0") == "1"
         if self.fuse_ln:
             st0 = torch.cuda.current_stream(dev).cuda_stream
             for lay in self.layers:
@@ -292,6 +298,10 @@ class WhisperDecoding:
         # generation phase: LayerNorm + qkv projection + self-attention as ONE kernel per layer (csrc/qkv_mmha.cu)
         fused_qkv = (not context and self.fuse_ln and self.fuse_qkv_mmha and s_q == 1
                      and self.lib.b200_qkv_mmha_decode_supported(nb, H, Dh) == 1)
+        # generation phase: cross_q projection inside the cross-attention kernel (needs the static-cache promise: the
+        # kernel streams the cross-KV cache before its dependency wait)
+        fused_xq = (not context and self.fuse_ln and self.fuse_cross_q and self.static_kv and s_q == 1
+                    and self.lib.b200_cross_attention_qproj_supported(nb, H, Dh, self.S_enc) == 1)
         for i, lay in enumerate(self.layers):
             kv_i = self.self_kv[i] if nb == self.B else self.self_kv[i][b0:b0 + nb]
             ckv_i = self.cross_kv[i] if nb == self.B else self.cross_kv[i][b0:b0 + nb]
@@ -327,12 +337,22 @@ class WhisperDecoding:
                 p.max_seq_len, p.past_kv_length, p.int8_kv_cache, p.q_scaling = self.Smax, 0, 1, 1.0
                 _lib.check(self.lib.b200_mmha_generation(ctypes.byref(p), st), "mmha_generation")
             self._gemm(ctx, rows, lay["attn_out"], x, residual=x, ws=ws)
-            if self.fuse_ln:
+            if fused_xq:
+                if not getattr(self, "_measure_without_cross_attention", False):
+                    lin = lay["cross_q"]
+                    rc = self.lib.b200_cross_attention_qproj(
+                        x.data_ptr(), lay["cross_ln"][0].data_ptr(), lin.c1s.data_ptr(), lin.c2.data_ptr(), 1e-5,
+                        lin.weight.data_ptr(), lin.scales.data_ptr(), lin.bias.data_ptr() if lin.bias is not None else None,
+                        ckv_i.data_ptr(), lay["ckv_qo"].data_ptr(), ctx.data_ptr(), nb, H, Dh, self.S_enc, st)
+                    _lib.check(rc, "cross_attention_qproj")
+            elif self.fuse_ln:
                 self._gemm_ln(x, lay["cross_ln"], rows, lay["cross_q"], q, ws=ws)
             else:
                 self._ln(x, lay["cross_ln"], h, rows)
                 self._gemm(h, rows, lay["cross_q"], q, ws=ws)
-            if not getattr(self, "_measure_without_cross_attention", False):  # bench.py: in-graph cost by difference
+            if fused_xq:
+                pass
+            elif not getattr(self, "_measure_without_cross_attention", False):  # bench.py: in-graph cost by difference
                 rc = self.lib.b200_cross_attention(q.data_ptr(), ckv_i.data_ptr(), lay["ckv_qo"].data_ptr(),
                                                    ctx.data_ptr(), rows, s_q, H, Dh, self.S_enc, 1, ws.data_ptr(),
                                                    ws.numel(), st)

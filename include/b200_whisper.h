@@ -240,6 +240,20 @@ size_t b200_cross_attention_workspace_bytes(int batch_size, int num_heads, int h
 int b200_cross_attention(const void* q, const void* cross_kv, const float* kv_scale_quant_orig, void* out,
     int num_q_rows, int q_rows_per_seq, int num_heads, int head_size, int kv_len, int int8_kv_cache, void* workspace,
     size_t workspace_bytes, b200_stream_t stream);
+/* Cross attention of the generation phase WITH its q projection (one launch instead of two per layer): the attention
+ * CTAs compute q = Linear_q(LayerNorm(x)) for their own (row, head) pairs -- the `cross_attn.q` weight-only Linear of
+ * T/tensorrt_llm/layers/attention.py:308-313 behind the decoder layer's cross_attention_layernorm
+ * (T/tensorrt_llm/models/whisper/model.py:257-292) -- so the cross-KV stream starts one kernel boundary earlier and the
+ * projection runs while the first ring stages are in flight (csrc/attention.cu, cross_attention_qproj_kernel).
+ * x [B, d] fp16 raw residual rows (d = num_heads * 64); ln_gamma [d]; c1s / c2 [d] fp32 from b200_woq_ln_fold_prepare;
+ * Wproc / scales / bias: the q Linear (N = K = d) as for b200_woq_int8_gemm_ln_folded; cross_kv: the int8 cache written
+ * by b200_cross_kv_pack, which must NOT be written by the kernel launched right before (it is streamed before the
+ * dependency wait); out [B, d] fp16.  b200_cross_attention_qproj_supported tells whether a shape is handled (at least
+ * one (row, head) pair per SM, at most 6 rows per CTA); otherwise call the two operators. */
+int b200_cross_attention_qproj_supported(int batch_size, int num_heads, int head_size, int kv_len);
+int b200_cross_attention_qproj(const void* x, const void* ln_gamma, const float* c1s, const float* c2, float ln_eps,
+    const int8_t* Wproc, const void* scales, const void* bias, const void* cross_kv, const float* kv_scale_quant_orig,
+    void* out, int batch_size, int num_heads, int head_size, int kv_len, b200_stream_t stream);
 /* Packs fp16 K and V projections [B, S, H*Dh] into the cross-KV cache layout, quantizing with
  * cvt.rni.sat.s8.f32(scale * x) when int8_kv_cache (same rule as the self-attention cache).
  * The int8 CROSS cache is stored in offset-binary form: byte = (uint8)(q + 128), i.e. the two's-complement byte with
