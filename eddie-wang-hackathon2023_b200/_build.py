@@ -34,7 +34,8 @@ if TC_DEBUG:
     COMMON = COMMON + ["-DB200_TC_DEBUG=1"]
 if DS_DEBUG:
     COMMON = COMMON + ["-DB200_DS_DEBUG=1"]
-# experiment switches (bisecting): B200_EXTRA_DEFS="-DX -DY"
+# experiment switches (bisecting): B200_EXTRA_DEFS="-DX -DY"; -DB200_XA_DEBUG=1 compiles per-CTA %globaltimer stamps into
+# the whole-pair cross-attention kernel (tools/xa_timeline.py)
 EXTRA_DEFS = os.environ.get("B200_EXTRA_DEFS", "").split()
 if EXTRA_DEFS:
     COMMON = COMMON + EXTRA_DEFS

@@ -84,6 +84,8 @@ _SIGS = {
     "b200_mmha_generation": (_i, [ctypes.POINTER(MmhaParams), _vp]),
     "b200_qkv_mmha_decode_supported": (_i, [_i, _i, _i]),
     "b200_cross_attention_qproj_supported": (_i, [_i, _i, _i, _i]),
+    "b200_debug_xa_timeline": (_i, [_vp]),
+    "b200_set_cross_attention_split": (_i, [_i]),
     "b200_cross_attention_qproj": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_qkv_mmha_decode": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200_attention_context": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),

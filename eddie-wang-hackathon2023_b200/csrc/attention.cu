@@ -569,7 +569,26 @@ struct XAttnParams
     int max_parts;
     int early_kv; // the cache is not written by the kernel right before this one: stream it before the PDL wait
     float inv_sqrt_dh;
+    long long* dbg; // B200_XA_DEBUG builds: 8 %globaltimer stamps per CTA of the row-head kernel (b200_debug_xa_timeline)
 };
+
+#if defined(B200_XA_DEBUG)
+#define XA_STAMP(slot)                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (p.dbg != nullptr && threadIdx.x == 0)                                                                      \
+        {                                                                                                              \
+            long long t_;                                                                                              \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                     \
+            p.dbg[(size_t) blockIdx.x * 8 + (slot)] = t_;                                                              \
+        }                                                                                                              \
+    } while (0)
+#else
+#define XA_STAMP(slot)                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+    } while (0)
+#endif
 
 
 
@@ -772,7 +791,38 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_kernel(const X
 // of the CTA split the pair's chunks into contiguous runs, stream them through their private TMA rings exactly like
 // the split kernel above, and merge their partial softmax states through shared memory -- no global partials, no
 // fences, no counters.  q of the next pair is fetched while the current one is being processed.
-template <bool INT8, typename CFG>
+//
+// SPLIT (launched as clusters of two CTAs): the pairs that do not fill a whole round of the grid -- 320 pairs on 148 CTAs
+// leave 24 -- are not dealt whole to the first CTAs (a third pair for 24 of them while 124 wait: the kernel is issue-bound
+// on exactly those CTAs) but split by keys over the two CTAs of a cluster.  Rank 1 pushes its warps' partial softmax
+// states into rank 0's shared memory (st.async, complete_tx on an mbarrier there) and rank 0 merges all 2 W of them:
+// critical path 2.5 instead of 3 pairs.
+__device__ __forceinline__ uint32_t xa_cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t xa_cluster_id()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void xa_push_f32(uint32_t remote_addr, float v, uint32_t remote_mbar)
+{
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "r"(__float_as_uint(v)), "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t xa_mapa(uint32_t local_smem_addr, uint32_t cta_rank)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+    return remote;
+}
+
+template <bool INT8, typename CFG, bool SPLIT = false>
 __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead_kernel(const XAttnParams p)
 {
     constexpr int W = CFG::W, ST = CFG::ST;
@@ -790,27 +840,73 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
     // (barrier block rounded up to 16 bytes: the partials are read as float4 -- an odd W * ST, config E, misaligned them)
     float* parts = reinterpret_cast<float*>(smem + (size_t) W * ST * kStageBytes + ((sizeof(uint64_t) * W * ST + 15) & ~size_t(15))); // [2][W][68]
 
+    XA_STAMP(0);
     const int RH = p.B * p.H;
-    const int nbh = (RH - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x; // pairs of this CTA (>= 1)
     const int wc0 = warp * p.nch / W, wc1 = (warp + 1) * p.nch / W;                   // this warp's chunks of every pair
     const int n_w = wc1 - wc0;
-    const int tot = nbh * n_w;
+    // SPLIT: whole rounds of the grid are dealt pair by pair; the remaining pairs (host: at most one per cluster) are
+    // shared by the two CTAs of a cluster: rank k takes chunks [k nch / 2, (k + 1) nch / 2), split over its warps
+    const int rounds = RH / (int) gridDim.x;
+    const int nbh = SPLIT ? rounds : (RH - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x; // whole pairs of this CTA
+    int left_bh = -1, lc0 = 0, n_l = 0; // the shared pair, this warp's first chunk of it and chunk count
+    uint32_t crank = 0;
+    float* lparts = nullptr;   // [2 W][68] partial states of the shared pair (rank 0 merges)
+    uint64_t* lbar = nullptr;  // rank 0: the partials of rank 1 have landed
+    if constexpr (SPLIT)
+    {
+        lparts = parts + 2 * W * kPart;
+        lbar = reinterpret_cast<uint64_t*>(lparts + 2 * W * kPart);
+        crank = xa_cluster_rank();
+        const int cand = rounds * (int) gridDim.x + (int) xa_cluster_id();
+        if (cand < RH)
+        {
+            left_bh = cand;
+            const int h0 = (int) crank * p.nch / 2, h1 = ((int) crank + 1) * p.nch / 2;
+            lc0 = h0 + warp * (h1 - h0) / W;
+            n_l = h0 + (warp + 1) * (h1 - h0) / W - lc0;
+        }
+    }
+    const int tot = nbh * n_w + n_l;
 
     if (lane == 0)
     {
         for (int s = 0; s < ST; ++s)
             mbar_init(&bars[s], 1);
+        if (SPLIT && warp == 0 && left_bh >= 0 && crank == 0)
+        {
+            mbar_init(lbar, 1);
+            mbar_arrive_expect_tx(lbar, (uint32_t) (W * (kDh + 2) * sizeof(float)));
+        }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
     __syncwarp();
+    if constexpr (SPLIT)
+    {
+        // rank 0's inbox barrier is armed before rank 1 may push into it: arrive now, rank 1 waits right before its push
+        if (left_bh >= 0)
+        {
+            __syncthreads();
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        }
+    }
     grid_dep_launch_dependents();
 
     const uint64_t pol = policy_evict_first();
     auto issue = [&](int i, int s)
     {
-        const int r = i / n_w, ch = wc0 + (i - r * n_w);
-        const int bh = blockIdx.x + r * gridDim.x;
+        int bh, ch;
+        if (SPLIT && i >= nbh * n_w)
+        {
+            bh = left_bh;
+            ch = lc0 + (i - nbh * n_w);
+        }
+        else
+        {
+            const int r = i / n_w;
+            ch = wc0 + (i - r * n_w);
+            bh = blockIdx.x + r * gridDim.x;
+        }
         const int b = (bh / p.H) / p.q_per_seq, h = bh % p.H;
         const int key0 = ch * CK;
         const int nk = min(CK, p.S - key0);
@@ -831,16 +927,21 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
     if (p.early_kv)
         grid_dep_wait(); // q comes from the previous kernel
 
+    XA_STAMP(1);
     // q of the first pair and the dequant scale: both loads in flight together
-    const uint4* qsrc = reinterpret_cast<const uint4*>(p.q + (size_t) blockIdx.x * kDh + chunk * 16);
+    const int first_bh = (!SPLIT || nbh > 0) ? (int) blockIdx.x : left_bh;
+    const uint4* qsrc = reinterpret_cast<const uint4*>(p.q + (size_t) first_bh * kDh + chunk * 16);
     uint4 qn0 = __ldg(qsrc), qn1 = __ldg(qsrc + 1);
     const float s_qo = INT8 ? __ldg(p.scale_quant_orig) : 1.f;
     const float sscale = s_qo * p.inv_sqrt_dh * 1.4426950408889634f;
 
+    const int npairs = nbh + ((SPLIT && left_bh >= 0) ? 1 : 0);
     int i = 0;
-    for (int r = 0; r < nbh; ++r)
+    for (int r = 0; r < npairs; ++r)
     {
-        const int bh = blockIdx.x + r * gridDim.x;
+        const bool shared = SPLIT && r == nbh; // the pair this CTA shares with the other CTA of its cluster
+        const int bh = shared ? left_bh : (int) blockIdx.x + r * (int) gridDim.x;
+        const int c_first = shared ? lc0 : wc0, c_cnt = shared ? n_l : n_w;
         uint32_t bq[8];
         float koff = 0.f; // int8 cache: 1152 * sum of q over the 64 dims, the bias of the 1024 + byte key values (xa_chunk KOFF)
         {
@@ -866,9 +967,10 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
                 koff = 1152.f * qs;
             }
         }
-        if (r + 1 < nbh)
+        if (r + 1 < npairs)
         {
-            const uint4* qs = reinterpret_cast<const uint4*>(p.q + (size_t) (bh + gridDim.x) * kDh + chunk * 16);
+            const int nbh_next = (SPLIT && r + 1 == nbh) ? left_bh : bh + (int) gridDim.x;
+            const uint4* qs = reinterpret_cast<const uint4*>(p.q + (size_t) nbh_next * kDh + chunk * 16);
             qn0 = __ldg(qs);
             qn1 = __ldg(qs + 1);
         }
@@ -877,10 +979,10 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             o[j] = 0.f;
-        for (int j = 0; j < n_w; ++j, ++i)
+        for (int j = 0; j < c_cnt; ++j, ++i)
         {
             const int s = i % ST;
-            const int nk = min(CK, p.S - (wc0 + j) * CK);
+            const int nk = min(CK, p.S - (c_first + j) * CK);
             mbar_wait(&bars[s], (i / ST) & 1);
             const uint8_t* kst = ring + s * kStageBytes + (size_t) (kl * kDh + chunk * 16) * ESZ;
             const uint8_t* vst = kst + kHalfBytes;
@@ -909,7 +1011,35 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
             v += __shfl_xor_sync(0xffffffffu, v, 16);
             o[j] = v;
         }
-        float* pr = parts + ((r & 1) * W + warp) * kPart;
+        XA_STAMP(2 + (r < 4 ? r : 4)); // warp 0 finished its chunks of pair r
+        if (SPLIT && shared && crank != 0)
+        {
+            // rank 1: push this warp's partial into slot W + warp of rank 0's inbox and leave
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); // rank 0 has armed its inbox barrier
+            if (kl == 0)
+            {
+                const uint32_t dst = xa_mapa(smem_u32(lparts + (size_t) (W + warp) * kPart), 0u);
+                const uint32_t bar = xa_mapa(smem_u32(lbar), 0u);
+                const uint32_t od = dst + (uint32_t) (4 + chunk * 16) * 4u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
+                    xa_push_f32(od + (uint32_t) (4 * j + 0) * 4u, o[4 * j + 0], bar);
+                    xa_push_f32(od + (uint32_t) (4 * j + 1) * 4u, o[4 * j + 2], bar);
+                    xa_push_f32(od + (uint32_t) (4 * j + 2) * 4u, o[4 * j + 1], bar);
+                    xa_push_f32(od + (uint32_t) (4 * j + 3) * 4u, o[4 * j + 3], bar);
+                }
+                if (chunk == 0)
+                {
+                    xa_push_f32(dst, m_run, bar);
+                    xa_push_f32(dst + 4u, l, bar);
+                }
+            }
+            XA_STAMP(7);
+            return;
+        }
+        float* pr = (SPLIT && shared) ? lparts + (size_t) warp * kPart : parts + ((r & 1) * W + warp) * kPart;
         if (kl == 0)
         {
             // o[2i], o[2i+1] hold the pair of w[i]: w[2j] = dims (4j, 4j+2), w[2j+1] = dims (4j+1, 4j+3)
@@ -926,26 +1056,34 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
         __syncthreads();
         if (warp == r % W)
         {
-            const float* pb = parts + (r & 1) * W * kPart;
+            const float* pb = (SPLIT && shared) ? lparts : parts + (r & 1) * W * kPart;
+            const int np = (SPLIT && shared) ? 2 * W : W;
+            if (SPLIT && shared)
+                mbar_wait(lbar, 0); // the W partials of rank 1 have landed
             float gm = -FLT_MAX;
 #pragma unroll
-            for (int w2 = 0; w2 < W; ++w2)
-                gm = fmaxf(gm, pb[w2 * kPart]);
+            for (int w2 = 0; w2 < 2 * W; ++w2)
+                if (w2 < np)
+                    gm = fmaxf(gm, pb[w2 * kPart]);
             float gl = 0.f, a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int w2 = 0; w2 < W; ++w2)
+            for (int w2 = 0; w2 < 2 * W; ++w2)
             {
-                const float* ps = pb + w2 * kPart;
-                const float wt = fast_exp2(ps[0] - gm);
-                gl += wt * ps[1];
-                a0 += wt * ps[4 + lane];
-                a1 += wt * ps[4 + 32 + lane];
+                if (w2 < np)
+                {
+                    const float* ps = pb + w2 * kPart;
+                    const float wt = fast_exp2(ps[0] - gm);
+                    gl += wt * ps[1];
+                    a0 += wt * ps[4 + lane];
+                    a1 += wt * ps[4 + 32 + lane];
+                }
             }
             const float inv = s_qo / gl; // hoisted V dequant scale
             p.out[(size_t) bh * kDh + lane] = __float2half_rn(a0 * inv);
             p.out[(size_t) bh * kDh + 32 + lane] = __float2half_rn(a1 * inv);
         }
     }
+    XA_STAMP(7);
 }
 
 // ---- cross attention with its q projection inside ("q-fused row-head" kernel, generation phase, int8 cache) -------
@@ -1001,8 +1139,8 @@ __global__ void __launch_bounds__(CFG::W * 32, 1) cross_attention_qproj_kernel(c
     float* parts = reinterpret_cast<float*>(smem + (size_t) W * ST * kStageBytes + ((sizeof(uint64_t) * W * ST + 15) & ~size_t(15))); // [2][W][68]
     float* qpart = parts + 2 * W * kPart;                       // [W][maxr][64] partial projections (one per k range)
     float* stat = qpart + (size_t) W * p.maxr * kDh;            // [W][maxr][2] partial sums of (x - x0), (x - x0)^2
-    float* x0s = stat + (size_t) W * p.maxr * 2;                // [maxr (rounded up to even)] x0 of every row
-    __half* qs = reinterpret_cast<__half*>(x0s + ((p.maxr + 1) & ~1)); // [maxr][64] finished q rows
+    float* x0s = stat + (size_t) W * p.maxr * 2;                // [maxr rounded up to 4] x0 of every row
+    __half* qs = reinterpret_cast<__half*>(x0s + ((p.maxr + 3) & ~3)); // [maxr][64] finished q rows (16-byte aligned)
 
     const int K = p.H * kDh, nkb = p.H;
     // this CTA's head and rows
@@ -1437,9 +1575,12 @@ namespace b200
 struct XaPlan
 {
     int nch, chunks_per_warp, max_parts, blocks, cfg, rowhead;
+    int split; // row-head kernel as clusters of two CTAs that share the pairs left over after the whole rounds
     size_t smem, ws_bytes;
 };
 
+static long long* g_xa_dbg = nullptr; // b200_debug_xa_timeline
+static int g_xa_split = -1;           // b200_set_cross_attention_split / env B200_XA_SPLIT (default off)
 static int g_xa_cfg = -1;  // env B200_XA_CFG = A .. F
 static int g_xa_mode = -1; // env B200_XA_MODE = split | rowhead | auto (default)
 
@@ -1475,6 +1616,22 @@ static XaPlan xattn_plan(int R, int H, int S, int int8)
         pl.smem = (size_t) W * ST * 2 * ck * kDh * (int8 ? 1 : 2) + ((sizeof(uint64_t) * W * ST + 15) & ~size_t(15))
             + sizeof(float) * 2 * W * (kDh + 4);
         pl.ws_bytes = 0;
+        // 2-CTA clusters share the pairs that do not fill a whole round (at most one per cluster).  Opt-in
+        // (b200_set_cross_attention_split / env B200_XA_SPLIT=1): the kernel itself ends 1.0 us earlier at batch 16, but the
+        // step gets 0.9 us per layer SLOWER -- the CTAs that used to leave after two pairs are where the next GEMM starts
+        // its weight stream and dequant ahead of its dependency (tools/xa_timeline.py)
+        if (g_xa_split < 0)
+        {
+            const char* e = getenv("B200_XA_SPLIT");
+            g_xa_split = (e != nullptr && e[0] == '1') ? 1 : 0;
+        }
+        const int left = R * H - (R * H / pl.blocks) * pl.blocks;
+        if (g_xa_split == 1 && kOCC[g_xa_cfg] == 1 && pl.blocks % 2 == 0 && R * H >= pl.blocks && left > 0 && 2 * left <= pl.blocks
+            && pl.nch >= 2)
+        {
+            pl.split = 1;
+            pl.smem += sizeof(float) * 2 * W * (kDh + 4) + 16;
+        }
         return pl;
     }
     const long long total = (long long) R * H * pl.nch;
@@ -1507,8 +1664,49 @@ static int xattn_launch(const XAttnParams& p, const XaPlan& pl, cudaStream_t st)
 }
 
 template <bool INT8, typename CFG>
+static int xattn_launch_rowhead_split(const XAttnParams& p, const XaPlan& pl, cudaStream_t st)
+{
+    auto kern = cross_attention_rowhead_kernel<INT8, CFG, true>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.blocks);
+    cfg.blockDim = dim3(CFG::W * 32);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl_enabled())
+    {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    count_launch();
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    return B200_OK;
+}
+
+template <bool INT8, typename CFG>
 static int xattn_launch_rowhead(const XAttnParams& p, const XaPlan& pl, cudaStream_t st)
 {
+    if (pl.split)
+    {
+        if constexpr (CFG::OCC == 1)
+            return xattn_launch_rowhead_split<INT8, CFG>(p, pl, st);
+    }
     static bool attr_set = false;
     if (!attr_set)
     {
@@ -1563,6 +1761,7 @@ extern "C" int b200_cross_attention(const void* q, const void* cross_kv, const f
     p.max_parts = pl.max_parts;
     p.early_kv = static_kv_hint() ? 1 : 0;
     p.inv_sqrt_dh = 1.f / sqrtf((float) kDh);
+    p.dbg = g_xa_dbg;
     cudaStream_t st = as_stream(stream);
     if (pl.rowhead)
     {
@@ -1629,7 +1828,7 @@ static XqPlan xq_plan(int B, int H, int S)
         return pl;
     pl.nch = (S + CFG::CK - 1) / CFG::CK;
     pl.smem = (size_t) CFG::W * CFG::ST * 2 * CFG::CK * kDh + ((sizeof(uint64_t) * CFG::W * CFG::ST + 15) & ~size_t(15))
-        + sizeof(float) * 2 * CFG::W * (kDh + 4) + sizeof(float) * CFG::W * pl.maxr * (kDh + 2) + sizeof(float) * ((pl.maxr + 1) & ~1) + sizeof(__half) * pl.maxr * kDh;
+        + sizeof(float) * 2 * CFG::W * (kDh + 4) + sizeof(float) * CFG::W * pl.maxr * (kDh + 2) + sizeof(float) * ((pl.maxr + 3) & ~3) + sizeof(__half) * pl.maxr * kDh;
     pl.ok = pl.smem <= 227 * 1024 ? 1 : 0;
     return pl;
 }
@@ -1679,6 +1878,30 @@ extern "C" int b200_cross_attention_qproj(const void* x, const void* ln_gamma, c
         attr_smem = 227 * 1024;
     }
     B200_LAUNCH((cross_attention_qproj_kernel<CFG>), dim3(pl.blocks), dim3(CFG::W * 32), pl.smem, as_stream(stream), p);
+    return B200_OK;
+}
+
+/* Tuning switch (process-wide, set before the launches are captured; returns the previous value): 1 = the whole-pair
+ * cross-attention kernel runs as clusters of two CTAs that share the (row, head) pairs left over after the whole rounds
+ * of the grid.  Default 0 (env B200_XA_SPLIT=1 turns it on). */
+extern "C" int b200_set_cross_attention_split(int enabled)
+{
+    if (g_xa_split < 0)
+    {
+        const char* e = getenv("B200_XA_SPLIT");
+        g_xa_split = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    const int prev = g_xa_split;
+    g_xa_split = enabled ? 1 : 0;
+    return prev;
+}
+
+/* Debug aid (B200_XA_DEBUG=1 builds only; a no-op otherwise): device buffer of >= 8 int64 per SM receiving %globaltimer
+ * stamps of every CTA of the following row-head cross-attention launches: entry, dependency return, warp 0 done with
+ * pair 0 / 1 / 2 / 3 / later, exit.  NULL switches it off. */
+extern "C" int b200_debug_xa_timeline(void* device_buffer)
+{
+    g_xa_dbg = static_cast<long long*>(device_buffer);
     return B200_OK;
 }
 

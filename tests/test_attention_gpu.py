@@ -115,10 +115,26 @@ def test_context_then_generation(int8, in_len):
 
 
 # the last three shapes have enough (row, head) pairs for the one-CTA-per-pair kernel, with fewer chunks than warps
+# (16, 20, *), (10, 16, 700), (40, 4, 100), (38, 4, 333), (8, 20, 1500): a few pairs are left after the whole rounds of the grid and
+# are shared by the two CTAs of a cluster (split row-head kernel); (37, 4, 1500): exactly one pair per SM, nothing to share
 @pytest.mark.parametrize("B,H,S", [(1, 20, 1500), (16, 20, 1500), (3, 6, 1500), (2, 2, 96), (5, 4, 333),
-                                   (10, 16, 700), (40, 4, 100), (9, 20, 1)])
+                                   (10, 16, 700), (40, 4, 100), (9, 20, 1), (16, 20, 130), (38, 4, 333), (8, 20, 1500),
+                                   (37, 4, 1500), (16, 20, 65)])
 @pytest.mark.parametrize("int8", [True, False])
-def test_cross_attention(B, H, S, int8):
+@pytest.mark.parametrize("split", [False, True])
+def test_cross_attention(B, H, S, int8, split):
+    import b200_whisper
+    from b200_whisper.functional import cross_attention, cross_kv_pack
+    if split and not (B * H >= 148 and S > 64):
+        pytest.skip("the cluster-split variant only differs when pairs are left over after whole rounds of the grid")
+    prev = b200_whisper.load().b200_set_cross_attention_split(1 if split else 0)
+    try:
+        _cross_attention_case(B, H, S, int8)
+    finally:
+        b200_whisper.load().b200_set_cross_attention_split(prev)
+
+
+def _cross_attention_case(B, H, S, int8):
     from b200_whisper.functional import cross_attention, cross_kv_pack
     torch.manual_seed(B * 131 + S)
     D = 64
@@ -152,6 +168,12 @@ def test_cross_attention_multi_query_rows():
     torch.manual_seed(5)
     _multi_query_rows(3, 4, 200, 4)
     _multi_query_rows(6, 8, 130, 5)  # 240 (row, head) pairs: one-CTA-per-pair kernel
+    import b200_whisper
+    prev = b200_whisper.load().b200_set_cross_attention_split(1)
+    try:
+        _multi_query_rows(3, 10, 200, 5)  # 150 pairs: two of them shared by the CTAs of a cluster
+    finally:
+        b200_whisper.load().b200_set_cross_attention_split(prev)
 
 
 def _multi_query_rows(B, H, S, Sq):
