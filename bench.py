@@ -427,6 +427,26 @@ def main():
                       "ms_per_step": 1e3 * float(tp.item()) / n_p,
                       "plugin_enqueues_per_step": (stepper.enqueues - enq0) // n_p,
                       "path": "IPluginV2DynamicExt::enqueue per operator (eager, unfused glue), host token buffers"}
+        # the same enqueue sequence captured once in a CUDA graph (as TensorRT captures an execution context) and replayed
+        try:
+            stepper.capture()
+            n_g = max(8, min(args.steps, 32))
+            for _ in range(3):
+                host_tokens = stepper.step_host_graph(host_tokens).numpy().copy()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_g):
+                host_tokens = stepper.step_host_graph(host_tokens).numpy().copy()
+            barrier()
+            tg = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            e2e_plugin["cuda_graph"] = {"value": world * B * n_g / float(tg.item()), "unit": UNIT, "steps": n_g,
+                                        "ms_per_step": 1e3 * float(tg.item()) / n_g,
+                                        "path": "the same plugin enqueues and glue layers captured in one CUDA graph, host "
+                                                "token buffers in and out per step"}
+        except Exception as e:  # the eager figure stands on its own
+            e2e_plugin["cuda_graph"] = {"error": str(e)[:200]}
         stepper.close()
 
     # ---- extras: BASELINE.json configs[1] (batch 1) and configs[3] (64 utterances sharded over the GPUs) -----------

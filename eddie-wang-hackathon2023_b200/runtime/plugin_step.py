@@ -105,11 +105,19 @@ class PluginDecoderStep:
 
     def step(self):
         """One greedy step for the whole batch: consumes dec.tokens / dec.seq_len, leaves dec.next_tokens, advances."""
-        dec, lib, B = self.dec, self.lib, self.dec.B
-        st = self._st()
+        dec = self.dec
         past = int(dec._host_len)
         if past >= dec.Smax:
             raise RuntimeError("the text context is full")
+        self._enqueue_step(past)
+        dec._host_len = past + 1
+        return dec.next_tokens
+
+    def _enqueue_step(self, past):
+        """The device work of one step: every launch goes to the current stream and reads its lengths / tokens from device
+        buffers, so the sequence can be captured in a CUDA graph (TensorRT captures an engine's enqueue the same way)."""
+        dec, lib, B = self.dec, self.lib, self.dec.B
+        st = self._st()
         x = self.x
         _lib.check(lib.b200_embed_tokens_fp16(dec.tokens.data_ptr(), dec.seq_len.data_ptr(), dec.tok_emb.data_ptr(),
                                               dec.pos_emb.data_ptr(), x.data_ptr(), B, dec.d, dec.V, dec.Smax, st), "embed")
@@ -139,9 +147,47 @@ class PluginDecoderStep:
             self._linear(self.ff, lay["fc2"], x, residual=x)
         dec._head(x, B, dec.logits, dec.next_tokens)
         dec.seq_len.add_(1)
-        dec._host_len = past + 1
         dec.tokens.copy_(dec.next_tokens)
-        return dec.next_tokens
+
+    def capture(self):
+        """Captures the step -- host token ids in, all plugin enqueues and glue layers, next ids out -- in ONE CUDA graph,
+        the way a TensorRT execution context is captured (enqueue on a capturing stream): the plugins' enqueue performs
+        no allocation and no synchronization, and the generation kernel takes its lengths from the device tensor
+        `sequence_length` (the HOST past-length scalar is only range-checked at capture time)."""
+        dec = self.dec
+        snap, host_len = dec._snapshot(), int(dec._host_len)
+        enq0 = self.enqueues
+        s = torch.cuda.Stream(device=dec.device)
+        s.wait_stream(torch.cuda.current_stream(dec.device))
+        with torch.cuda.stream(s):
+            self._enqueue_step(host_len)  # warm-up outside capture (function attributes, allocator pool)
+        torch.cuda.current_stream(dec.device).wait_stream(s)
+        torch.cuda.synchronize(dec.device)
+        dec._restore(snap)
+        enq = self.enqueues
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            dec.tokens.copy_(dec._pinned_in, non_blocking=True)
+            self._enqueue_step(host_len)
+            dec._pinned_out.copy_(dec.next_tokens, non_blocking=True)
+        torch.cuda.synchronize(dec.device)
+        dec._restore(snap)
+        self.enqueues_per_step = self.enqueues - enq
+        self.enqueues = enq0  # neither the warm-up nor the capture advanced the sequences
+        self.graph = g
+        return g
+
+    def step_host_graph(self, tokens_host):
+        """host token ids in -> host next-token ids out through the captured step (capture() first)"""
+        dec = self.dec
+        if int(dec._host_len) >= dec.Smax:
+            raise RuntimeError("the text context is full")
+        dec._host_len = int(dec._host_len) + 1
+        dec._pinned_in.copy_(torch.as_tensor(tokens_host, dtype=torch.int32))
+        self.graph.replay()
+        self.enqueues += self.enqueues_per_step
+        torch.cuda.current_stream(dec.device).synchronize()
+        return dec._pinned_out
 
     def step_host(self, tokens_host):
         """host token ids in -> host next-token ids out (pinned buffers of the decoder)"""

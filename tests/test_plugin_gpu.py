@@ -211,6 +211,45 @@ def test_decoder_step_through_the_plugin_classes_matches_the_fused_path():
     assert (t_plug[:, 0] == t_fused[:, 0]).all()
 
 
+def test_plugin_step_captured_in_a_cuda_graph_equals_the_eager_enqueues():
+    """PluginDecoderStep.capture(): the plugin enqueues of a step recorded in one CUDA graph (how TensorRT captures an
+    execution context) and replayed from host token buffers -- same tokens and logits, bit for bit, as enqueueing every
+    step eagerly, over several steps (the lengths advance on the device, not in the captured host scalars)."""
+    from b200_whisper.runtime import PluginDecoderStep, WhisperDecoding
+    from oracle import whisper_oracle as wo
+    dims = wo.ModelDimensions(80, 1500, 1280, 20, 1, 51865, 448, 1280, 20, 2)
+    B, prompt, n_new = 4, [50258, 50259, 50359], 6
+    sd = wo.synthetic_state_dict(dims, seed=5, decoder_only=True)
+    L = dims.n_text_layer
+    g = torch.Generator(device="cuda").manual_seed(7)
+    cross = [torch.randint(-127, 128, (B, 2, dims.n_text_head, 200, 64), generator=g, device="cuda", dtype=torch.int8)
+             for _ in range(L)]
+
+    def run(graph):
+        dec = WhisperDecoding(dims, sd, B, [0.05] * L, [0.03] * L, n_audio_ctx=200)
+        dec.set_cross_kv([c.clone() for c in cross])
+        dec.reset()
+        host = dec.prefill([prompt] * B).cpu().numpy().copy()
+        stepper = PluginDecoderStep(dec)
+        if graph:
+            stepper.capture()
+        toks, logits = [], []
+        for _ in range(n_new):
+            host = (stepper.step_host_graph(host) if graph else stepper.step_host(host)).numpy().copy()
+            toks.append(torch.from_numpy(host.copy()))
+            logits.append(dec.logits.clone())
+        n_enq = stepper.enqueues
+        stepper.close()
+        return torch.stack(toks, 1), torch.stack(logits, 1).cpu(), n_enq, dec.seq_len.cpu()
+
+    t_e, l_e, n_e, len_e = run(False)
+    t_g, l_g, n_g, len_g = run(True)
+    assert torch.equal(t_e, t_g)
+    assert torch.equal(l_e, l_g)
+    assert torch.equal(len_e, len_g)
+    assert n_e == n_g == n_new * L * 7
+
+
 def test_two_threads_enqueue_concurrently():
     """Two plugin instances enqueueing from two host threads on two streams (two execution contexts of an engine): the
     library's switches are thread-local and its counter / scratch slots are per stream, so neither thread can disturb
