@@ -1131,6 +1131,237 @@ __global__ void __launch_bounds__(192, 1)
     }
 }
 
+// =====================================================================================================
+// Large-M path (encoder, M in the thousands): PERSISTENT tcgen05 GEMM with two TMEM accumulators.
+//
+// The kernel above dequantizes its weight tile once per m-tile (94 times per weight tile at M = 24000) with the warps
+// that also run the epilogue, so epilogue and main loop of consecutive tiles cannot overlap (M = 24000: 1.1-1.25 PFLOP/s
+// plain, 0.6-0.85 with a residual / GELU epilogue; tensor pipe 40-55 % active).  Here the int8 weights are expanded ONCE
+// per call to exact fp16 integers ([N][K], K-major; 6.5-13 MB, about 1-3 % of the GEMM's time at M = 24000) and the GEMM
+// is a plain fp16 x fp16 SS-UMMA pipeline:
+//   D[m, n] = sum_k X[m, k] * W16[n, k]     UMMA M = 128 activation rows, UMMA N = 256 weight columns, fp32 in TMEM
+//  * one CTA per SM walks tiles t = blockIdx.x, + gridDim.x, ... (n fastest: the CTAs running together share a few
+//    128-row activation panels in L2; the fp16 weights stay L2-resident);
+//  * warp 0 (one lane): TMA producer, 4 stages of (16 KB activations + 32 KB weights), 128B swizzle;
+//  * warp 1 (one lane): tcgen05.mma issuer; the 512 TMEM columns hold TWO 128 x 256 accumulators, so the MMAs of tile
+//    i + 1 run while
+//  * warps 2-5 drain tile i: tcgen05.ld 16 columns at a time, column scale in fp32, bias / GELU / residual with the
+//    same rounding sequence as finish_output_tile, 32-byte vector stores (a thread owns a row: 16 consecutive columns).
+// =====================================================================================================
+struct LgParams
+{
+    const __half* scales;
+    const __half* bias;
+    const __half* residual;
+    __half* C;
+    int M, N, ldc, kb_total, m_tiles, n_tiles;
+};
+
+constexpr int kLgBM = 128, kLgBN = 256, kLgStages = 4, kLgThreads = 192;
+constexpr int kLgATile = kLgBM * 128, kLgBTile = kLgBN * 128; // bytes per stage (64 halves = 128 B per row)
+
+// int8 (reference layout, [N/2][2K] bytes) -> fp16 exact integers [N][K]; one thread per 16-byte chunk = 16 k values
+__global__ void __launch_bounds__(256) woq_expand_fp16_kernel(const uint8_t* __restrict__ W, __half* __restrict__ W16, int N, int K)
+{
+    grid_dep_launch_dependents();
+    const int cpr = K / 16; // chunks per column
+    const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long) N * cpr)
+        return;
+    const int n = (int) (idx / cpr), c = (int) (idx - (long long) n * cpr);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(W + (size_t) (n >> 1) * 2 * K + (size_t) (c >> 2) * 128 + (n & 1) * 64 + (c & 3) * 16));
+    const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+    {
+        __half2 l, h;
+        dequant_word(words[w], l, h); // l = k (2w, 2w+1), h = k (8+2w, 9+2w) of the chunk
+        lo[w] = *reinterpret_cast<uint32_t*>(&l);
+        hi[w] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    grid_dep_wait(); // the scratch buffer may still be read by the GEMM two launches back
+    uint4* dst = reinterpret_cast<uint4*>(W16 + (size_t) n * K + (size_t) c * 16);
+    dst[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    dst[1] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kLgThreads, 1)
+    woq_gemm_large_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const LgParams p)
+{
+    constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t) (kLgBN >> 3) << 17) | ((uint32_t) (kLgBM >> 4) << 24);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + kLgStages * kLgATile;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kLgStages * kLgBTile);
+    uint64_t* empty = full + kLgStages;
+    uint64_t* acc_full = empty + kLgStages; // [2] MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;     // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* sm_scale = reinterpret_cast<float*>(tmem_slot + 4); // [2][256]
+    __half* sm_bias = reinterpret_cast<__half*>(sm_scale + 2 * kLgBN); // [2][256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.kb_total;
+    const int num_tiles = p.m_tiles * p.n_tiles;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < kLgStages; ++s)
+        {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b)
+        {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    grid_dep_launch_dependents();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0)
+    {
+        if (elect_one_sync())
+        {
+            grid_dep_wait(); // activations AND the expanded weights come from earlier kernels on the stream
+            int g = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x)
+            {
+                const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
+                for (int kb = 0; kb < nkb; ++kb, ++g)
+                {
+                    const int s = g % kLgStages;
+                    if (g >= kLgStages)
+                        mbar_wait(&empty[s], ((g / kLgStages) - 1) & 1);
+                    mbar_arrive_expect_tx(&full[s], kLgATile + kLgBTile);
+                    tma_load_2d(smA + s * kLgATile, &tmX, kb * 64, m_tile * kLgBM, &full[s]);
+                    tma_load_2d(smB + s * kLgBTile, &tmW, kb * 64, n_tile * kLgBN, &full[s]);
+                }
+            }
+        }
+    }
+    else if (warp == 1)
+    {
+        int g = 0, it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it)
+        {
+            const int buf = it & 1, use = it >> 1;
+            if (use > 0)
+            {
+                mbar_wait(&acc_empty[buf], (use - 1) & 1); // the epilogue has drained this accumulator
+                tc_fence_after();
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t) buf * kLgBN;
+            for (int kb = 0; kb < nkb; ++kb, ++g)
+            {
+                const int s = g % kLgStages;
+                mbar_wait(&full[s], (g / kLgStages) & 1);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_k_sw128(smem_u32(smA + s * kLgATile));
+                const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smB + s * kLgBTile));
+                if (elect_one_sync())
+                {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        tc_mma_ss(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, kIdesc, (kb | k4) != 0 ? 1u : 0u);
+                    tc_commit(&empty[s]);
+                    if (kb == nkb - 1)
+                        tc_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    else
+    {
+        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4, thread = one output row =====
+        const int quarter = warp & 3;
+        const int et = (int) threadIdx.x - 64; // 0..127
+        const uint32_t lane_field = (uint32_t) (quarter * 32) << 16;
+        const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it)
+        {
+            const int buf = it & 1, use = it >> 1;
+            const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
+            const int n0 = n_tile * kLgBN;
+            // column vectors of this tile -> shared memory (this buffer's previous reader finished two tiles ago)
+            for (int c = et; c < kLgBN; c += 128)
+            {
+                const int n = n0 + c;
+                sm_scale[buf * kLgBN + c] = n < p.N ? __half2float(__ldg(p.scales + n)) : 0.f;
+                sm_bias[buf * kLgBN + c] = (has_bias && n < p.N) ? __ldg(p.bias + n) : __float2half(0.f);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            const int m = m_tile * kLgBM + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            const size_t rbase = (size_t) m * p.ldc + n0;
+            const float* sc = sm_scale + buf * kLgBN;
+            const __half* bs = sm_bias + buf * kLgBN;
+#pragma unroll 1
+            for (int c16 = 0; c16 < kLgBN / 16; ++c16)
+            {
+                uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+                const bool cols_ok = n0 + c16 * 16 < p.N; // N is a multiple of 64: a 16-column group is in or out as a whole
+                if (has_res && row_ok && cols_ok)
+                {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rbase + c16 * 16);
+                    r0 = rp[0];
+                    r1 = rp[1];
+                }
+                uint32_t acc[16];
+                tc_ld_x16(tmem_base + lane_field + (uint32_t) buf * kLgBN + c16 * 16, acc);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const __half* rh0 = reinterpret_cast<const __half*>(&r0);
+                const __half* rh1 = reinterpret_cast<const __half*>(&r1);
+                __align__(16) __half o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                {
+                    const float v = __uint_as_float(acc[i]) * sc[c16 * 16 + i];
+                    o[i] = finish_output_tile<ACT>(v, has_bias, bs[c16 * 16 + i], has_res, i < 8 ? rh0[i] : rh1[i - 8]);
+                }
+                if (row_ok && cols_ok)
+                {
+                    uint4* cp = reinterpret_cast<uint4*>(p.C + rbase + c16 * 16);
+                    cp[0] = *reinterpret_cast<const uint4*>(&o[0]);
+                    cp[1] = *reinterpret_cast<const uint4*>(&o[8]);
+                }
+            }
+            // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+    {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1446,10 +1677,16 @@ bool woq_tc_can_fold_ln(int M, int N, int K)
 
 // tcgen05 path entry: any M >= 1.  fold_gamma != nullptr: A is the raw residual stream and the LayerNorm is folded
 // into the kernel (see TcParams).
+bool woq_large_applies(int M, int N, int K, size_t workspace_bytes);
+int woq_gemm_large(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
+    int activation, const __half* residual, __half* C, void* workspace, cudaStream_t stream);
+
 int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
     int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
     const __half* fold_gamma, const float* fold_c1s, const float* fold_c2, float ln_eps)
 {
+    if (fold_gamma == nullptr && workspace != nullptr && woq_large_applies(M, N, K, workspace_bytes))
+        return woq_gemm_large(A, M, K, W, scales, N, bias, activation, residual, C, workspace, stream);
     const TcPlan pl = plan_tc(M, N, K);
     B200_REQUIRE(pl.slab_bytes == 0 || (workspace != nullptr && workspace_bytes >= pl.slab_bytes), B200_ERR_WORKSPACE,
         "woq gemm: workspace of %zu bytes needed for split-K, got %zu", pl.slab_bytes, workspace_bytes);
@@ -1515,6 +1752,78 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     }
 }
 
+// ---- large-M path: host side ----
+static int g_large_m = -1; // rows from which the persistent large-M kernel is used (env B200_LARGE_M; 0 = never)
+static int large_m_threshold()
+{
+    if (g_large_m < 0)
+    {
+        const char* e = getenv("B200_LARGE_M");
+        g_large_m = e != nullptr ? atoi(e) : 4096;
+    }
+    return g_large_m;
+}
+
+bool woq_large_applies(int M, int N, int K, size_t workspace_bytes)
+{
+    const int thr = large_m_threshold();
+    return thr > 0 && M >= thr && N % 64 == 0 && K % 64 == 0 && workspace_bytes >= (size_t) N * K * sizeof(__half);
+}
+
+template <int ACT>
+static int launch_large(const CUtensorMap& tmX, const CUtensorMap& tmW, const LgParams& p, int grid, cudaStream_t stream)
+{
+    const size_t smem = 1024 + (size_t) kLgStages * (kLgATile + kLgBTile) + 128 + 2 * kLgBN * (sizeof(float) + sizeof(__half));
+    auto kern = woq_gemm_large_kernel<ACT>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_set = true;
+    }
+    B200_LAUNCH(kern, dim3(grid), dim3(kLgThreads), smem, stream, tmX, tmW, p);
+    return B200_OK;
+}
+
+int woq_gemm_large(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
+    int activation, const __half* residual, __half* C, void* workspace, cudaStream_t stream)
+{
+    __half* W16 = static_cast<__half*>(workspace);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W16) & 127) == 0
+            && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (residual == nullptr || (reinterpret_cast<uintptr_t>(residual) & 15) == 0),
+        B200_ERR_INVALID_ARG, "woq gemm (large M): A / C / residual must be 16-byte and the workspace 128-byte aligned");
+    {
+        const long long chunks = (long long) N * (K / 16);
+        B200_LAUNCH(woq_expand_fp16_kernel, dim3((unsigned) ((chunks + 255) / 256)), dim3(256), 0, stream, W, W16, N, K);
+    }
+    CUtensorMap tmX, tmW;
+    if (int rc = make_tmap_2d(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A, (uint64_t) K, (uint64_t) M, (uint64_t) K * 2, 64, kLgBM,
+            CU_TENSOR_MAP_SWIZZLE_128B))
+        return rc;
+    if (int rc = make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W16, (uint64_t) K, (uint64_t) N, (uint64_t) K * 2, 64, kLgBN,
+            CU_TENSOR_MAP_SWIZZLE_128B))
+        return rc;
+    LgParams p{};
+    p.scales = scales;
+    p.bias = bias;
+    p.residual = residual;
+    p.C = C;
+    p.M = M;
+    p.N = N;
+    p.ldc = N;
+    p.kb_total = K / 64;
+    p.m_tiles = (M + kLgBM - 1) / kLgBM;
+    p.n_tiles = (N + kLgBN - 1) / kLgBN;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    switch (activation)
+    {
+    case B200_ACT_GELU_ERF: return launch_large<B200_ACT_GELU_ERF>(tmX, tmW, p, grid, stream);
+    case B200_ACT_GELU_TANH: return launch_large<B200_ACT_GELU_TANH>(tmX, tmW, p, grid, stream);
+    default: return launch_large<B200_ACT_NONE>(tmX, tmW, p, grid, stream);
+    }
+}
+
 // Host-side launch plan of the tcgen05 path, exported for tests (no device work; without a GPU the SM count is 148).
 void woq_tc_plan_query(int M, int N, int K, int* mt, int* m_tiles, int* n_tiles, int* splits, int* cluster)
 {
@@ -1533,7 +1842,12 @@ size_t woq_tc_workspace_bytes(int max_m, int N, int K)
     (void) N;
     (void) K;
     const int MT = max_m <= 16 ? 16 : max_m <= 32 ? 32 : max_m <= 64 ? 64 : max_m <= 128 ? 128 : 256;
-    return (size_t) num_sms() * 128 * MT * sizeof(float);
+    size_t bytes = (size_t) num_sms() * 128 * MT * sizeof(float);
+    // large-M path: the weights expanded to fp16 live in the workspace for the duration of the call
+    const int thr = large_m_threshold();
+    if (thr > 0 && max_m >= thr && (size_t) N * K * sizeof(__half) > bytes)
+        bytes = (size_t) N * K * sizeof(__half);
+    return bytes;
 }
 
 template <int MT, int SS>
