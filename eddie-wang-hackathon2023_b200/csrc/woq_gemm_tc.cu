@@ -1155,7 +1155,27 @@ struct LgParams
     const __half* residual;
     __half* C;
     int M, N, ldc, kb_total, m_tiles, n_tiles;
+    int m_pairs; // multicast variant: pairs of m-tiles (the two CTAs of a cluster take m-tiles 2 i and 2 i + 1 of one n-tile)
 };
+
+// 2-D tiled TMA load delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA
+// in cta_mask of the cluster
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
 
 constexpr int kLgBM = 128, kLgBN = 256, kLgStages = 4, kLgThreads = 192;
 constexpr int kLgATile = kLgBM * 128, kLgBTile = kLgBN * 128; // bytes per stage (64 halves = 128 B per row)
@@ -1186,7 +1206,10 @@ __global__ void __launch_bounds__(256) woq_expand_fp16_kernel(const uint8_t* __r
     dst[1] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
 }
 
-template <int ACT>
+// MC: clusters of two CTAs work on two m-tiles of the same n-tile; each CTA fetches half of the 256-column weight tile
+// and multicasts it to both (L2 -> SM traffic per k-block 32 KB instead of 48 KB per CTA: the kernel without it sits at
+// the L2 feed rate, 148 SMs x 48 KB per 2.1 M MACs).  A stage is refilled only after BOTH CTAs' MMAs have released it.
+template <int ACT, bool MC>
 __global__ void __launch_bounds__(kLgThreads, 1)
     woq_gemm_large_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const LgParams p)
 {
@@ -1205,14 +1228,24 @@ __global__ void __launch_bounds__(kLgThreads, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.kb_total;
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    const uint32_t crank = MC ? cluster_ctarank() : 0u;
+    // work items: tiles (plain) or pairs of m-tiles (multicast); every role walks the same sequence
+    const int t_first = MC ? (int) (blockIdx.x >> 1) : (int) blockIdx.x;
+    const int t_stride = MC ? (int) (gridDim.x >> 1) : (int) gridDim.x;
+    const int num_tiles = (MC ? p.m_pairs : p.m_tiles) * p.n_tiles;
+    auto tile_of = [&](int t, int& m_tile, int& n_tile)
+    {
+        const int mq = t / p.n_tiles;
+        n_tile = t - mq * p.n_tiles;
+        m_tile = MC ? 2 * mq + (int) crank : mq;
+    };
 
     if (threadIdx.x == 0)
     {
         for (int s = 0; s < kLgStages; ++s)
         {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], MC ? 2 : 1);
         }
         for (int b = 0; b < 2; ++b)
         {
@@ -1232,6 +1265,8 @@ __global__ void __launch_bounds__(kLgThreads, 1)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if constexpr (MC)
+        cluster_sync_all(); // both CTAs' barriers exist before either multicasts into the other
     grid_dep_launch_dependents();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -1241,17 +1276,23 @@ __global__ void __launch_bounds__(kLgThreads, 1)
         {
             grid_dep_wait(); // activations AND the expanded weights come from earlier kernels on the stream
             int g = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x)
+            for (int t = t_first; t < num_tiles; t += t_stride)
             {
-                const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
+                int m_tile, n_tile;
+                tile_of(t, m_tile, n_tile);
+                const int m_load = m_tile < p.m_tiles ? m_tile : p.m_tiles - 1; // odd tail: load valid rows, store nothing
                 for (int kb = 0; kb < nkb; ++kb, ++g)
                 {
                     const int s = g % kLgStages;
                     if (g >= kLgStages)
                         mbar_wait(&empty[s], ((g / kLgStages) - 1) & 1);
                     mbar_arrive_expect_tx(&full[s], kLgATile + kLgBTile);
-                    tma_load_2d(smA + s * kLgATile, &tmX, kb * 64, m_tile * kLgBM, &full[s]);
-                    tma_load_2d(smB + s * kLgBTile, &tmW, kb * 64, n_tile * kLgBN, &full[s]);
+                    tma_load_2d(smA + s * kLgATile, &tmX, kb * 64, m_load * kLgBM, &full[s]);
+                    if constexpr (MC)
+                        tma_load_2d_mc(smB + s * kLgBTile + crank * (kLgBTile / 2), &tmW, kb * 64,
+                            n_tile * kLgBN + (int) crank * (kLgBN / 2), &full[s], (uint16_t) 3);
+                    else
+                        tma_load_2d(smB + s * kLgBTile, &tmW, kb * 64, n_tile * kLgBN, &full[s]);
                 }
             }
         }
@@ -1259,7 +1300,7 @@ __global__ void __launch_bounds__(kLgThreads, 1)
     else if (warp == 1)
     {
         int g = 0, it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it)
+        for (int t = t_first; t < num_tiles; t += t_stride, ++it)
         {
             const int buf = it & 1, use = it >> 1;
             if (use > 0)
@@ -1280,7 +1321,10 @@ __global__ void __launch_bounds__(kLgThreads, 1)
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
                         tc_mma_ss(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, kIdesc, (kb | k4) != 0 ? 1u : 0u);
-                    tc_commit(&empty[s]);
+                    if constexpr (MC)
+                        tc_commit_mc(&empty[s], (uint16_t) 3); // the stage is shared: both producers wait for both MMAs
+                    else
+                        tc_commit(&empty[s]);
                     if (kb == nkb - 1)
                         tc_commit(&acc_full[buf]);
                 }
@@ -1296,10 +1340,11 @@ __global__ void __launch_bounds__(kLgThreads, 1)
         const uint32_t lane_field = (uint32_t) (quarter * 32) << 16;
         const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr;
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it)
+        for (int t = t_first; t < num_tiles; t += t_stride, ++it)
         {
             const int buf = it & 1, use = it >> 1;
-            const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
+            int m_tile, n_tile;
+            tile_of(t, m_tile, n_tile);
             const int n0 = n_tile * kLgBN;
             // column vectors of this tile -> shared memory (this buffer's previous reader finished two tiles ago)
             for (int c = et; c < kLgBN; c += 128)
@@ -1316,34 +1361,53 @@ __global__ void __launch_bounds__(kLgThreads, 1)
             const size_t rbase = (size_t) m * p.ldc + n0;
             const float* sc = sm_scale + buf * kLgBN;
             const __half* bs = sm_bias + buf * kLgBN;
-#pragma unroll 1
-            for (int c16 = 0; c16 < kLgBN / 16; ++c16)
+            // 32 columns per iteration; the residual of the NEXT 32 columns is requested before this iteration's TMEM
+            // read (a dependent global load per 16 columns made the epilogue, not the main loop, the limit of the K = 1280
+            // GEMMs with a residual: 118 us against 69 us for the plain product at M = 24000)
+            const bool res_row = has_res && row_ok;
+            uint4 rn[4];
+            auto fetch_res = [&](int c32)
             {
-                uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-                const bool cols_ok = n0 + c16 * 16 < p.N; // N is a multiple of 64: a 16-column group is in or out as a whole
-                if (has_res && row_ok && cols_ok)
-                {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rbase + c16 * 16);
-                    r0 = rp[0];
-                    r1 = rp[1];
-                }
-                uint32_t acc[16];
-                tc_ld_x16(tmem_base + lane_field + (uint32_t) buf * kLgBN + c16 * 16, acc);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const __half* rh0 = reinterpret_cast<const __half*>(&r0);
-                const __half* rh1 = reinterpret_cast<const __half*>(&r1);
-                __align__(16) __half o[16];
+                const bool ok = res_row && n0 + c32 * 32 < p.N; // N is a multiple of 64: a 32-column group is in or out as a whole
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rbase + c32 * 32);
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
+                for (int q = 0; q < 4; ++q)
+                    rn[q] = ok ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
+            };
+            fetch_res(0);
+#pragma unroll 1
+            for (int c32 = 0; c32 < kLgBN / 32; ++c32)
+            {
+                uint4 rc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    rc[q] = rn[q];
+                if (c32 + 1 < kLgBN / 32)
+                    fetch_res(c32 + 1);
+                const bool cols_ok = n0 + c32 * 32 < p.N;
+                uint32_t acc[32];
+                tc_ld_x32(tmem_base + lane_field + (uint32_t) buf * kLgBN + c32 * 32, acc);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const __half* rh = reinterpret_cast<const __half*>(rc);
+                __align__(16) __half o[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
                 {
-                    const float v = __uint_as_float(acc[i]) * sc[c16 * 16 + i];
-                    o[i] = finish_output_tile<ACT>(v, has_bias, bs[c16 * 16 + i], has_res, i < 8 ? rh0[i] : rh1[i - 8]);
+                    const float4 s4 = *reinterpret_cast<const float4*>(sc + c32 * 32 + q * 4);
+                    const uint2 b4 = *reinterpret_cast<const uint2*>(bs + c32 * 32 + q * 4);
+                    const __half* bh = reinterpret_cast<const __half*>(&b4);
+                    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        o[q * 4 + i] = finish_output_tile<ACT>(__uint_as_float(acc[q * 4 + i]) * sv[i], has_bias, bh[i], has_res,
+                            rh[q * 4 + i]);
                 }
                 if (row_ok && cols_ok)
                 {
-                    uint4* cp = reinterpret_cast<uint4*>(p.C + rbase + c16 * 16);
-                    cp[0] = *reinterpret_cast<const uint4*>(&o[0]);
-                    cp[1] = *reinterpret_cast<const uint4*>(&o[8]);
+                    uint4* cp = reinterpret_cast<uint4*>(p.C + rbase + c32 * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        cp[q] = *reinterpret_cast<const uint4*>(&o[q * 8]);
                 }
             }
             // accumulator drained: hand it back to the MMA warp
@@ -1355,6 +1419,8 @@ __global__ void __launch_bounds__(kLgThreads, 1)
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (MC)
+        cluster_sync_all(); // no CTA leaves while its mate may still multicast into it or arrive on its barriers
     if (warp == 1)
     {
         tc_fence_after();
@@ -1770,19 +1836,57 @@ bool woq_large_applies(int M, int N, int K, size_t workspace_bytes)
     return thr > 0 && M >= thr && N % 64 == 0 && K % 64 == 0 && workspace_bytes >= (size_t) N * K * sizeof(__half);
 }
 
-template <int ACT>
+template <int ACT, bool MC>
 static int launch_large(const CUtensorMap& tmX, const CUtensorMap& tmW, const LgParams& p, int grid, cudaStream_t stream)
 {
     const size_t smem = 1024 + (size_t) kLgStages * (kLgATile + kLgBTile) + 128 + 2 * kLgBN * (sizeof(float) + sizeof(__half));
-    auto kern = woq_gemm_large_kernel<ACT>;
+    auto kern = woq_gemm_large_kernel<ACT, MC>;
     static bool attr_set = false;
     if (!attr_set)
     {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr_set = true;
     }
-    B200_LAUNCH(kern, dim3(grid), dim3(kLgThreads), smem, stream, tmX, tmW, p);
+    if constexpr (!MC)
+    {
+        B200_LAUNCH(kern, dim3(grid), dim3(kLgThreads), smem, stream, tmX, tmW, p);
+        return B200_OK;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kLgThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl_enabled())
+    {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    count_launch();
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p));
     return B200_OK;
+}
+
+template <bool MC>
+static int launch_large_act(int activation, const CUtensorMap& tmX, const CUtensorMap& tmW, const LgParams& p, int grid,
+    cudaStream_t stream)
+{
+    switch (activation)
+    {
+    case B200_ACT_GELU_ERF: return launch_large<B200_ACT_GELU_ERF, MC>(tmX, tmW, p, grid, stream);
+    case B200_ACT_GELU_TANH: return launch_large<B200_ACT_GELU_TANH, MC>(tmX, tmW, p, grid, stream);
+    default: return launch_large<B200_ACT_NONE, MC>(tmX, tmW, p, grid, stream);
+    }
 }
 
 int woq_gemm_large(const __half* A, int M, int K, const uint8_t* W, const __half* scales, int N, const __half* bias,
@@ -1800,8 +1904,10 @@ int woq_gemm_large(const __half* A, int M, int K, const uint8_t* W, const __half
     if (int rc = make_tmap_2d(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A, (uint64_t) K, (uint64_t) M, (uint64_t) K * 2, 64, kLgBM,
             CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
-    if (int rc = make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W16, (uint64_t) K, (uint64_t) N, (uint64_t) K * 2, 64, kLgBN,
-            CU_TENSOR_MAP_SWIZZLE_128B))
+    // multicast variant (default; env B200_LARGE_MC=0: every CTA fetches its whole weight tile): a box is half a weight tile
+    static const bool mc = [] { const char* e = getenv("B200_LARGE_MC"); return e == nullptr || e[0] != '0'; }();
+    if (int rc = make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W16, (uint64_t) K, (uint64_t) N, (uint64_t) K * 2, 64,
+            mc ? kLgBN / 2 : kLgBN, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
     LgParams p{};
     p.scales = scales;
@@ -1814,14 +1920,14 @@ int woq_gemm_large(const __half* A, int M, int K, const uint8_t* W, const __half
     p.kb_total = K / 64;
     p.m_tiles = (M + kLgBM - 1) / kLgBM;
     p.n_tiles = (N + kLgBN - 1) / kLgBN;
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    switch (activation)
+    p.m_pairs = (p.m_tiles + 1) / 2;
+    if (mc)
     {
-    case B200_ACT_GELU_ERF: return launch_large<B200_ACT_GELU_ERF>(tmX, tmW, p, grid, stream);
-    case B200_ACT_GELU_TANH: return launch_large<B200_ACT_GELU_TANH>(tmX, tmW, p, grid, stream);
-    default: return launch_large<B200_ACT_NONE>(tmX, tmW, p, grid, stream);
+        const int items = p.m_pairs * p.n_tiles, clusters = num_sms() / 2;
+        return launch_large_act<true>(activation, tmX, tmW, p, 2 * (items < clusters ? items : clusters), stream);
     }
+    const int tiles = p.m_tiles * p.n_tiles;
+    return launch_large_act<false>(activation, tmX, tmW, p, tiles < num_sms() ? tiles : num_sms(), stream);
 }
 
 // Host-side launch plan of the tcgen05 path, exported for tests (no device work; without a GPU the SM count is 148).

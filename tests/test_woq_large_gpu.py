@@ -63,9 +63,9 @@ def test_large_m_path_equals_the_tiled_kernel_and_the_reference_tolerance(m, k, 
     if act == "none" and k <= 1280:
         assert torch.equal(out, ref), f"max diff {(out.float() - ref.float()).abs().max().item()}"
     elif act == "none":
-        # deep K: the per-tile kernel splits K over CTAs at 2048 rows (another summation order): one fp16 ulp apart at most
+        # deep K: the per-tile kernel splits K over CTAs at 2048 rows (another summation order): a couple of fp16 ulps apart at most (product and residual add both round)
         d = (out.float() - ref.float()).abs()
-        assert (d <= ref.float().abs() * 2.0 ** -10 + 1e-3).all(), f"max diff {d.max().item()}"
+        assert (d <= ref.float().abs() * 2.0 ** -9 + 2e-3).all(), f"max diff {d.max().item()}"
     else:
         # the two epilogues share finish_output_tile: same bits expected here too, but GELU may amplify a last-bit difference
         assert (out.float() - ref.float()).abs().max().item() <= 1e-3
