@@ -1145,7 +1145,7 @@ __global__ void __launch_bounds__(192, 1)
 //  * warp 0 (one lane): TMA producer, 4 stages of (16 KB activations + 32 KB weights), 128B swizzle;
 //  * warp 1 (one lane): tcgen05.mma issuer; the 512 TMEM columns hold TWO 128 x 256 accumulators, so the MMAs of tile
 //    i + 1 run while
-//  * warps 2-5 drain tile i: tcgen05.ld 16 columns at a time, column scale in fp32, bias / GELU / residual with the
+//  * warps 2-9 drain tile i: tcgen05.ld 16 columns at a time, column scale in fp32, bias / GELU / residual with the
 //    same rounding sequence as finish_output_tile, 32-byte vector stores (a thread owns a row: 16 consecutive columns).
 // =====================================================================================================
 struct LgParams
@@ -1177,7 +1177,7 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask)
                  : "memory");
 }
 
-constexpr int kLgBM = 128, kLgBN = 256, kLgStages = 4, kLgThreads = 192;
+constexpr int kLgBM = 128, kLgBN = 256, kLgStages = 4, kLgThreads = 320; // producer, MMA issuer, 8 epilogue warps
 constexpr int kLgATile = kLgBM * 128, kLgBTile = kLgBN * 128; // bytes per stage (64 halves = 128 B per row)
 
 // int8 (reference layout, [N/2][2K] bytes) -> fp16 exact integers [N][K]; one thread per 16-byte chunk = 16 k values
@@ -1250,7 +1250,7 @@ __global__ void __launch_bounds__(kLgThreads, 1)
         for (int b = 0; b < 2; ++b)
         {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4);
+            mbar_init(&acc_empty[b], 8);
         }
         fence_mbar_init();
         tma_prefetch_desc(&tmX);
@@ -1334,9 +1334,11 @@ __global__ void __launch_bounds__(kLgThreads, 1)
     }
     else
     {
-        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4, thread = one output row =====
+        // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, thread = one output row; warps 2-5 take the first 128
+        // columns of the tile, warps 6-9 the other 128 (a GELU epilogue on four warps alone did not keep up with the main loop)
         const int quarter = warp & 3;
-        const int et = (int) threadIdx.x - 64; // 0..127
+        const int et = (int) threadIdx.x - 64; // 0..255
+        const int chalf = et >> 7;
         const uint32_t lane_field = (uint32_t) (quarter * 32) << 16;
         const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr;
         int it = 0;
@@ -1347,13 +1349,13 @@ __global__ void __launch_bounds__(kLgThreads, 1)
             tile_of(t, m_tile, n_tile);
             const int n0 = n_tile * kLgBN;
             // column vectors of this tile -> shared memory (this buffer's previous reader finished two tiles ago)
-            for (int c = et; c < kLgBN; c += 128)
             {
+                const int c = et;
                 const int n = n0 + c;
                 sm_scale[buf * kLgBN + c] = n < p.N ? __half2float(__ldg(p.scales + n)) : 0.f;
                 sm_bias[buf * kLgBN + c] = (has_bias && n < p.N) ? __ldg(p.bias + n) : __float2half(0.f);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
             const int m = m_tile * kLgBM + quarter * 32 + lane;
@@ -1374,15 +1376,16 @@ __global__ void __launch_bounds__(kLgThreads, 1)
                 for (int q = 0; q < 4; ++q)
                     rn[q] = ok ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
             };
-            fetch_res(0);
+            const int c32_0 = chalf * (kLgBN / 64), c32_1 = c32_0 + kLgBN / 64;
+            fetch_res(c32_0);
 #pragma unroll 1
-            for (int c32 = 0; c32 < kLgBN / 32; ++c32)
+            for (int c32 = c32_0; c32 < c32_1; ++c32)
             {
                 uint4 rc[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     rc[q] = rn[q];
-                if (c32 + 1 < kLgBN / 32)
+                if (c32 + 1 < c32_1)
                     fetch_res(c32 + 1);
                 const bool cols_ok = n0 + c32 * 32 < p.N;
                 uint32_t acc[32];
