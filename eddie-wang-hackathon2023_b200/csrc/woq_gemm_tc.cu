@@ -65,9 +65,15 @@ struct TcParams
     int splits;
     int cluster;  // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
     int x3_depth; // > 0: tmX is a 3-D map (64 k, rows, k-blocks) whose box holds this many k-blocks: ONE activation load
+    int mma_burst; // 1: decode launches issue all their MMAs after one wait (env B200_TC_BURST=0 restores the per-block loop)
     long long* gt;  // optional: 4 global-timer values of this launch (min entry, min dependency return, max store, -)
     long long* dbg; // optional: clock64() stamps of CTA (0,0,0) at the phase boundaries (b200_debug_tc_timing)
 };
+
+__device__ __forceinline__ bool tc_burst_enabled(const TcParams& p)
+{
+    return p.mma_burst != 0;
+}
 
 __device__ __forceinline__ long long global_timer_ns()
 {
@@ -421,6 +427,40 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     {
         // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
         const uint32_t d_tmem = tmem_base + kDCol;
+        // Decode launches (the CTA's whole k range fits the TMEM A ring and arrives on ONE activation barrier): the per
+        // k-block loop below costs ~490 cycles per block on the critical path (barrier try-wait, fence, election,
+        // descriptor set-up in front of every four MMAs: 2200 of the 5300 cycles a 5-block projection spends after its
+        // dependency, tools/tc_timing_insitu.py).  Here every A stage is awaited BEFORE the activation barrier (they complete
+        // ahead of the dependency), and once the activations land all 4 nkb MMAs are issued back to back.
+        const bool burst = x_single && nkb <= AS && nkb > 0 && tc_burst_enabled(p);
+        if (burst)
+        {
+            for (int i = 0; i < nkb; ++i)
+                mbar_wait(&a_ready[i], 0);
+            mbar_wait(&xfull[0], 0);
+            tc_fence_after();
+            if (lane == 0)
+                TC_STAMP(16 + 2);
+            const uint64_t bdesc0 = umma_desc_k_sw128(smem_u32(smX));
+            if (elect_one_sync())
+            {
+#pragma unroll 1
+                for (int i = 0; i < nkb; ++i)
+                {
+                    // stage i: activation tile i (XTileBytes apart: the descriptor's 14-bit start address counts 16-byte
+                    // units) against TMEM A stage i
+                    const uint64_t bdesc = bdesc0 + (uint64_t) (i * (XTileBytes >> 4));
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        tc_mma_ts(d_tmem, tmem_base + i * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
+                }
+                tc_commit(acc_done);
+            }
+            __syncwarp();
+            if (lane == 0)
+                TC_STAMP(16 + 4 * (nkb - 1 < 11 ? nkb - 1 : 11) + 3);
+        }
+        else
         for (int i = 0; i < nkb; ++i)
         {
             const int ss = i % SS, as = i % AS;
@@ -1786,6 +1826,8 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
         return rc;
     TcParams p{};
     p.x3_depth = x3_depth;
+    static const bool burst_on = getenv("B200_TC_BURST") == nullptr || getenv("B200_TC_BURST")[0] != '0';
+    p.mma_burst = burst_on ? 1 : 0;
     p.scales = scales;
     p.bias = bias;
     p.residual = residual;
