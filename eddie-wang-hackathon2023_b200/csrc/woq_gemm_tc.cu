@@ -1246,6 +1246,67 @@ __global__ void __launch_bounds__(256) woq_expand_fp16_kernel(const uint8_t* __r
     dst[1] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
 }
 
+// Epilogue of one 128 x 256 tile for one thread (= output row m): this warp's half of the columns (chalf) from the TMEM
+// accumulator at tmem_acc (lane field and accumulator column offset included), scale / bias from shared memory.
+template <int ACT>
+__device__ __forceinline__ void lg_drain_tile(const LgParams& p, uint32_t tmem_acc, const float* sc, const __half* bs, int m, int n0,
+    int chalf)
+{
+    const bool has_bias = p.bias != nullptr, has_res = p.residual != nullptr;
+    const bool row_ok = m < p.M;
+    const size_t rbase = (size_t) m * p.ldc + n0;
+    // 32 columns per iteration; the residual of the NEXT 32 columns is requested before this iteration's TMEM
+    // read (a dependent global load per 16 columns made the epilogue, not the main loop, the limit of the K = 1280
+    // GEMMs with a residual: 118 us against 69 us for the plain product at M = 24000)
+    const bool res_row = has_res && row_ok;
+    uint4 rn[4];
+    auto fetch_res = [&](int c32)
+    {
+        const bool ok = res_row && n0 + c32 * 32 < p.N; // N is a multiple of 64: a 32-column group is in or out as a whole
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rbase + c32 * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            rn[q] = ok ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
+    };
+    const int c32_0 = chalf * (kLgBN / 64), c32_1 = c32_0 + kLgBN / 64;
+    fetch_res(c32_0);
+#pragma unroll 1
+    for (int c32 = c32_0; c32 < c32_1; ++c32)
+    {
+        uint4 rc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            rc[q] = rn[q];
+        if (c32 + 1 < c32_1)
+            fetch_res(c32 + 1);
+        const bool cols_ok = n0 + c32 * 32 < p.N;
+        uint32_t acc[32];
+        tc_ld_x32(tmem_acc + c32 * 32, acc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const __half* rh = reinterpret_cast<const __half*>(rc);
+        __align__(16) __half o[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+        {
+            const float4 s4 = *reinterpret_cast<const float4*>(sc + c32 * 32 + q * 4);
+            const uint2 b4 = *reinterpret_cast<const uint2*>(bs + c32 * 32 + q * 4);
+            const __half* bh = reinterpret_cast<const __half*>(&b4);
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                o[q * 4 + i] = finish_output_tile<ACT>(__uint_as_float(acc[q * 4 + i]) * sv[i], has_bias, bh[i], has_res,
+                    rh[q * 4 + i]);
+        }
+        if (row_ok && cols_ok)
+        {
+            uint4* cp = reinterpret_cast<uint4*>(p.C + rbase + c32 * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                cp[q] = *reinterpret_cast<const uint4*>(&o[q * 8]);
+        }
+    }
+}
+
 // MC: clusters of two CTAs work on two m-tiles of the same n-tile; each CTA fetches half of the 256-column weight tile
 // and multicasts it to both (L2 -> SM traffic per k-block 32 KB instead of 48 KB per CTA: the kernel without it sits at
 // the L2 feed rate, 148 SMs x 48 KB per 2.1 M MACs).  A stage is refilled only after BOTH CTAs' MMAs have released it.
@@ -1398,61 +1459,8 @@ __global__ void __launch_bounds__(kLgThreads, 1)
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
-            const int m = m_tile * kLgBM + quarter * 32 + lane;
-            const bool row_ok = m < p.M;
-            const size_t rbase = (size_t) m * p.ldc + n0;
-            const float* sc = sm_scale + buf * kLgBN;
-            const __half* bs = sm_bias + buf * kLgBN;
-            // 32 columns per iteration; the residual of the NEXT 32 columns is requested before this iteration's TMEM
-            // read (a dependent global load per 16 columns made the epilogue, not the main loop, the limit of the K = 1280
-            // GEMMs with a residual: 118 us against 69 us for the plain product at M = 24000)
-            const bool res_row = has_res && row_ok;
-            uint4 rn[4];
-            auto fetch_res = [&](int c32)
-            {
-                const bool ok = res_row && n0 + c32 * 32 < p.N; // N is a multiple of 64: a 32-column group is in or out as a whole
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rbase + c32 * 32);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    rn[q] = ok ? rp[q] : make_uint4(0u, 0u, 0u, 0u);
-            };
-            const int c32_0 = chalf * (kLgBN / 64), c32_1 = c32_0 + kLgBN / 64;
-            fetch_res(c32_0);
-#pragma unroll 1
-            for (int c32 = c32_0; c32 < c32_1; ++c32)
-            {
-                uint4 rc[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    rc[q] = rn[q];
-                if (c32 + 1 < c32_1)
-                    fetch_res(c32 + 1);
-                const bool cols_ok = n0 + c32 * 32 < p.N;
-                uint32_t acc[32];
-                tc_ld_x32(tmem_base + lane_field + (uint32_t) buf * kLgBN + c32 * 32, acc);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const __half* rh = reinterpret_cast<const __half*>(rc);
-                __align__(16) __half o[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                {
-                    const float4 s4 = *reinterpret_cast<const float4*>(sc + c32 * 32 + q * 4);
-                    const uint2 b4 = *reinterpret_cast<const uint2*>(bs + c32 * 32 + q * 4);
-                    const __half* bh = reinterpret_cast<const __half*>(&b4);
-                    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        o[q * 4 + i] = finish_output_tile<ACT>(__uint_as_float(acc[q * 4 + i]) * sv[i], has_bias, bh[i], has_res,
-                            rh[q * 4 + i]);
-                }
-                if (row_ok && cols_ok)
-                {
-                    uint4* cp = reinterpret_cast<uint4*>(p.C + rbase + c32 * 32);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        cp[q] = *reinterpret_cast<const uint4*>(&o[q * 8]);
-                }
-            }
+            lg_drain_tile<ACT>(p, tmem_base + lane_field + (uint32_t) buf * kLgBN, sm_scale + buf * kLgBN, sm_bias + buf * kLgBN,
+                m_tile * kLgBM + quarter * 32 + lane, n0, chalf);
             // accumulator drained: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -1468,6 +1476,210 @@ __global__ void __launch_bounds__(kLgThreads, 1)
     {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- CTA-pair variant (tcgen05 cta_group::2) -------------------------------------------------------------------------
+// The two CTAs of a cluster compute ONE 256 x 256 tile: CTA r stages activation rows [128 r, 128 r + 128) and weight
+// columns [128 r, 128 r + 128) of every k-block (32 KB per stage instead of 48: SIX stages in flight), the leader (rank 0)
+// issues tcgen05.mma.cta_group::2 (UMMA M = 256, N = 256), which reads both CTAs' shared memory and writes 128 rows x 256
+// columns into each CTA's TMEM.  Barriers: the TMA loads of both CTAs signal the LEADER's `full` barrier (2 producer arrivals
+// + 64 KB of transactions per stage); the leader's tcgen05.commit multicasts its arrival to both CTAs' `empty` and `acc_full`
+// barriers; the epilogue warps of both CTAs arrive on the LEADER's `acc_empty` (16 arrivals).
+constexpr int kL2Stages = 6, kL2BTile = 128 * 128;
+
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes)
+{
+    // (no .release.cluster: that form compiles to MEMBAR.ALL.GPU + ERRBAR per stage and starved the pipeline -- tensor pipe
+    // 33 % active; arming a barrier orders nothing)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: data to THIS CTA's shared memory, completion on the barrier at cluster address mbar_cluster
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, int c0, int c1, uint32_t mbar_cluster)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(mbar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kLgThreads, 1)
+    woq_gemm_large2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const LgParams p)
+{
+    constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t) (kLgBN >> 3) << 17) | ((uint32_t) ((2 * kLgBM) >> 4) << 24);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + kL2Stages * kLgATile;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smB + kL2Stages * kL2BTile);
+    uint64_t* empty = full + kL2Stages;
+    uint64_t* acc_full = empty + kL2Stages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* sm_scale = reinterpret_cast<float*>(tmem_slot + 4);          // [2][256]
+    __half* sm_bias = reinterpret_cast<__half*>(sm_scale + 2 * kLgBN);  // [2][256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.kb_total;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int t_first = (int) (blockIdx.x >> 1), t_stride = (int) (gridDim.x >> 1);
+    const int num_tiles = p.m_pairs * p.n_tiles;
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < kL2Stages; ++s)
+        {
+            mbar_init(&full[s], 2);  // (leader's copy is the one in use) one arrive.expect_tx per CTA of the pair
+            mbar_init(&empty[s], 1); // the leader's commit, multicast to both CTAs
+        }
+        for (int b = 0; b < 2; ++b)
+        {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 16); // (leader's copy) the eight epilogue warps of both CTAs
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1)
+    {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster_sync_all(); // both CTAs' barriers and TMEM exist before any cross-CTA traffic
+    grid_dep_launch_dependents();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0)
+    {
+        if (elect_one_sync())
+        {
+            grid_dep_wait();
+            int g = 0;
+            for (int t = t_first; t < num_tiles; t += t_stride)
+            {
+                const int mq = t / p.n_tiles, n_tile = t - mq * p.n_tiles;
+                const int m_tile = 2 * mq + (int) crank;
+                const int m_load = m_tile < p.m_tiles ? m_tile : p.m_tiles - 1;
+                for (int kb = 0; kb < nkb; ++kb, ++g)
+                {
+                    const int s = g % kL2Stages;
+                    if (g >= kL2Stages)
+                        mbar_wait(&empty[s], ((g / kL2Stages) - 1) & 1);
+                    const uint32_t lfull = mapa_u32(smem_u32(&full[s]), 0u); // the leader's barrier
+                    mbar_arrive_expect_tx_cluster(lfull, kLgATile + kL2BTile);
+                    tma_load_2d_pair(smA + s * kLgATile, &tmX, kb * 64, m_load * kLgBM, lfull);
+                    tma_load_2d_pair(smB + s * kL2BTile, &tmW, kb * 64, n_tile * kLgBN + (int) crank * (kLgBN / 2), lfull);
+                }
+            }
+        }
+    }
+    else if (warp == 1)
+    {
+        // one lane runs the whole issue loop (no election, reconvergence or descriptor set-up per k-block: the loop has to
+        // stay well under the 512 cycles of tensor work a k-block holds)
+        if (leader && elect_one_sync())
+        {
+            const uint64_t adesc0 = umma_desc_k_sw128(smem_u32(smA)), bdesc0 = umma_desc_k_sw128(smem_u32(smB));
+            int g = 0, it = 0, s = 0;
+            uint32_t ph = 0;
+            for (int t = t_first; t < num_tiles; t += t_stride, ++it)
+            {
+                const int buf = it & 1, use = it >> 1;
+                if (use > 0)
+                {
+                    mbar_wait(&acc_empty[buf], (use - 1) & 1); // both CTAs' epilogues have drained this accumulator
+                    tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t) buf * kLgBN;
+                for (int kb = 0; kb < nkb; ++kb, ++g)
+                {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    // the descriptors' 14-bit start-address field counts 16-byte units: stage s is s tiles further
+                    const uint64_t adesc = adesc0 + (uint64_t) (s * (kLgATile >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t) (s * (kL2BTile >> 4));
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        tc_mma_ss_pair(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, kIdesc, (kb | k4) != 0 ? 1u : 0u);
+                    tc_commit_pair(&empty[s], (uint16_t) 3);
+                    if (kb == nkb - 1)
+                        tc_commit_pair(&acc_full[buf], (uint16_t) 3);
+                    if (++s == kL2Stages)
+                    {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    }
+    else
+    {
+        const int quarter = warp & 3;
+        const int et = (int) threadIdx.x - 64; // 0..255
+        const int chalf = et >> 7;
+        const uint32_t lane_field = (uint32_t) (quarter * 32) << 16;
+        const bool has_bias = p.bias != nullptr;
+        int it = 0;
+        for (int t = t_first; t < num_tiles; t += t_stride, ++it)
+        {
+            const int buf = it & 1, use = it >> 1;
+            const int mq = t / p.n_tiles, n_tile = t - mq * p.n_tiles;
+            const int m_tile = 2 * mq + (int) crank;
+            const int n0 = n_tile * kLgBN;
+            {
+                const int n = n0 + et;
+                sm_scale[buf * kLgBN + et] = n < p.N ? __half2float(__ldg(p.scales + n)) : 0.f;
+                sm_bias[buf * kLgBN + et] = (has_bias && n < p.N) ? __ldg(p.bias + n) : __float2half(0.f);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            lg_drain_tile<ACT>(p, tmem_base + lane_field + (uint32_t) buf * kLgBN, sm_scale + buf * kLgBN, sm_bias + buf * kLgBN,
+                m_tile * kLgBM + quarter * 32 + lane, n0, chalf);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0u));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1)
+    {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -1922,6 +2134,53 @@ static int launch_large(const CUtensorMap& tmX, const CUtensorMap& tmW, const Lg
     return B200_OK;
 }
 
+template <int ACT>
+static int launch_large2(const CUtensorMap& tmX, const CUtensorMap& tmW, const LgParams& p, int grid, cudaStream_t stream)
+{
+    const size_t smem = 1024 + (size_t) kL2Stages * (kLgATile + kL2BTile) + 256 + 2 * kLgBN * (sizeof(float) + sizeof(__half));
+    auto kern = woq_gemm_large2_kernel<ACT>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kLgThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl_enabled())
+    {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    count_launch();
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p));
+    return B200_OK;
+}
+
+static int launch_large2_act(int activation, const CUtensorMap& tmX, const CUtensorMap& tmW, const LgParams& p, int grid,
+    cudaStream_t stream)
+{
+    switch (activation)
+    {
+    case B200_ACT_GELU_ERF: return launch_large2<B200_ACT_GELU_ERF>(tmX, tmW, p, grid, stream);
+    case B200_ACT_GELU_TANH: return launch_large2<B200_ACT_GELU_TANH>(tmX, tmW, p, grid, stream);
+    default: return launch_large2<B200_ACT_NONE>(tmX, tmW, p, grid, stream);
+    }
+}
+
 template <bool MC>
 static int launch_large_act(int activation, const CUtensorMap& tmX, const CUtensorMap& tmW, const LgParams& p, int grid,
     cudaStream_t stream)
@@ -1949,8 +2208,10 @@ int woq_gemm_large(const __half* A, int M, int K, const uint8_t* W, const __half
     if (int rc = make_tmap_2d(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A, (uint64_t) K, (uint64_t) M, (uint64_t) K * 2, 64, kLgBM,
             CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
-    // multicast variant (default; env B200_LARGE_MC=0: every CTA fetches its whole weight tile): a box is half a weight tile
-    static const bool mc = [] { const char* e = getenv("B200_LARGE_MC"); return e == nullptr || e[0] != '0'; }();
+    // B200_LARGE_MC: 2 (default) = CTA-pair MMA (tcgen05 cta_group::2), 1 = two independent MMAs with the weight tile
+    // multicast, 0 = every CTA fetches its whole weight tile.  In modes 1 and 2 a TMA box is half a weight tile.
+    static const int mode = [] { const char* e = getenv("B200_LARGE_MC"); return e == nullptr ? 2 : atoi(e); }();
+    const bool mc = mode != 0;
     if (int rc = make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, W16, (uint64_t) K, (uint64_t) N, (uint64_t) K * 2, 64,
             mc ? kLgBN / 2 : kLgBN, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
@@ -1969,7 +2230,10 @@ int woq_gemm_large(const __half* A, int M, int K, const uint8_t* W, const __half
     if (mc)
     {
         const int items = p.m_pairs * p.n_tiles, clusters = num_sms() / 2;
-        return launch_large_act<true>(activation, tmX, tmW, p, 2 * (items < clusters ? items : clusters), stream);
+        const int grid = 2 * (items < clusters ? items : clusters);
+        if (mode == 2)
+            return launch_large2_act(activation, tmX, tmW, p, grid, stream);
+        return launch_large_act<true>(activation, tmX, tmW, p, grid, stream);
     }
     const int tiles = p.m_tiles * p.n_tiles;
     return launch_large_act<false>(activation, tmX, tmW, p, tiles < num_sms() ? tiles : num_sms(), stream);
