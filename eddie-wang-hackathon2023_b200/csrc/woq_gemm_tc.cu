@@ -2006,7 +2006,11 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     int activation, const __half* residual, __half* C, void* workspace, size_t workspace_bytes, cudaStream_t stream,
     const __half* fold_gamma, const float* fold_c1s, const float* fold_c2, float ln_eps)
 {
-    if (fold_gamma == nullptr && workspace != nullptr && woq_large_applies(M, N, K, workspace_bytes))
+    // (a workspace, output or residual that is not aligned for the vector / TMA accesses of the large-M kernel simply keeps
+    // the per-tile kernel)
+    if (fold_gamma == nullptr && workspace != nullptr && woq_large_applies(M, N, K, workspace_bytes)
+        && (reinterpret_cast<uintptr_t>(workspace) & 127) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0
+        && (residual == nullptr || (reinterpret_cast<uintptr_t>(residual) & 15) == 0))
         return woq_gemm_large(A, M, K, W, scales, N, bias, activation, residual, C, workspace, stream);
     const TcPlan pl = plan_tc(M, N, K);
     B200_REQUIRE(pl.slab_bytes == 0 || (workspace != nullptr && workspace_bytes >= pl.slab_bytes), B200_ERR_WORKSPACE,

@@ -127,3 +127,23 @@ def test_small_workspace_falls_back_to_the_tiled_kernel():
     torch.cuda.synchronize()
     assert lib.b200_launch_count() - n0 == 1
     assert torch.equal(a, b)
+
+
+def test_misaligned_workspace_falls_back_to_the_tiled_kernel():
+    """The expanded weights are a TMA source (128-byte aligned box rows): a workspace pointer that is not keeps the per-tile
+    kernel instead of failing."""
+    import b200_whisper as bw
+    from b200_whisper import _lib
+    lib = _lib.load()
+    m, k, n = 4200, 1280, 1280
+    x = gen((m, k), 31).cuda()
+    weight = gen((k, n), 32) * 0.05
+    raw, proc, scales = bw.ops._symmetric_quantize_last_axis_of_batched_matrix(weight.cuda(), torch.int8)
+    big = torch.empty((lib.b200_woq_workspace_bytes(m, n, k) + 256,), dtype=torch.uint8, device="cuda")
+    a, b = (torch.empty((m, n), dtype=torch.float16, device="cuda") for _ in range(2))
+    _fused(lib, x, proc, scales, n, None, _lib.ACT_NONE, None, a, big)
+    n0 = lib.b200_launch_count()
+    _fused(lib, x, proc, scales, n, None, _lib.ACT_NONE, None, b, big[16:])
+    torch.cuda.synchronize()
+    assert lib.b200_launch_count() - n0 == 1
+    assert torch.equal(a, b)
