@@ -432,10 +432,14 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         // descriptor set-up in front of every four MMAs: 2200 of the 5300 cycles a 5-block projection spends after its
         // dependency, tools/tc_timing_insitu.py).  Here every A stage is awaited BEFORE the activation barrier (they complete
         // ahead of the dependency), and once the activations land all 4 nkb MMAs are issued back to back.
-        const bool burst = x_single && nkb <= AS && nkb > 0 && tc_burst_enabled(p);
+        // A CTA with more k-blocks than TMEM A stages (fc2: ten blocks, six stages) bursts the first AS blocks and walks the
+        // recycled stages with the per-block loop.
+        const bool burst = x_single && nkb > 0 && tc_burst_enabled(p);
+        int i0 = 0;
         if (burst)
         {
-            for (int i = 0; i < nkb; ++i)
+            const int nb = nkb < AS ? nkb : AS;
+            for (int i = 0; i < nb; ++i)
                 mbar_wait(&a_ready[i], 0);
             mbar_wait(&xfull[0], 0);
             tc_fence_after();
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
             if (elect_one_sync())
             {
 #pragma unroll 1
-                for (int i = 0; i < nkb; ++i)
+                for (int i = 0; i < nb; ++i)
                 {
                     // stage i: activation tile i (XTileBytes apart: the descriptor's 14-bit start address counts 16-byte
                     // units) against TMEM A stage i
@@ -453,15 +457,18 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
                         tc_mma_ts(d_tmem, tmem_base + i * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
+                    if (i + AS < nkb)
+                        tc_commit(&stage_free[i]); // (i < AS <= SS: stage i) the dequant warps recycle TMEM stage i for block i + AS
                 }
-                tc_commit(acc_done);
+                if (nb == nkb)
+                    tc_commit(acc_done);
             }
             __syncwarp();
             if (lane == 0)
-                TC_STAMP(16 + 4 * (nkb - 1 < 11 ? nkb - 1 : 11) + 3);
+                TC_STAMP(16 + 4 * (nb - 1 < 11 ? nb - 1 : 11) + 3);
+            i0 = nb;
         }
-        else
-        for (int i = 0; i < nkb; ++i)
+        for (int i = i0; i < nkb; ++i)
         {
             const int ss = i % SS, as = i % AS;
             mbar_wait(&a_ready[as], (i / AS) & 1);
