@@ -2079,7 +2079,7 @@ int woq_gemm_tc(const __half* A, int M, int K, const uint8_t* W, const __half* s
     switch (pl.MT)
     {
     case 16: return launch_tc<16, 10, 7>(tmW, tmX, p, grid, stream); // 7 x 32 A columns + 16 accumulator columns = 240 of the 256 a CTA may hold
-    case 32: return launch_tc<32, 7, 6>(tmW, tmX, p, grid, stream);
+    case 32: return launch_tc<32, 7, 7>(tmW, tmX, p, grid, stream); // 7 x 32 + 32 = all 256 columns
     case 64: return launch_tc<64, 6, 6>(tmW, tmX, p, grid, stream);
     case 128: return launch_tc<128, 4, 4>(tmW, tmX, p, grid, stream);
     default: return launch_tc<256, 4, 4>(tmW, tmX, p, grid, stream);
