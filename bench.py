@@ -544,7 +544,7 @@ def main():
     lay0 = dec.layers[0]
     gemm_b = sum(gemm_bytes(lay0[nm]) for nm in ("qkv", "attn_out", "cross_q", "cross_out", "fc1", "fc2")) / 6.0
     gemm_ach = gemm_b / (gemm_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "woq_gemm_tc_kernel<16,10,6,cluster> (6 launches per layer: qkv, attn_out, cross_q, "
+    roofline = {"bound": "hbm", "kernel": "woq_gemm_tc_kernel<16,10,7,cluster> (6 launches per layer: qkv, attn_out, cross_q, "
                 "cross_out, fc1, fc2; LayerNorm folded in 3 of them)", "achieved": gemm_ach, "peak": peak,
                 "unit": "GB/s", "frac": gemm_ach / peak, "traffic": traffic.get("woq_gemm_tc_kernel"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": gemm_b, "avg_launch_ms": gemm_ms,
