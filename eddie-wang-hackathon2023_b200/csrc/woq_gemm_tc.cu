@@ -312,6 +312,12 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     // the whole k range of this CTA fits the ring (always true for decode shapes): all activation tiles complete on
     // ONE barrier, so the MMA loop and the statistics wait once instead of once per k-block
     const bool x_single = nkb <= SS;
+    // "A from shared memory" for the k-blocks beyond the TMEM ring (fc2 at batch <= 16: ten blocks, seven TMEM stages): instead
+    // of recycling TMEM stages AFTER the dependency (wait for the MMAs of block i - AS, then dequantize block i), the dequant
+    // warps write those blocks as fp16 K-major / 128B-swizzled UMMA A tiles over the int8 stages they have already
+    // consumed (two 8 KB stages per 16 KB tile) and the MMA warp issues them in SS form -- all of the CTA's dequantisation
+    // happens ahead of the dependency again.  Needs the tiles to fit into consumed stages: 2 (nkb - AS) <= AS.
+    const bool a_smem = p.mma_burst != 0 && x_single && nkb > AS && 2 * (nkb - AS) <= AS;
     if (warp == kProducerWarp && elect_one_sync())
     {
         tma_prefetch_desc(&tmW);
@@ -438,9 +444,9 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         int i0 = 0;
         if (burst)
         {
-            const int nb = nkb < AS ? nkb : AS;
+            const int nb = (nkb < AS || a_smem) ? nkb : AS;
             for (int i = 0; i < nb; ++i)
-                mbar_wait(&a_ready[i], 0);
+                mbar_wait(&a_ready[i % AS], (i / AS) & 1);
             mbar_wait(&xfull[0], 0);
             tc_fence_after();
             if (lane == 0)
@@ -454,11 +460,22 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                     // stage i: activation tile i (XTileBytes apart: the descriptor's 14-bit start address counts 16-byte
                     // units) against TMEM A stage i
                     const uint64_t bdesc = bdesc0 + (uint64_t) (i * (XTileBytes >> 4));
+                    if (i < AS)
+                    {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        tc_mma_ts(d_tmem, tmem_base + i * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
-                    if (i + AS < nkb)
-                        tc_commit(&stage_free[i]); // (i < AS <= SS: stage i) the dequant warps recycle TMEM stage i for block i + AS
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc_mma_ts(d_tmem, tmem_base + i * 32 + k4 * 8, bdesc + 2 * k4, kIdesc, (i | k4) != 0 ? 1u : 0u);
+                        if (i + AS < nkb && !a_smem)
+                            tc_commit(&stage_free[i]); // (i < AS <= SS: stage i) the dequant warps recycle TMEM stage i for block i + AS
+                    }
+                    else
+                    {
+                        // block i lives in shared memory as a K-major A tile (a_smem): SS form
+                        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smW + (size_t) (i - AS) * 2 * kWTileBytes));
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc_mma_ss(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, kIdesc, 1u);
+                    }
                 }
                 if (nb == nkb)
                     tc_commit(acc_done);
@@ -563,6 +580,24 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                         r[4 * q + w] = *reinterpret_cast<const uint32_t*>(&pr);
                     }
                 }
+            }
+            if (i >= AS && a_smem)
+            {
+                if (i == AS) // every thread has read the int8 tiles of the stages that are overwritten from here on
+                    asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory");
+                // row T of the A tile (128 B = 64 k), this thread's k-half = 16-byte chunks 4 kh .. 4 kh + 3, XOR-swizzled by row
+                uint8_t* arow = smW + (size_t) (i - AS) * 2 * kWTileBytes + T * 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(arow + (((4 * kh + q) ^ (T & 7)) << 4))
+                        = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                if (i + 1 < nkb)
+                    load_w(i + 1);
+                fence_proxy_async_smem(); // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&a_ready[as]);
+                continue;
             }
             if (i >= AS)
             {
