@@ -383,7 +383,12 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     __syncthreads();
     tc_fence_after();
     if (is_cluster)
-        cluster_sync_all(); // every rank's inbox barrier is armed before anybody can push into it
+    {
+        // every rank's inbox barrier is armed before anybody can push into it.  RELAXED arrival: the barrier initialisation
+        // is already published cluster-wide by fence.mbarrier_init.release.cluster; arrive.release would add a full
+        // MEMBAR.ALL.GPU + ERRBAR to every CTA's prologue (seen as such in the SASS and as 1-2 us in "prologue done")
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     grid_dep_launch_dependents(); // PDL: the next kernel may start its own prologue / weight prefetch now
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     if (threadIdx.x == 0)
