@@ -639,7 +639,9 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
         // static operands (weights-side vectors) of the final outputs this thread will write, requested before the
         // accumulator is waited for
         float own_bias = 0.f, own_c1 = 0.f, own_c2 = 0.f;
-        float own_res[4] = {0.f, 0.f, 0.f, 0.f};
+        // raw bits of the residual values, converted where they are used (a half -> float conversion right after the load
+        // made every warp wait for the load BEFORE it pushed its partial sums: 4 % of all warp samples on that one line)
+        unsigned short own_res[4] = {0, 0, 0, 0};
         // cluster mode: this thread reduces elements (ml_first + j*ml_step, own_nn), j = 0, 1, ... -- one fixed column
         // (256 threads are a multiple of the slice width), so bias and the fold vectors are per-thread constants
         const int ns_shift = __ffs(nslice) - 1; // nslice is a power of two
@@ -813,7 +815,8 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (ml_first + j * ml_step < m_valid)
-                    own_res[j] = __half2float(p.residual[(size_t) (m_tile * MT + ml_first + j * ml_step) * p.ldc + own_nn]);
+                    own_res[j] = __ldcg(reinterpret_cast<const unsigned short*>(p.residual)
+                        + (size_t) (m_tile * MT + ml_first + j * ml_step) * p.ldc + own_nn);
         }
         if (tq == 0)
             TC_STAMP(7);
@@ -983,7 +986,7 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (ml_first + j * ml_step < m_valid)
-                        reduce_one(ml_first + j * ml_step, own_res[j]);
+                        reduce_one(ml_first + j * ml_step, __half2float(__ushort_as_half(own_res[j])));
                 for (int ml = ml_first + 4 * ml_step; ml < m_valid; ml += ml_step) // more than 4 rows per thread
                     reduce_one(ml, has_res ? __half2float(p.residual[(size_t) (m_tile * MT + ml) * p.ldc + own_nn]) : 0.f);
             }
