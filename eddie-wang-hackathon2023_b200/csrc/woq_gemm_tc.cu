@@ -372,12 +372,23 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     __half sc = __float2half(0.f);
     if (warp < kTcDequantWarps && n < p.N)
         sc = __ldg(p.scales + n);
+    // gamma never depends on the previous kernel: this split's slice is REQUESTED here and stored to shared memory after
+    // the CTA / cluster barriers below (storing it here put the load's latency into every CTA's prologue)
+    uint4 g_reg = make_uint4(0u, 0u, 0u, 0u);
+    const bool g_one = nkb * 8 <= kDq; // one 16-byte piece per dequant thread at most (always true for decode launches)
     if (fold && warp < kTcDequantWarps)
     {
-        // gamma never depends on the previous kernel: stage this split's slice before the dependency wait
         const uint4* g4 = reinterpret_cast<const uint4*>(p.fold_gamma) + (size_t) kb_begin * 8;
-        for (int idx = threadIdx.x; idx < nkb * 8; idx += kDq)
-            reinterpret_cast<uint4*>(ln_g)[idx] = __ldg(g4 + idx);
+        if (g_one)
+        {
+            if ((int) threadIdx.x < nkb * 8)
+                g_reg = __ldg(g4 + threadIdx.x);
+        }
+        else
+        {
+            for (int idx = threadIdx.x; idx < nkb * 8; idx += kDq)
+                reinterpret_cast<uint4*>(ln_g)[idx] = __ldg(g4 + idx);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -527,6 +538,12 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     {
         // ===== warps 0..7: (LayerNorm of the activation tile,) dequant, then epilogue =====
         const int tq = threadIdx.x; // 0..255
+        if (fold && g_one)
+        {
+            if (tq < nkb * 8)
+                reinterpret_cast<uint4*>(ln_g)[tq] = g_reg;
+            asm volatile("bar.sync 1, %0;" ::"n"(kDq) : "memory"); // gamma staged before any dequant thread multiplies by it
+        }
         const int jl = T >> 1, hf = T & 1, sw = jl & 7;
         const float scf = __half2float(sc); // per-column dequant scale, applied in the epilogue
         const uint32_t lane_field = (uint32_t) ((warp & 3) * 32) << 16;
