@@ -1000,11 +1000,14 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                         sum = ln_fin[2 * ml + 1] * (sum - ln_fin[2 * ml] * own_c1) + own_c2;
                     p.C[idx] = finish_output_rt(sum, has_bias, own_bias, p.activation, has_res, res);
                 };
+                // rows of this thread with a prefetched residual (unrolled copies of the finishing code): 16-row tiles split
+                // four or eight ways have at most two rows per thread, and two copies less is shorter code on the critical path
+                constexpr int kUnrolledRows = MT <= 16 ? 2 : 4;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < kUnrolledRows; ++j)
                     if (ml_first + j * ml_step < m_valid)
                         reduce_one(ml_first + j * ml_step, __half2float(__ushort_as_half(own_res[j])));
-                for (int ml = ml_first + 4 * ml_step; ml < m_valid; ml += ml_step) // more than 4 rows per thread
+                for (int ml = ml_first + kUnrolledRows * ml_step; ml < m_valid; ml += ml_step) // further rows of this thread
                     reduce_one(ml, has_res ? __half2float(p.residual[(size_t) (m_tile * MT + ml) * p.ldc + own_nn]) : 0.f);
             }
             if (tq == 0)
