@@ -175,15 +175,19 @@ __device__ __forceinline__ __half finish_output_tile(float acc, bool has_bias, _
 // Run-time activation: used by the decode-sized cluster reduction, where ONE compact instruction stream matters more than
 // the masked-off instructions (six specialised copies of that epilogue measured 8 % slower on the decoder step:
 // instruction-cache misses on the critical path of a 3 us kernel).
+// (out of line on purpose: the inlined erff / tanhf bodies sat, mostly unexecuted, in every copy of the finishing code)
+__device__ __noinline__ float activation_rt(float x, int activation)
+{
+    return activation == B200_ACT_GELU_ERF ? gelu_erf(x) : gelu_tanh(x);
+}
+
 __device__ __forceinline__ __half finish_output_rt(float acc, bool has_bias, float biasv, int activation, bool has_res, float res)
 {
     __half o = __float2half_rn(acc);
     if (has_bias)
         o = __float2half_rn(__half2float(o) + biasv);
-    if (activation == B200_ACT_GELU_ERF)
-        o = __float2half_rn(gelu_erf(__half2float(o)));
-    else if (activation == B200_ACT_GELU_TANH)
-        o = __float2half_rn(gelu_tanh(__half2float(o)));
+    if (activation != B200_ACT_NONE)
+        o = __float2half_rn(activation_rt(__half2float(o), activation));
     if (has_res)
         o = __float2half_rn(__half2float(o) + res);
     return o;
