@@ -994,12 +994,9 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                     for (uint32_t q = 0; q < 8; ++q)
                         if (q < S)
                             sum += src[(size_t) q * MT * nslice];
-                    if (S > 8) // 16-CTA clusters (opt-in)
-                    {
-#pragma unroll
-                        for (uint32_t q = 8; q < 16; ++q)
-                            sum += src[(size_t) q * MT * nslice];
-                    }
+#pragma unroll 1
+                    for (uint32_t q = 8; q < S; ++q) // 16-CTA clusters (opt-in): rolled, off the usual path
+                        sum += src[(size_t) q * MT * nslice];
                     if (fold)
                         sum = ln_fin[2 * ml + 1] * (sum - ln_fin[2 * ml] * own_c1) + own_c2;
                     p.C[idx] = finish_output_rt(sum, has_bias, own_bias, p.activation, has_res, res);
