@@ -299,8 +299,9 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
-    const int kb_begin = (int) (((long long) split * p.kb_total) / p.splits);
-    const int kb_end = (int) (((long long) (split + 1) * p.kb_total) / p.splits);
+    // (32-bit: split <= 16 and kb_total = K / 64; the 64-bit form cost two calls into the division routine per CTA prologue)
+    const int kb_begin = (int) (((unsigned) split * (unsigned) p.kb_total) / (unsigned) p.splits);
+    const int kb_end = (int) (((unsigned) (split + 1) * (unsigned) p.kb_total) / (unsigned) p.splits);
     const int nkb = kb_end - kb_begin;
     const bool fold = p.fold_gamma != nullptr;
     if (threadIdx.x == 0)
