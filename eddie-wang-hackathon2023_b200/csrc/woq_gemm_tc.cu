@@ -1002,9 +1002,11 @@ __global__ void __launch_bounds__(kTcThreads, MT <= 32 ? 2 : 1)
                         sum = ln_fin[2 * ml + 1] * (sum - ln_fin[2 * ml] * own_c1) + own_c2;
                     p.C[idx] = finish_output_rt(sum, has_bias, own_bias, p.activation, has_res, res);
                 };
-                // rows of this thread with a prefetched residual (unrolled copies of the finishing code): 16-row tiles split
-                // four or eight ways have at most two rows per thread, and two copies less is shorter code on the critical path
-                constexpr int kUnrolledRows = MT <= 16 ? 2 : 4;
+                // rows of this thread that get an unrolled copy of the finishing code (with the prefetched residual): 16-row
+                // tiles split eight ways -- every projection with a residual -- have ONE row per thread, split four ways (qkv,
+                // fc1: no residual) two; every copy less is shorter code on the critical path (four copies 1.198 ms, two
+                // 1.185, one + the rolled loop below 1.168 with the other trims)
+                constexpr int kUnrolledRows = MT <= 16 ? 1 : 4;
 #pragma unroll
                 for (int j = 0; j < kUnrolledRows; ++j)
                     if (ml_first + j * ml_step < m_valid)
