@@ -822,9 +822,14 @@ __device__ __forceinline__ uint32_t xa_mapa(uint32_t local_smem_addr, uint32_t c
     return remote;
 }
 
-template <bool INT8, typename CFG, bool SPLIT = false>
+// CS = 0: whole pairs only.  CS = 2 / 4: launched as clusters of CS CTAs that share ONE pair per cluster by keys -- the pair left
+// over after the whole rounds (CS = 2, many pairs), or, with fewer pairs than SMs / CS (batch 1-3: 20-60 pairs), every pair: the
+// grid then has pairs x CS CTAs instead of one CTA per pair on a mostly idle GPU.
+template <bool INT8, typename CFG, int CS = 0>
 __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead_kernel(const XAttnParams p)
 {
+    constexpr bool SPLIT = CS > 0;
+    constexpr int kRanks = CS > 0 ? CS : 1;
     constexpr int W = CFG::W, ST = CFG::ST;
     constexpr int ESZ = INT8 ? 1 : 2;
     constexpr int CK = INT8 ? CFG::CK : CFG::CK / 2;
@@ -855,13 +860,13 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
     if constexpr (SPLIT)
     {
         lparts = parts + 2 * W * kPart;
-        lbar = reinterpret_cast<uint64_t*>(lparts + 2 * W * kPart);
+        lbar = reinterpret_cast<uint64_t*>(lparts + kRanks * W * kPart);
         crank = xa_cluster_rank();
         const int cand = rounds * (int) gridDim.x + (int) xa_cluster_id();
         if (cand < RH)
         {
             left_bh = cand;
-            const int h0 = (int) crank * p.nch / 2, h1 = ((int) crank + 1) * p.nch / 2;
+            const int h0 = (int) crank * p.nch / kRanks, h1 = ((int) crank + 1) * p.nch / kRanks;
             lc0 = h0 + warp * (h1 - h0) / W;
             n_l = h0 + (warp + 1) * (h1 - h0) / W - lc0;
         }
@@ -875,7 +880,7 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
         if (SPLIT && warp == 0 && left_bh >= 0 && crank == 0)
         {
             mbar_init(lbar, 1);
-            mbar_arrive_expect_tx(lbar, (uint32_t) (W * (kDh + 2) * sizeof(float)));
+            mbar_arrive_expect_tx(lbar, (uint32_t) ((kRanks - 1) * W * (kDh + 2) * sizeof(float)));
         }
         fence_mbar_init();
         fence_proxy_async_smem();
@@ -1021,7 +1026,7 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); // rank 0 has armed its inbox barrier
             if (kl == 0)
             {
-                const uint32_t dst = xa_mapa(smem_u32(lparts + (size_t) (W + warp) * kPart), 0u);
+                const uint32_t dst = xa_mapa(smem_u32(lparts + (size_t) ((int) crank * W + warp) * kPart), 0u);
                 const uint32_t bar = xa_mapa(smem_u32(lbar), 0u);
                 const uint32_t od = dst + (uint32_t) (4 + chunk * 16) * 4u;
 #pragma unroll
@@ -1060,17 +1065,17 @@ __global__ void __launch_bounds__(CFG::W * 32, CFG::OCC) cross_attention_rowhead
         if (warp == r % W)
         {
             const float* pb = (SPLIT && shared) ? lparts : parts + (r & 1) * W * kPart;
-            const int np = (SPLIT && shared) ? 2 * W : W;
+            const int np = (SPLIT && shared) ? kRanks * W : W;
             if (SPLIT && shared)
                 mbar_wait(lbar, 0); // the W partials of rank 1 have landed
             float gm = -FLT_MAX;
 #pragma unroll
-            for (int w2 = 0; w2 < 2 * W; ++w2)
+            for (int w2 = 0; w2 < kRanks * W; ++w2)
                 if (w2 < np)
                     gm = fmaxf(gm, pb[w2 * kPart]);
             float gl = 0.f, a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int w2 = 0; w2 < 2 * W; ++w2)
+            for (int w2 = 0; w2 < kRanks * W; ++w2)
             {
                 if (w2 < np)
                 {
@@ -1583,7 +1588,16 @@ struct XaPlan
 };
 
 static long long* g_xa_dbg = nullptr; // b200_debug_xa_timeline
-static int g_xa_split = -1;           // b200_set_cross_attention_split / env B200_XA_SPLIT (default off)
+// b200_set_cross_attention_split / env B200_XA_SPLIT: bit 0 = left-over pairs shared inside 2-CTA clusters, bit 1 = with few
+// pairs (batch 1-3) every pair shared by a cluster of 4 / 2 CTAs.  Both default OFF: each shortens the kernel and lengthens the
+// step (batch 16: 1.322 vs 1.293 ms with bit 0; batch 1: 0.991 vs 0.932 ms with bit 1) -- CTAs that own whole SMs, launched
+// as clusters, start later and leave later, and the next GEMM's prologue pays for it (profiles/r02_xattn_timeline.txt)
+static int g_xa_split = -1;
+static int xa_split_default()
+{
+    const char* e = getenv("B200_XA_SPLIT");
+    return e != nullptr ? (atoi(e) & 3) : 0;
+}
 static int g_xa_cfg = -1;  // env B200_XA_CFG = A .. F
 static int g_xa_mode = -1; // env B200_XA_MODE = split | rowhead | auto (default)
 
@@ -1624,16 +1638,20 @@ static XaPlan xattn_plan(int R, int H, int S, int int8)
         // step gets 0.9 us per layer SLOWER -- the CTAs that used to leave after two pairs are where the next GEMM starts
         // its weight stream and dequant ahead of its dependency (tools/xa_timeline.py)
         if (g_xa_split < 0)
-        {
-            const char* e = getenv("B200_XA_SPLIT");
-            g_xa_split = (e != nullptr && e[0] == '1') ? 1 : 0;
-        }
+            g_xa_split = xa_split_default();
         const int left = R * H - (R * H / pl.blocks) * pl.blocks;
-        if (g_xa_split == 1 && kOCC[g_xa_cfg] == 1 && pl.blocks % 2 == 0 && R * H >= pl.blocks && left > 0 && 2 * left <= pl.blocks
+        if ((g_xa_split & 1) && kOCC[g_xa_cfg] == 1 && pl.blocks % 2 == 0 && R * H >= pl.blocks && left > 0 && 2 * left <= pl.blocks
             && pl.nch >= 2)
         {
-            pl.split = 1;
+            pl.split = 2;
             pl.smem += sizeof(float) * 2 * W * (kDh + 4) + 16;
+        }
+        // few pairs (batch 1-3): every pair shared by a cluster of 4 (or 2) CTAs -- pairs x CS CTAs instead of one CTA per pair
+        else if ((g_xa_split & 2) && kOCC[g_xa_cfg] == 1 && 2 * R * H <= slots && pl.nch >= 4)
+        {
+            pl.split = (4 * R * H <= slots && pl.nch >= 8) ? 4 : 2;
+            pl.blocks = R * H * pl.split;
+            pl.smem += sizeof(float) * pl.split * W * (kDh + 4) + 16;
         }
         return pl;
     }
@@ -1666,16 +1684,16 @@ static int xattn_launch(const XAttnParams& p, const XaPlan& pl, cudaStream_t st)
     return B200_OK;
 }
 
-template <bool INT8, typename CFG>
+template <bool INT8, typename CFG, int CS>
 static int xattn_launch_rowhead_split(const XAttnParams& p, const XaPlan& pl, cudaStream_t st)
 {
-    auto kern = cross_attention_rowhead_kernel<INT8, CFG, true>;
-    static bool attr_set = false;
-    if (!attr_set)
+    auto kern = cross_attention_rowhead_kernel<INT8, CFG, CS>;
+    static size_t attr_smem = 0;
+    if (pl.smem > attr_smem)
     {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl.smem));
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
+        attr_smem = pl.smem;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pl.blocks);
@@ -1691,7 +1709,7 @@ static int xattn_launch_rowhead_split(const XAttnParams& p, const XaPlan& pl, cu
         ++na;
     }
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.x = CS;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
@@ -1708,7 +1726,8 @@ static int xattn_launch_rowhead(const XAttnParams& p, const XaPlan& pl, cudaStre
     if (pl.split)
     {
         if constexpr (CFG::OCC == 1)
-            return xattn_launch_rowhead_split<INT8, CFG>(p, pl, st);
+            return pl.split == 4 ? xattn_launch_rowhead_split<INT8, CFG, 4>(p, pl, st)
+                                 : xattn_launch_rowhead_split<INT8, CFG, 2>(p, pl, st);
     }
     static bool attr_set = false;
     if (!attr_set)
@@ -1890,12 +1909,9 @@ extern "C" int b200_cross_attention_qproj(const void* x, const void* ln_gamma, c
 extern "C" int b200_set_cross_attention_split(int enabled)
 {
     if (g_xa_split < 0)
-    {
-        const char* e = getenv("B200_XA_SPLIT");
-        g_xa_split = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
+        g_xa_split = xa_split_default();
     const int prev = g_xa_split;
-    g_xa_split = enabled ? 1 : 0;
+    g_xa_split = enabled & 3;
     return prev;
 }
 

@@ -254,11 +254,13 @@ int b200_cross_attention_qproj_supported(int batch_size, int num_heads, int head
 int b200_cross_attention_qproj(const void* x, const void* ln_gamma, const float* c1s, const float* c2, float ln_eps,
     const int8_t* Wproc, const void* scales, const void* bias, const void* cross_kv, const float* kv_scale_quant_orig,
     void* out, int batch_size, int num_heads, int head_size, int kv_len, b200_stream_t stream);
-/* Tuning switch of b200_cross_attention (process-wide; set it before launches are captured in a graph; returns the
- * previous value).  1: when the (row, head) pairs do not fill whole rounds of the grid (320 pairs on 148 CTAs leave 24),
- * the kernel runs as clusters of two CTAs that share one left-over pair each, split by keys and merged through
- * distributed shared memory, instead of dealing those pairs whole to the first CTAs.  Same results up to the order of
- * the softmax merge.  Default 0 (env B200_XA_SPLIT=1): measured faster as a kernel and slower in the decoder step. */
+/* Tuning switch of b200_cross_attention (process-wide bit mask; set it before launches are captured in a graph; returns
+ * the previous value).  Bit 0: when the (row, head) pairs do not fill whole rounds of the grid (320 pairs on 148 CTAs leave
+ * 24), the kernel runs as clusters of two CTAs that share one left-over pair each, split by keys and merged through
+ * distributed shared memory, instead of dealing those pairs whole to the first CTAs (default off: measured faster as a
+ * kernel and slower in the decoder step).  Bit 1: with fewer pairs than half the SMs (batch 1-3) EVERY pair is shared by a
+ * cluster of 4 or 2 CTAs instead of one CTA per pair (default off as well: 0.991 vs 0.932 ms per batch-1 step).  Same
+ * results up to the order of the softmax merge.  Default 0; env B200_XA_SPLIT=<mask>. */
 int b200_set_cross_attention_split(int enabled);
 /* Debug aid (library built with B200_XA_DEBUG=1; a no-op otherwise): device buffer of >= 8 int64 per SM receiving
  * %globaltimer stamps of every CTA of the following whole-pair cross-attention launches (entry, dependency return,

@@ -121,13 +121,15 @@ def test_context_then_generation(int8, in_len):
                                    (10, 16, 700), (40, 4, 100), (9, 20, 1), (16, 20, 130), (38, 4, 333), (8, 20, 1500),
                                    (37, 4, 1500), (16, 20, 65)])
 @pytest.mark.parametrize("int8", [True, False])
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("split", [0, 3])
 def test_cross_attention(B, H, S, int8, split):
+    """split = 3: both cluster-sharing modes on (bit 0: the pairs left over after whole rounds of the grid are shared by the two
+    CTAs of a cluster; bit 1: with fewer pairs than half the SMs EVERY pair is shared by a cluster of 2 or 4 CTAs); 0: off."""
     import b200_whisper
     from b200_whisper.functional import cross_attention, cross_kv_pack
-    if split and not (B * H >= 148 and S > 64):
-        pytest.skip("the cluster-split variant only differs when pairs are left over after whole rounds of the grid")
-    prev = b200_whisper.load().b200_set_cross_attention_split(1 if split else 0)
+    if split and not ((B * H >= 148 and S > 64) or (2 * B * H <= 148 and S > 192)):
+        pytest.skip("neither sharing mode applies to this shape")
+    prev = b200_whisper.load().b200_set_cross_attention_split(split)
     try:
         _cross_attention_case(B, H, S, int8)
     finally:
@@ -169,9 +171,10 @@ def test_cross_attention_multi_query_rows():
     _multi_query_rows(3, 4, 200, 4)
     _multi_query_rows(6, 8, 130, 5)  # 240 (row, head) pairs: one-CTA-per-pair kernel
     import b200_whisper
-    prev = b200_whisper.load().b200_set_cross_attention_split(1)
+    prev = b200_whisper.load().b200_set_cross_attention_split(3)
     try:
         _multi_query_rows(3, 10, 200, 5)  # 150 pairs: two of them shared by the CTAs of a cluster
+        _multi_query_rows(2, 4, 1500, 3)  # 24 pairs: every pair shared by a cluster of four CTAs
     finally:
         b200_whisper.load().b200_set_cross_attention_split(prev)
 
